@@ -1,0 +1,494 @@
+"""CPU oracle for the fit -> weight -> barycentre hot path.  TEST INFRASTRUCTURE ONLY.
+
+This module is a NumPy/SciPy fp64 *restatement* of the arithmetic the reference
+(mattramos/bayesian_ensembling, mounted read-only at /root/reference) performs
+on its hot path.  It is the checker for the CUDA path.  Only ``tests/``,
+``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` / ``--impl
+reference`` legs may import it; nothing under ``bayesian_ensembling_b200/``
+does (tests/test_no_oracle_in_product.py enforces that).
+
+Parity pinning status
+---------------------
+* ``mvn_scale_tri`` (a3) is PINNED by the reference's own pickled fits
+  (``experiments/pre_fit_models/*.pkl``: ``_scale_tri`` vs ``covariance``,
+  18 members, <= 2e-14) -- see tests/golden/ and tests/test_oracle_golden.py.
+* ``gp_posterior_closed_form`` / ``vgp_*`` (a1, a2) are pinned only
+  *structurally* by those pickles (fitted covariance minus diag(var) is
+  reproduced by the closed form to ~1e-6 abs after a 2-parameter fit): the
+  arithmetic itself lives in GPflow 2.1.5 / TensorFlow 2.8.1, neither of which
+  is vendored in the reference nor installable here (no network).  The VGP
+  functions below restate GPflow's published algorithm
+  (gpflow/models/vgp.py, gpflow/conditionals/util.py, gpflow/kernels/
+  stationaries.py, gpflow/kullback_leiblers.py, gpflow/optimizers/natgrad.py,
+  TF-Keras Adam) and are cross-checked against each other
+  (natgrad fixed point == closed form; analytic gradient == finite differences).
+* weights (a4), barycentre (a5/a6), sqrtm / W2 (a7/a8): the reference's tests
+  pin no values (tests/test_weights.py:99-101 checks shape and sum only), and
+  distrax/JAX cannot run here => **parity unpinned** beyond the line-by-line
+  restatement cited in each docstring.
+* ``fullcov_barycentre`` (a9, BASELINE config 5) has no reference code at all;
+  the oracle DEFINES it (see docstring) => parity unpinned.
+
+Every function cites the reference file:line it follows.
+"""
+from __future__ import annotations
+
+import math
+import warnings
+
+import numpy as np
+import scipy.linalg as sla
+
+LOG_2PI = math.log(2.0 * math.pi)
+DEFAULT_JITTER = 1e-6  # gpflow.config.default_jitter()
+SQRT3 = math.sqrt(3.0)
+
+
+# --------------------------------------------------------------------------------------
+# a1: kernel
+# --------------------------------------------------------------------------------------
+def scaled_square_distance(X: np.ndarray, lengthscale: float) -> np.ndarray:
+    """GPflow ``IsotropicStationary.scaled_squared_euclid_dist`` + ``square_distance``:
+    ``Xs = X/l``; ``r2 = -2 Xs Xs^T + |Xs|^2[:,None] + |Xs|^2[None,:]``.
+    Used by ``gpf.kernels.Matern32()`` built at ensembles/models.py:186 on
+    ``X = realisation_set.T`` (models.py:182)."""
+    Xs = X / lengthscale
+    sq = np.sum(Xs * Xs, axis=-1)
+    return -2.0 * (Xs @ Xs.T) + sq[:, None] + sq[None, :]
+
+
+def matern32_gram(X: np.ndarray, variance: float, lengthscale: float) -> np.ndarray:
+    """``K_ij = s2 (1 + sqrt3 r) exp(-sqrt3 r)``, ``r = sqrt(max(r2, 1e-36))``
+    (GPflow ``Matern32.K_r`` with ``IsotropicStationary.K`` clamping).  models.py:186."""
+    r2 = scaled_square_distance(X, lengthscale)
+    r = np.sqrt(np.maximum(r2, 1e-36))
+    return variance * (1.0 + SQRT3 * r) * np.exp(-SQRT3 * r)
+
+
+def matern32_gram_grads(X, variance, lengthscale):
+    """(K, dK/dvariance, dK/dlengthscale) -- derivatives used by the analytic
+    hyper-parameter gradient (TensorFlow obtains them by autodiff, models.py:210)."""
+    r2 = scaled_square_distance(X, lengthscale)
+    r = np.sqrt(np.maximum(r2, 1e-36))
+    e = np.exp(-SQRT3 * r)
+    K = variance * (1.0 + SQRT3 * r) * e
+    dK_dvar = (1.0 + SQRT3 * r) * e
+    # dK/dr = -3 s2 r e ; dr/dl = -r/l  (r clamped: derivative of max() is 0 below the clamp)
+    dr_dl = np.where(r2 > 1e-36, -r / lengthscale, 0.0)
+    dK_dl = (-3.0 * variance * r * e) * dr_dl
+    return K, dK_dvar, dK_dl
+
+
+# --------------------------------------------------------------------------------------
+# a2: likelihood
+# --------------------------------------------------------------------------------------
+def hetero_variational_expectations(Fmu, Fvar, y, noise_var):
+    """``_HeteroskedasticGaussian._variational_expectations``, models.py:142-149."""
+    return -0.5 * LOG_2PI - 0.5 * np.log(noise_var) - 0.5 * ((y - Fmu) ** 2 + Fvar) / noise_var
+
+
+def gpdtw1d_inputs(realisation_set: np.ndarray, y_mean: np.ndarray | None = None):
+    """Inputs ``GPDTW1D.fit`` hands to GPflow (models.py:175-182).
+
+    ``y_mean`` is the DTW-barycentre-averaging mean in the reference
+    (models.py:176-178, tslearn, unseeded => not reproducible); the
+    oracle takes it as an input and defaults to the arithmetic mean over
+    realisations (tslearn's DBA initialiser).  ``y_var`` is the population
+    variance (ddof=0), models.py:179.  ``X = realisation_set.T``, models.py:182."""
+    realisation_set = np.asarray(realisation_set, dtype=np.float64)
+    if y_mean is None:
+        y_mean = realisation_set.mean(axis=0)
+    y_var = np.var(realisation_set, axis=0)
+    X = realisation_set.T.copy()
+    return X, np.asarray(y_mean, dtype=np.float64).ravel(), y_var
+
+
+# --------------------------------------------------------------------------------------
+# a1: L1 -- fixed-hyper-parameter posterior (the natural-gradient fixed point)
+# --------------------------------------------------------------------------------------
+def gp_posterior_closed_form(X, y_mean, y_var, variance, lengthscale, jitter=DEFAULT_JITTER):
+    """Posterior ``GPDTW1D.fit`` converges to for fixed kernel hyper-parameters.
+
+    For the Gaussian likelihood the natural-gradient fixed point of the whitened
+    VGP (models.py:187-215) is the exact heteroskedastic GP regression posterior
+    with ``K + jitter*I`` as the prior covariance inside the solves; ``predict_f``
+    (models.py:217) then gives ``mean = K (K+D+jI)^-1 y`` and
+    ``cov = K - K (K+D+jI)^-1 K``; models.py:220 adds ``diag(y_var)``.
+    Computed the textbook way (Cholesky, triangular solve, A^T A)."""
+    K = matern32_gram(X, variance, lengthscale)
+    T = K.shape[0]
+    M = K + np.diag(y_var) + jitter * np.eye(T)
+    C = np.linalg.cholesky(M)
+    A = sla.solve_triangular(C, K, lower=True)
+    u = sla.solve_triangular(C, y_mean, lower=True)
+    mean = A.T @ u
+    cov = K - A.T @ A + np.diag(y_var)
+    return mean, cov
+
+
+# --------------------------------------------------------------------------------------
+# a1: L2 -- the VGP the reference actually trains (GPflow 2.1.5 semantics)
+# --------------------------------------------------------------------------------------
+def softplus(u):
+    return np.logaddexp(0.0, u)
+
+
+def softplus_inv(x):
+    return x + np.log(-np.expm1(-x))
+
+
+def vgp_elbo(X, y_mean, y_var, variance, lengthscale, q_mu, q_sqrt, jitter=DEFAULT_JITTER):
+    """``gpflow.models.VGP.elbo`` for the model built at models.py:185-189
+    (whitened, one latent GP, zero mean function)."""
+    T = X.shape[0]
+    K = matern32_gram(X, variance, lengthscale) + jitter * np.eye(T)
+    L = np.linalg.cholesky(K)
+    fmean = L @ q_mu
+    LTA = L @ np.tril(q_sqrt)
+    fvar = np.sum(LTA * LTA, axis=1)
+    var_exp = hetero_variational_expectations(fmean, fvar, y_mean, y_var)
+    # gpflow.kullback_leiblers.gauss_kl, whitened (K=None)
+    d = np.diag(q_sqrt)
+    kl = 0.5 * (np.sum(q_mu * q_mu) + np.sum(np.tril(q_sqrt) ** 2) - T - np.sum(np.log(d * d)))
+    return float(np.sum(var_exp) - kl)
+
+
+def _inverse_lower_triangular(M):
+    """gpflow.optimizers.natgrad._inverse_lower_triangular."""
+    return sla.solve_triangular(M, np.eye(M.shape[0]), lower=True)
+
+
+def meanvarsqrt_to_natural(mu, s_sqrt):
+    """gpflow.optimizers.natgrad.meanvarsqrt_to_natural."""
+    s_sqrt_inv = _inverse_lower_triangular(s_sqrt)
+    s_inv = s_sqrt_inv.T @ s_sqrt_inv
+    return s_inv @ mu, -0.5 * s_inv
+
+
+def natural_to_meanvarsqrt(nat1, nat2):
+    """gpflow.optimizers.natgrad.natural_to_meanvarsqrt."""
+    var_sqrt_inv = np.linalg.cholesky(-2.0 * nat2)
+    var_sqrt = _inverse_lower_triangular(var_sqrt_inv)
+    S = var_sqrt.T @ var_sqrt
+    mu = S @ nat1
+    return mu, np.linalg.cholesky(S)
+
+
+def vgp_natgrad_step(L, y_mean, y_var, q_mu, q_sqrt, gamma=0.5):
+    """One ``NaturalGradient(gamma).minimize(loss, [(q_mu, q_sqrt)])`` step
+    (models.py:191,209) with the default XiNat parameterisation.
+
+    ``nat <- nat - gamma * dLoss/d eta``; for this model
+    ``dLoss/d eta = nat - nat*`` exactly, with ``nat1* = L^T D^-1 y`` and
+    ``nat2* = -1/2 (I + L^T D^-1 L)`` (derivation in DESIGN.md), ``L`` the
+    Cholesky factor of ``K + jitter I`` at the CURRENT hyper-parameters."""
+    nat1, nat2 = meanvarsqrt_to_natural(q_mu, q_sqrt)
+    T = L.shape[0]
+    Lw = L / y_var[:, None]  # D^-1 L
+    nat1_star = Lw.T @ y_mean
+    nat2_star = -0.5 * (np.eye(T) + L.T @ Lw)
+    nat1 = nat1 - gamma * (nat1 - nat1_star)
+    nat2 = nat2 - gamma * (nat2 - nat2_star)
+    nat2 = 0.5 * (nat2 + nat2.T)
+    return natural_to_meanvarsqrt(nat1, nat2)
+
+
+def _chol_backprop(L, Lbar):
+    """Reverse-mode derivative of ``L = chol(K)``: returns ``Kbar`` (symmetric)
+    with ``<Kbar, dK> = <Lbar, dL>`` for symmetric ``dK`` (Murray 2016, eq. 10)."""
+    P = np.tril(L.T @ np.tril(Lbar))
+    P[np.diag_indices_from(P)] *= 0.5
+    # S = L^-T P L^-1
+    S = sla.solve_triangular(L, P, lower=True, trans="T")
+    S = sla.solve_triangular(L, S.T, lower=True, trans="T").T
+    return 0.5 * (S + S.T)
+
+
+def vgp_hyper_grad(X, y_mean, y_var, variance, lengthscale, q_mu, q_sqrt, jitter=DEFAULT_JITTER):
+    """Gradient of ``training_loss = -ELBO`` w.r.t. the UNCONSTRAINED (softplus)
+    kernel variance and lengthscale -- what ``adam.minimize(loss,
+    gp_model.trainable_variables)`` differentiates at models.py:210 (q_mu and
+    q_sqrt are frozen at models.py:194-195).  Analytic; checked against finite
+    differences of ``vgp_elbo`` in tests/test_oracle.py."""
+    T = X.shape[0]
+    K, dK_dvar, dK_dl = matern32_gram_grads(X, variance, lengthscale)
+    L = np.linalg.cholesky(K + jitter * np.eye(T))
+    Ls = np.tril(q_sqrt)
+    fmean = L @ q_mu
+    LS = L @ (Ls @ Ls.T)
+    r = (y_mean - fmean) / y_var
+    Lbar = np.outer(r, q_mu) - LS / y_var[:, None]  # d ELBO / d L
+    Kbar = _chol_backprop(L, Lbar)
+    g_var = np.sum(Kbar * dK_dvar)
+    g_ls = np.sum(Kbar * dK_dl)
+    # chain through softplus: d softplus(u)/du = sigmoid(u) = 1 - exp(-x)
+    g_u_var = -g_var * (-np.expm1(-variance))
+    g_u_ls = -g_ls * (-np.expm1(-lengthscale))
+    return np.array([g_u_var, g_u_ls])
+
+
+class _Adam:
+    """tf.optimizers.Adam(0.01) of TF 2.8 (Keras OptimizerV2): beta1=0.9,
+    beta2=0.999, eps=1e-7, ``lr_t = lr sqrt(1-b2^t)/(1-b1^t)``,
+    ``x -= lr_t m/(sqrt(v)+eps)``.  models.py:192."""
+
+    def __init__(self, n, lr=0.01, b1=0.9, b2=0.999, eps=1e-7):
+        self.lr, self.b1, self.b2, self.eps = lr, b1, b2, eps
+        self.m = np.zeros(n)
+        self.v = np.zeros(n)
+        self.t = 0
+
+    def step(self, x, g):
+        self.t += 1
+        self.m = self.b1 * self.m + (1 - self.b1) * g
+        self.v = self.b2 * self.v + (1 - self.b2) * g * g
+        lr_t = self.lr * math.sqrt(1 - self.b2**self.t) / (1 - self.b1**self.t)
+        return x - lr_t * self.m / (np.sqrt(self.v) + self.eps)
+
+
+def vgp_predict_full_cov(X, variance, lengthscale, q_mu, q_sqrt, jitter=DEFAULT_JITTER):
+    """``gp_model.predict_f(X, full_cov=True)`` at the training inputs
+    (models.py:217): gpflow ``base_conditional`` with ``white=True``."""
+    T = X.shape[0]
+    K = matern32_gram(X, variance, lengthscale)
+    Lm = np.linalg.cholesky(K + jitter * np.eye(T))
+    A = sla.solve_triangular(Lm, K, lower=True)
+    fvar = K - A.T @ A
+    fmean = A.T @ q_mu
+    LTA = np.tril(q_sqrt).T @ A
+    fvar = fvar + LTA.T @ LTA
+    return fmean, fvar
+
+
+def gpdtw1d_fit(
+    realisation_set,
+    n_optim_nits=500,
+    y_mean=None,
+    gamma=0.5,
+    lr=0.01,
+    init_variance=1.0,
+    init_lengthscale=1.0,
+    train_hypers=True,
+    jitter=DEFAULT_JITTER,
+    return_state=False,
+):
+    """``GPDTW1D.fit`` below the DBA step (models.py:179-220): returns
+    ``(mu [T], cov [T,T])`` exactly as handed to ``Distribution`` at
+    models.py:224-229.  ``train_hypers=False`` freezes the kernel (L1 studies)."""
+    X, y, s = gpdtw1d_inputs(realisation_set, y_mean)
+    T = X.shape[0]
+    q_mu = np.zeros(T)
+    q_sqrt = np.eye(T)
+    u = np.array([softplus_inv(init_variance), softplus_inv(init_lengthscale)])
+    adam = _Adam(2, lr=lr)
+    for _ in range(n_optim_nits):
+        var, ls = softplus(u[0]), softplus(u[1])
+        K = matern32_gram(X, var, ls)
+        L = np.linalg.cholesky(K + jitter * np.eye(T))
+        q_mu, q_sqrt = vgp_natgrad_step(L, y, s, q_mu, q_sqrt, gamma)  # models.py:209
+        if train_hypers:
+            g = vgp_hyper_grad(X, y, s, var, ls, q_mu, q_sqrt, jitter)  # models.py:210
+            u = adam.step(u, g)
+    var, ls = softplus(u[0]), softplus(u[1])
+    mu, cov = vgp_predict_full_cov(X, var, ls, q_mu, q_sqrt, jitter)  # models.py:217
+    cov = cov + np.diag(s)  # models.py:220
+    if return_state:
+        return mu, cov, dict(variance=var, lengthscale=ls, q_mu=q_mu, q_sqrt=q_sqrt)
+    return mu, cov
+
+
+# --------------------------------------------------------------------------------------
+# a3: the distrax distributions the reference builds (data.py:38-39)
+# --------------------------------------------------------------------------------------
+def mvn_scale_tri(cov):
+    """distrax ``MultivariateNormalFullCovariance.__init__``: ``jnp.linalg.cholesky(cov)``
+    (built at models.py:224-229 through data.py:38-39)."""
+    return np.linalg.cholesky(cov)
+
+
+def mvn_log_prob(mu, scale_tri, x):
+    """distrax ``MultivariateNormalTri.log_prob``: event dim = last axis, ``x``
+    broadcasts against ``mu``:  ``-1/2 |L^-1 (x-mu)|^2 - T/2 log 2pi - sum log|diag L|``."""
+    mu = np.asarray(mu)
+    T = mu.shape[-1]
+    x = np.asarray(x, dtype=np.float64)
+    xb = np.broadcast_to(x, np.broadcast_shapes(x.shape, mu.shape))
+    diff = (xb - mu).reshape(-1, T).T  # [T, N]
+    z = sla.solve_triangular(scale_tri, diff, lower=True)
+    maha = np.sum(z * z, axis=0)
+    logdet = np.sum(np.log(np.abs(np.diag(scale_tri))))
+    return (-0.5 * maha - 0.5 * T * LOG_2PI - logdet).reshape(xb.shape[:-1])
+
+
+def normal_log_prob(loc, scale, x):
+    """distrax ``Normal(loc, scale).log_prob`` (2nd positional arg is a SCALE: quirk Q-SCALE)."""
+    z = (np.asarray(x) - loc) / scale
+    return -0.5 * z * z - 0.5 * LOG_2PI - np.log(scale)
+
+
+def mvn_diag_log_prob(loc, scale_diag, x):
+    """distrax ``MultivariateNormalDiag(loc, scale_diag).log_prob`` (event = last axis)."""
+    return np.sum(normal_log_prob(loc, scale_diag, x), axis=-1)
+
+
+# --------------------------------------------------------------------------------------
+# a4: log-likelihood weights
+# --------------------------------------------------------------------------------------
+def loglik_weights_mvn(mus, scale_tris, obs, standardisation_constant=1.0):
+    """``LogLikelihoodWeight._compute`` for full-covariance members (weights.py:87-123).
+
+    mus ``[M,T]``, scale_tris ``[M,T,T]``, obs ``[R_o,T]``.
+    weights.py:98-100 calls ``log_prob(expand_dims(obs_real.ravel(), -1))``: the
+    ``[T,1]`` input broadcasts to ``[T,T]`` so entry i is the density of the
+    CONSTANT vector ``o_i * 1_T`` (quirk Q-LL).  Mean over obs realisations
+    (:103-104), ``exp(c * .)`` with no max-subtraction (:107, Q-EXP), plain
+    normalisation by the sum over models (:122-123; 0/0 -> NaN is kept).
+    Returns ``(weights [M,T], lls_exp [M,T], lls_mean [M,T])``."""
+    M = len(mus)
+    lls_mean = []
+    for m in range(M):
+        lls = [mvn_log_prob(mus[m], scale_tris[m], o.ravel()[:, None]) for o in obs]
+        lls_mean.append(np.mean(np.asarray(lls), axis=0))
+    lls_mean = np.asarray(lls_mean)
+    with np.errstate(over="ignore", under="ignore", invalid="ignore", divide="ignore"):
+        model_lls = np.exp(standardisation_constant * lls_mean)
+        weights = model_lls / model_lls.sum(axis=0)
+    return weights, model_lls, lls_mean
+
+
+def loglik_weights_normal(locs, scales, obs, standardisation_constant=1.0):
+    """Same for ``dx.Normal`` members (weights.py:95-96): elementwise log-pdf."""
+    lls_mean = np.asarray(
+        [np.mean([normal_log_prob(l, s, o.ravel()) for o in obs], axis=0) for l, s in zip(locs, scales)]
+    )
+    with np.errstate(over="ignore", under="ignore", invalid="ignore", divide="ignore"):
+        model_lls = np.exp(standardisation_constant * lls_mean)
+        weights = model_lls / model_lls.sum(axis=0)
+    return weights, model_lls, lls_mean
+
+
+# --------------------------------------------------------------------------------------
+# a5 / a6: barycentre
+# --------------------------------------------------------------------------------------
+def gaussian_barycentre(means, std_devs, weights, tolerance=1e-6, init_var=1.0):
+    """Line-by-line restatement of ``ensembles/wasserstein.py:61-100`` (quirk Q-BARY:
+    SIGNED stopping test at :88).  Returns ``(mu, sigma, n_iters)``."""
+    barycentre_variance = init_var
+    n_iters = 0
+    while True:
+        candidate_variance = 0.0
+        for w, s in zip(weights, std_devs):
+            candidate_variance += w * np.sqrt(barycentre_variance) * s
+        if candidate_variance - barycentre_variance < tolerance:
+            barycentre_variance = candidate_variance
+            break
+        else:
+            barycentre_variance = candidate_variance
+        n_iters += 1
+        if n_iters > 200:
+            warnings.warn("Barycentre not converged for 1 time step")
+            break
+    mu = np.sum(np.asarray(weights) * np.asarray(means))
+    sigma = np.sqrt(barycentre_variance)
+    return mu, sigma, n_iters
+
+
+def barycentre_points(means, variances, weights, tolerance=1e-6, init_var=1.0):
+    """``Barycentre._compute`` (ensemble_scheme.py:43-81): per point t gather
+    ``mean[t]``, ``sqrt(variance[t])`` of every member (:63-67), the weights
+    column (:68) and call a5 (:69).  Inputs ``[M, Npts]``.  Returns
+    ``(bary_mu [Npts], bary_std [Npts], n_iters [Npts])``; the reference then
+    builds ``Distribution(mu, covariance=bary_std**2, MultivariateNormalDiag)``
+    (:75-78), whose ``.variance`` is ``bary_std**4`` (quirk Q-SCALE)."""
+    means = np.asarray(means, dtype=np.float64)
+    M, N = means.shape
+    stds = np.sqrt(np.asarray(variances, dtype=np.float64))
+    mu = np.empty(N)
+    sd = np.empty(N)
+    it = np.empty(N, dtype=np.int64)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for t in range(N):
+            mu[t], sd[t], it[t] = gaussian_barycentre(means[:, t], stds[:, t], weights[:, t], tolerance, init_var)
+    return mu, sd, it
+
+
+# --------------------------------------------------------------------------------------
+# a7 / a8: matrix square root and the W2 "distance"
+# --------------------------------------------------------------------------------------
+def sqrtm_svd(A):
+    """``ensembles/wasserstein.py:10-13``: ``U diag(sqrt(s)) V^H`` from an SVD."""
+    u, s, vh = np.linalg.svd(A)
+    return u @ np.diag(np.sqrt(s)) @ vh
+
+
+def gaussian_w2_distance(mu1, sigma1, mu2, sigma2):
+    """``gaussian_w2_distance_distrax`` (wasserstein.py:21-47).  The location term
+    is the UN-squared 2-norm (:40,45; quirk Q-W2).  ``sigma*`` are full matrices
+    (``full_cov=False`` callers pass ``diag(variance)``, :38-39)."""
+    location_gap = np.linalg.norm(mu1 - mu2, ord=2)
+    s1h = sqrtm_svd(sigma1)
+    covariance_gap = sigma1 + sigma2 - 2.0 * sqrtm_svd(s1h @ sigma2 @ s1h)
+    return location_gap + np.trace(covariance_gap)
+
+
+# --------------------------------------------------------------------------------------
+# a9: full-covariance barycentre (BASELINE config 5) -- DEFINED here, no reference code
+# --------------------------------------------------------------------------------------
+def fullcov_barycentre(mus, sigmas, weights, tolerance=1e-6, init_var=1.0, max_iters=200):
+    """Matrix generalisation of wasserstein.py:61-100 with wasserstein.py:10-13 as
+    the square root: ``S0 = init_var I``; ``S <- sum_m w_m (S^1/2 Sigma_m S^1/2)^1/2``.
+    The signed scalar stop rule (:88) has no unique matrix analogue; the oracle
+    DEFINES it on the mean diagonal: stop when ``tr(S_new - S)/T < tolerance``
+    (signed), which reduces EXACTLY to a5 when T == 1.  ``mu = sum_m w_m mu_m`` (:98).
+    Returns ``(mu [T], S [T,T], n_iters)``."""
+    sigmas = [np.asarray(s, dtype=np.float64) for s in sigmas]
+    T = sigmas[0].shape[0]
+    S = init_var * np.eye(T)
+    n_iters = 0
+    while True:
+        Sh = sqrtm_svd(S)
+        cand = np.zeros((T, T))
+        for w, Sig in zip(weights, sigmas):
+            cand += w * sqrtm_svd(Sh @ Sig @ Sh)
+        done = (np.trace(cand) - np.trace(S)) / T < tolerance
+        S = cand
+        if done:
+            break
+        n_iters += 1
+        if n_iters > max_iters:
+            break
+    mu = np.sum(np.asarray(weights)[:, None] * np.asarray(mus), axis=0)
+    return mu, S, n_iters
+
+
+# --------------------------------------------------------------------------------------
+# the whole path for one grid cell (what bench.py's cpu_baseline times)
+# --------------------------------------------------------------------------------------
+def cell_pipeline_L1(realisations, obs, variance, lengthscale, y_means=None, jitter=DEFAULT_JITTER,
+                     time_mean_weights=False):
+    """fit (fixed hyper-parameters) -> LogLikelihoodWeight -> Barycentre for one
+    cell: realisations ``[M,R,T]``, obs ``[R_o,T]``; ``variance``/``lengthscale``
+    scalars or ``[M]``.  Order of operations follows ``PerfectModelTest._run_single_test``
+    (utils.py:102-135); ``time_mean_weights`` reproduces utils.py:111,133.
+    Returns dict with mu [M,T], cov [M,T,T], scale_tri, weights [M,T], bary_mu [T], bary_std [T]."""
+    realisations = np.asarray(realisations, dtype=np.float64)
+    M, R, T = realisations.shape
+    variance = np.broadcast_to(np.asarray(variance, dtype=np.float64), (M,))
+    lengthscale = np.broadcast_to(np.asarray(lengthscale, dtype=np.float64), (M,))
+    mus, covs, tris = [], [], []
+    for m in range(M):
+        X, y, s = gpdtw1d_inputs(realisations[m], None if y_means is None else y_means[m])
+        mu, cov = gp_posterior_closed_form(X, y, s, variance[m], lengthscale[m], jitter)
+        mus.append(mu)
+        covs.append(cov)
+        tris.append(mvn_scale_tri(cov))
+    mus, covs, tris = np.asarray(mus), np.asarray(covs), np.asarray(tris)
+    weights, lls_exp, lls_mean = loglik_weights_mvn(mus, tris, obs)
+    w_used = weights
+    if time_mean_weights:
+        w_used = np.broadcast_to(np.nanmean(weights, axis=1)[:, None], weights.shape)
+    variances = np.asarray([np.diag(c) for c in covs])
+    bmu, bsd, bit = barycentre_points(mus, variances, w_used)
+    return dict(mu=mus, cov=covs, scale_tri=tris, weights=weights, lls_mean=lls_mean,
+                bary_mu=bmu, bary_std=bsd, bary_iters=bit)

@@ -1,0 +1,272 @@
+"""Device-side operator layer: torch tensors in, torch tensors out, arithmetic in the C ABI.
+
+PyTorch is plumbing only here (device memory, the current CUDA stream, dtype/contiguity
+checks).  Every numerical operation is a call into ``libbe_b200.so``.
+"""
+from __future__ import annotations
+
+import ctypes
+from dataclasses import dataclass
+
+import torch
+
+from . import _lib
+
+DEFAULT_JITTER = 1e-6  # gpflow.config.default_jitter()
+
+
+def _ptr(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+@dataclass
+class PosteriorBatch:
+    """Result of ``Backend.gp_posterior`` for B = cells * members problems (all on device)."""
+
+    mu: torch.Tensor  # [B,T]
+    var_diag: torch.Tensor  # [B,T]
+    mvn_stats: torch.Tensor  # [B,4]
+    info_fit: torch.Tensor  # [B] int32
+    info_dist: torch.Tensor  # [B] int32
+    cov: torch.Tensor | None = None  # [B,T,T]
+    scale_tri: torch.Tensor | None = None  # [B,T,T]
+
+
+class Backend:
+    """One per (process, device).  Calls are ordered on torch's current stream."""
+
+    _instances: dict = {}
+
+    @classmethod
+    def get(cls, device=None) -> "Backend":
+        if not torch.cuda.is_available():
+            raise _lib.BackendError(
+                "bayesian_ensembling_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback."
+            )
+        dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        if dev.index is None:
+            dev = torch.device("cuda", torch.cuda.current_device())
+        if dev.index not in cls._instances:
+            cls._instances[dev.index] = cls(dev)
+        return cls._instances[dev.index]
+
+    def __init__(self, device: torch.device):
+        self.lib = _lib.load_library()
+        self.device = device
+        self._workspace = None
+        handle = ctypes.c_void_p()
+        with torch.cuda.device(device):
+            stream = torch.cuda.current_stream(device).cuda_stream
+            rc = self.lib.be_ctx_create(device.index, ctypes.c_void_p(stream), ctypes.byref(handle))
+        if rc != 0:
+            raise _lib.BackendError(f"be_ctx_create failed ({rc})")
+        self.ctx = handle
+
+    # ------------------------------------------------------------------ plumbing
+    def _sync_stream(self):
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        self.lib.be_ctx_set_stream(self.ctx, ctypes.c_void_p(stream))
+
+    def _ws(self, nbytes: int) -> torch.Tensor:
+        if self._workspace is None or self._workspace.numel() < nbytes:
+            self._workspace = None
+            self._workspace = torch.empty(int(nbytes), dtype=torch.uint8, device=self.device)
+        return self._workspace
+
+    def _in(self, t, shape=None, name="tensor"):
+        if not isinstance(t, torch.Tensor):
+            t = torch.as_tensor(t, dtype=torch.float64)
+        if t.dtype != torch.float64:
+            t = t.to(torch.float64)
+        if t.device != self.device:
+            t = t.to(self.device)
+        t = t.contiguous()
+        if shape is not None and tuple(t.shape) != tuple(shape):
+            raise ValueError(f"{name}: expected shape {tuple(shape)}, got {tuple(t.shape)}")
+        return t
+
+    def _new(self, *shape, dtype=torch.float64):
+        return torch.empty(*shape, dtype=dtype, device=self.device)
+
+    def sync(self):
+        _lib.check(self.ctx, self.lib.be_ctx_sync(self.ctx), "be_ctx_sync")
+
+    @property
+    def launch_count(self) -> int:
+        return int(self.lib.be_ctx_launch_count(self.ctx))
+
+    def posterior_workspace_bytes(self, B, T, R) -> int:
+        return int(self.lib.be_gp_posterior_workspace_bytes(B, T, R))
+
+    # ------------------------------------------------------------------ a1
+    def gpdtw1d_inputs(self, realisations):
+        """[B,R,T] -> X [B,T,R], y_mean [B,T], y_var [B,T]   (models.py:175-182)"""
+        r = self._in(realisations)
+        B, R, T = r.shape
+        X, ym, yv = self._new(B, T, R), self._new(B, T), self._new(B, T)
+        self._sync_stream()
+        rc = self.lib.be_gpdtw1d_inputs(self.ctx, _ptr(r), B, R, T, _ptr(X), _ptr(ym), _ptr(yv))
+        _lib.check(self.ctx, rc, "be_gpdtw1d_inputs")
+        return X, ym, yv
+
+    def matern32_gram(self, X, variance, lengthscale):
+        X = self._in(X)
+        B, T, R = X.shape
+        var = self._in(variance, (B,), "variance")
+        ls = self._in(lengthscale, (B,), "lengthscale")
+        K = self._new(B, T, T)
+        self._sync_stream()
+        rc = self.lib.be_matern32_gram(self.ctx, _ptr(X), B, T, R, _ptr(var), _ptr(ls), _ptr(K))
+        _lib.check(self.ctx, rc, "be_matern32_gram")
+        return K
+
+    def potrf(self, A):
+        A = self._in(A)
+        B, T, _ = A.shape
+        L = self._new(B, T, T)
+        info = self._new(B, dtype=torch.int32)
+        nbytes = int(self.lib.be_potrf_workspace_bytes(B, T))
+        ws = self._ws(nbytes)
+        self._sync_stream()
+        rc = self.lib.be_potrf_batched(self.ctx, _ptr(A), B, T, _ptr(L), _ptr(info), _ptr(ws), nbytes)
+        _lib.check(self.ctx, rc, "be_potrf_batched")
+        return L, info
+
+    def gp_posterior(self, X, y_mean, y_var, variance, lengthscale, jitter=DEFAULT_JITTER,
+                     want_cov=True, want_scale_tri=True) -> PosteriorBatch:
+        X = self._in(X)
+        B, T, R = X.shape
+        ym = self._in(y_mean, (B, T), "y_mean")
+        yv = self._in(y_var, (B, T), "y_var")
+        var = self._in(variance, (B,), "variance")
+        ls = self._in(lengthscale, (B,), "lengthscale")
+        out = PosteriorBatch(
+            mu=self._new(B, T), var_diag=self._new(B, T), mvn_stats=self._new(B, 4),
+            info_fit=self._new(B, dtype=torch.int32), info_dist=self._new(B, dtype=torch.int32),
+            cov=self._new(B, T, T) if want_cov else None,
+            scale_tri=self._new(B, T, T) if want_scale_tri else None,
+        )
+        nbytes = self.posterior_workspace_bytes(B, T, R)
+        ws = self._ws(nbytes)
+        self._sync_stream()
+        rc = self.lib.be_gp_posterior(
+            self.ctx, _ptr(X), _ptr(ym), _ptr(yv), _ptr(var), _ptr(ls), float(jitter), B, T, R,
+            _ptr(out.mu), _ptr(out.var_diag), _ptr(out.cov), _ptr(out.scale_tri), _ptr(out.mvn_stats),
+            _ptr(out.info_fit), _ptr(out.info_dist), _ptr(ws), nbytes)
+        _lib.check(self.ctx, rc, "be_gp_posterior")
+        return out
+
+    # ------------------------------------------------------------------ a3
+    def mvn_from_cov(self, mu, cov, want_scale_tri=True):
+        cov = self._in(cov)
+        B, T, _ = cov.shape
+        mu = self._in(mu, (B, T), "mu")
+        tri = self._new(B, T, T) if want_scale_tri else None
+        var_diag, stats = self._new(B, T), self._new(B, 4)
+        info = self._new(B, dtype=torch.int32)
+        nbytes = int(self.lib.be_mvn_from_cov_workspace_bytes(B, T))
+        ws = self._ws(nbytes)
+        self._sync_stream()
+        rc = self.lib.be_mvn_from_cov(self.ctx, _ptr(mu), _ptr(cov), B, T, _ptr(tri), _ptr(var_diag), _ptr(stats),
+                                      _ptr(info), _ptr(ws), nbytes)
+        _lib.check(self.ctx, rc, "be_mvn_from_cov")
+        return tri, var_diag, stats, info
+
+    # ------------------------------------------------------------------ a4
+    def loglik_weights_mvn(self, mvn_stats, obs, M, standardisation_constant=1.0, want_lls=False):
+        """mvn_stats [C*M,4], obs [C,Ro,T] -> weights [C,M,T] (+ lls_exp, lls_mean)"""
+        obs = self._in(obs)
+        C, Ro, T = obs.shape
+        st = self._in(mvn_stats, (C * M, 4), "mvn_stats")
+        w = self._new(C, M, T)
+        le = self._new(C, M, T) if want_lls else None
+        lm = self._new(C, M, T) if want_lls else None
+        self._sync_stream()
+        rc = self.lib.be_loglik_weights_mvn(self.ctx, _ptr(st), _ptr(obs), C, M, Ro, T,
+                                            float(standardisation_constant), _ptr(w), _ptr(le), _ptr(lm))
+        _lib.check(self.ctx, rc, "be_loglik_weights_mvn")
+        return (w, le, lm) if want_lls else w
+
+    def mvn_constvec_logprob(self, mvn_stats, obs, M):
+        obs = self._in(obs)
+        C, Ro, T = obs.shape
+        st = self._in(mvn_stats, (C * M, 4), "mvn_stats")
+        ll = self._new(C, M, Ro, T)
+        self._sync_stream()
+        rc = self.lib.be_mvn_constvec_logprob(self.ctx, _ptr(st), _ptr(obs), C, M, Ro, T, _ptr(ll))
+        _lib.check(self.ctx, rc, "be_mvn_constvec_logprob")
+        return ll
+
+    def normal_logprob(self, loc, scale, x):
+        x = self._in(x)
+        loc = self._in(loc).expand_as(x).contiguous()
+        scale = self._in(scale).expand_as(x).contiguous()
+        ll = torch.empty_like(x)
+        self._sync_stream()
+        rc = self.lib.be_normal_logprob(self.ctx, _ptr(loc), _ptr(scale), _ptr(x), x.numel(), _ptr(ll))
+        _lib.check(self.ctx, rc, "be_normal_logprob")
+        return ll
+
+    def loglik_weights_normal(self, loc, scale, obs, standardisation_constant=1.0, want_lls=False):
+        """loc/scale [C,M,N], obs [C,Ro,N] -> weights [C,M,N]"""
+        loc = self._in(loc)
+        C, M, N = loc.shape
+        scale = self._in(scale, (C, M, N), "scale")
+        obs = self._in(obs)
+        Ro = obs.shape[1]
+        w = self._new(C, M, N)
+        le = self._new(C, M, N) if want_lls else None
+        lm = self._new(C, M, N) if want_lls else None
+        self._sync_stream()
+        rc = self.lib.be_loglik_weights_normal(self.ctx, _ptr(loc), _ptr(scale), _ptr(obs), C, M, Ro, N,
+                                               float(standardisation_constant), _ptr(w), _ptr(le), _ptr(lm))
+        _lib.check(self.ctx, rc, "be_loglik_weights_normal")
+        return (w, le, lm) if want_lls else w
+
+    def weights_time_mean(self, weights):
+        w = self._in(weights)
+        C, M, T = w.shape
+        out = torch.empty_like(w)
+        self._sync_stream()
+        rc = self.lib.be_weights_time_mean(self.ctx, _ptr(w), C, M, T, _ptr(out))
+        _lib.check(self.ctx, rc, "be_weights_time_mean")
+        return out
+
+    # ------------------------------------------------------------------ a5 / a6
+    def barycentre_1d(self, means, variances, weights, tolerance=1e-6, init_var=1.0, max_iters=200):
+        """[C,M,N] x3 -> mu [C,N], sigma [C,N], iters [C,N] (int32)"""
+        means = self._in(means)
+        C, M, N = means.shape
+        variances = self._in(variances, (C, M, N), "variances")
+        weights = self._in(weights, (C, M, N), "weights")
+        mu, sigma = self._new(C, N), self._new(C, N)
+        iters = self._new(C, N, dtype=torch.int32)
+        self._sync_stream()
+        rc = self.lib.be_barycentre_1d(self.ctx, _ptr(means), _ptr(variances), _ptr(weights), C, M, N,
+                                       float(tolerance), float(init_var), int(max_iters), _ptr(mu), _ptr(sigma),
+                                       _ptr(iters))
+        _lib.check(self.ctx, rc, "be_barycentre_1d")
+        return mu, sigma, iters
+
+    def barycentre_1d_partial(self, means, variances, lls_exp):
+        means = self._in(means)
+        C, M, N = means.shape
+        variances = self._in(variances, (C, M, N), "variances")
+        lls_exp = self._in(lls_exp, (C, M, N), "lls_exp")
+        partial = self._new(3, C, N)
+        self._sync_stream()
+        rc = self.lib.be_barycentre_1d_partial(self.ctx, _ptr(means), _ptr(variances), _ptr(lls_exp), C, M, N,
+                                               _ptr(partial))
+        _lib.check(self.ctx, rc, "be_barycentre_1d_partial")
+        return partial
+
+    def barycentre_1d_finish(self, partial, tolerance=1e-6, init_var=1.0, max_iters=200):
+        partial = self._in(partial)
+        _, C, N = partial.shape
+        mu, sigma = self._new(C, N), self._new(C, N)
+        iters = self._new(C, N, dtype=torch.int32)
+        self._sync_stream()
+        rc = self.lib.be_barycentre_1d_finish(self.ctx, _ptr(partial), C, N, float(tolerance), float(init_var),
+                                              int(max_iters), _ptr(mu), _ptr(sigma), _ptr(iters))
+        _lib.check(self.ctx, rc, "be_barycentre_1d_finish")
+        return mu, sigma, iters

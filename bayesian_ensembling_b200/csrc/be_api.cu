@@ -1,0 +1,447 @@
+// C ABI of the B200 hot path (see include/be_b200.h).  Host-side orchestration only: every
+// arithmetic operation is a kernel from be_kernels.cuh.  There is no CPU fallback.
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include "../../include/be_b200.h"
+#include "be_kernels.cuh"
+
+using namespace be;
+
+struct be_ctx {
+    int device;
+    cudaStream_t stream;
+    int sm_count;
+    long long launches;
+    char err[256];
+};
+
+namespace {
+
+inline int cuda_fail(be_ctx* ctx, cudaError_t e, const char* what) {
+    snprintf(ctx->err, sizeof(ctx->err), "%s: %s", what, cudaGetErrorString(e));
+    return BE_ERR_CUDA;
+}
+
+#define BE_CUDA(call)                                              \
+    do {                                                           \
+        cudaError_t e__ = (call);                                  \
+        if (e__ != cudaSuccess) return cuda_fail(ctx, e__, #call); \
+    } while (0)
+
+#define BE_LAUNCHED()                                                   \
+    do {                                                                \
+        ctx->launches++;                                                \
+        cudaError_t e__ = cudaGetLastError();                           \
+        if (e__ != cudaSuccess) return cuda_fail(ctx, e__, "launch");   \
+    } while (0)
+
+inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+struct Carver {
+    char* base;
+    size_t off, cap;
+    Carver(void* p, size_t bytes) : base((char*)p), off(0), cap(bytes) {}
+    template <typename T>
+    T* take(size_t n) {
+        size_t bytes = align_up(n * sizeof(T), 256);
+        if (off + bytes > cap) return nullptr;
+        T* r = (T*)(base + off);
+        off += bytes;
+        return r;
+    }
+};
+
+inline unsigned grid1d(size_t n, int block) { return (unsigned)((n + block - 1) / block); }
+
+bool g_attr_done = false;
+int ensure_kernel_attrs(be_ctx* ctx) {
+    if (g_attr_done) return BE_OK;
+    BE_CUDA(cudaFuncSetAttribute(k_syrk_trailing, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
+    BE_CUDA(cudaFuncSetAttribute(k_panel_scale, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
+    BE_CUDA(cudaFuncSetAttribute(k_trtri_accum, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
+    BE_CUDA(cudaFuncSetAttribute(k_lauum_cov, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
+    BE_CUDA(cudaFuncSetAttribute(k_diag_block, cudaFuncAttributeMaxDynamicSharedMemorySize, DIAG_SMEM_BYTES));
+    BE_CUDA(cudaFuncSetAttribute(k_matern32<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    BE_CUDA(cudaFuncSetAttribute(k_matern32<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    g_attr_done = true;
+    return BE_OK;
+}
+
+inline size_t matern_smem(int R) { return ((size_t)2 * NB * (R | 1) + 2 * NB) * sizeof(double); }
+
+// Blocked right-looking Cholesky of B padded matrices, in place (lower).  Never pivots on
+// columns >= T; rows >= T ride along (file header of be_kernels.cuh).  Fills Dinv with the
+// inverted diagonal blocks and, if V != nullptr, the diagonal tiles of V = C^-T.
+int potrf_padded(be_ctx* ctx, double* Mat, int Tp, int T, int B, double* Dinv, double* V, int* info) {
+    const int ld = Tp, nblk = num_blocks(Tp);
+    for (int kb = 0; kb < nblk; ++kb) {
+        k_diag_block<<<B, 256, DIAG_SMEM_BYTES, ctx->stream>>>(Mat, ld, Tp, T, kb, Dinv, nblk, V, info);
+        BE_LAUNCHED();
+        int t = nblk - kb - 1;
+        if (t > 0) {
+            k_panel_scale<<<(unsigned)((size_t)t * B), GEMM_THREADS, GEMM_SMEM_BYTES, ctx->stream>>>(
+                Mat, ld, Tp, kb + 1, kb, Dinv, nblk, 1.0, B);
+            BE_LAUNCHED();
+            k_syrk_trailing<<<(unsigned)((size_t)t * (t + 1) / 2 * B), GEMM_THREADS, GEMM_SMEM_BYTES, ctx->stream>>>(
+                Mat, ld, Tp, kb, B);
+            BE_LAUNCHED();
+        }
+    }
+    return BE_OK;
+}
+
+// V = C^-T (upper, row-major); diagonal tiles already written by potrf_padded.
+int trtri_padded(be_ctx* ctx, double* V, const double* Cm, int Tp, int B, const double* Dinv) {
+    const int ld = Tp, nblk = num_blocks(Tp);
+    for (int i = 1; i < nblk; ++i) {
+        k_trtri_accum<<<(unsigned)((size_t)i * B), GEMM_THREADS, GEMM_SMEM_BYTES, ctx->stream>>>(V, Cm, ld, Tp, i, B);
+        BE_LAUNCHED();
+        k_panel_scale<<<(unsigned)((size_t)i * B), GEMM_THREADS, GEMM_SMEM_BYTES, ctx->stream>>>(V, ld, Tp, 0, i, Dinv,
+                                                                                               nblk, -1.0, B);
+        BE_LAUNCHED();
+    }
+    return BE_OK;
+}
+
+size_t padded_matrix_doubles(int B, int T) {
+    size_t Tp = pad_dim(T);
+    return (size_t)B * Tp * Tp;
+}
+size_t dinv_doubles(int B, int T) { return (size_t)B * num_blocks(pad_dim(T)) * NB * NB; }
+
+}  // namespace
+
+extern "C" {
+
+int be_version(void) { return 100; }
+
+int be_ctx_create(int device, void* stream, be_ctx** out) {
+    if (!out) return -3;
+    be_ctx* ctx = new (std::nothrow) be_ctx();
+    if (!ctx) return BE_ERR_CUDA;
+    ctx->device = device;
+    ctx->stream = (cudaStream_t)stream;
+    ctx->launches = 0;
+    ctx->err[0] = 0;
+    cudaError_t e = cudaSetDevice(device);
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
+    if (e != cudaSuccess) {
+        delete ctx;
+        return BE_ERR_CUDA;
+    }
+    int rc = ensure_kernel_attrs(ctx);
+    if (rc != BE_OK) {
+        fprintf(stderr, "be_ctx_create: %s\n", ctx->err);
+        delete ctx;
+        return rc;
+    }
+    *out = ctx;
+    return BE_OK;
+}
+
+int be_ctx_set_stream(be_ctx* ctx, void* stream) {
+    if (!ctx) return -1;
+    ctx->stream = (cudaStream_t)stream;
+    return BE_OK;
+}
+
+int be_ctx_destroy(be_ctx* ctx) {
+    delete ctx;
+    return BE_OK;
+}
+
+int be_ctx_sync(be_ctx* ctx) {
+    if (!ctx) return -1;
+    BE_CUDA(cudaStreamSynchronize(ctx->stream));
+    return BE_OK;
+}
+
+const char* be_ctx_last_error(be_ctx* ctx) { return ctx ? ctx->err : "null ctx"; }
+long long be_ctx_launch_count(be_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int be_gpdtw1d_inputs(be_ctx* ctx, const double* realisations, int B, int R, int T, double* X, double* y_mean,
+                      double* y_var) {
+    if (!ctx) return -1;
+    if (!realisations) return -2;
+    if (B <= 0) return -3;
+    if (R <= 0) return -4;
+    if (T <= 0) return -5;
+    k_gpdtw1d_inputs<<<grid1d((size_t)B * T, 256), 256, 0, ctx->stream>>>(realisations, B, R, T, X, y_mean, y_var);
+    BE_LAUNCHED();
+    return BE_OK;
+}
+
+int be_matern32_gram(be_ctx* ctx, const double* X, int B, int T, int R, const double* variance,
+                     const double* lengthscale, double* K) {
+    if (!ctx) return -1;
+    if (!X) return -2;
+    if (B <= 0) return -3;
+    if (T <= 0) return -4;
+    if (R <= 0 || matern_smem(R) > 200 * 1024) return -5;
+    if (!variance) return -6;
+    if (!lengthscale) return -7;
+    if (!K) return -8;
+    int nt = (T + NB - 1) / NB;
+    k_matern32<0><<<(unsigned)((size_t)nt * nt * B), 256, matern_smem(R), ctx->stream>>>(
+        X, B, T, R, variance, lengthscale, nullptr, nullptr, 0.0, K, 0, 0, nt * nt);
+    BE_LAUNCHED();
+    return BE_OK;
+}
+
+size_t be_potrf_workspace_bytes(int B, int T) {
+    return align_up(padded_matrix_doubles(B, T) * 8, 256) + align_up(dinv_doubles(B, T) * 8, 256) + 1024;
+}
+
+int be_potrf_batched(be_ctx* ctx, const double* A, int B, int T, double* L, int* info, void* workspace,
+                     size_t workspace_bytes) {
+    if (!ctx) return -1;
+    if (!A) return -2;
+    if (B <= 0) return -3;
+    if (T <= 0) return -4;
+    if (!L) return -5;
+    if (!info) return -6;
+    if (!workspace || workspace_bytes < be_potrf_workspace_bytes(B, T)) return BE_ERR_WORKSPACE;
+    const int Tp = pad_dim(T);
+    Carver cv(workspace, workspace_bytes);
+    double* W = cv.take<double>(padded_matrix_doubles(B, T));
+    double* Dinv = cv.take<double>(dinv_doubles(B, T));
+    if (!W || !Dinv) return BE_ERR_WORKSPACE;
+    BE_CUDA(cudaMemsetAsync(info, 0, sizeof(int) * B, ctx->stream));
+    k_pad_from_dense<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(A, nullptr, B, T, Tp, Tp, W, 0);
+    BE_LAUNCHED();
+    int rc = potrf_padded(ctx, W, Tp, T, B, Dinv, nullptr, info);
+    if (rc != BE_OK) return rc;
+    k_copy_out_tri<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(W, Tp, Tp, T, L, B);
+    BE_LAUNCHED();
+    return BE_OK;
+}
+
+size_t be_gp_posterior_workspace_bytes(int B, int T, int R) {
+    (void)R;
+    size_t Tp = pad_dim(T);
+    return 2 * align_up(padded_matrix_doubles(B, T) * 8, 256) + align_up(dinv_doubles(B, T) * 8, 256) +
+           align_up((size_t)B * Tp * 8, 256) + 1024;
+}
+
+int be_gp_posterior(be_ctx* ctx, const double* X, const double* y_mean, const double* y_var, const double* variance,
+                    const double* lengthscale, double jitter, int B, int T, int R, double* mu, double* var_diag,
+                    double* cov, double* scale_tri, double* mvn_stats, int* info_fit, int* info_dist, void* workspace,
+                    size_t workspace_bytes) {
+    if (!ctx) return -1;
+    if (!X) return -2;
+    if (!y_mean) return -3;
+    if (!y_var) return -4;
+    if (!variance) return -5;
+    if (!lengthscale) return -6;
+    if (!(jitter >= 0.0)) return -7;
+    if (B <= 0) return -8;
+    if (T <= 0) return -9;
+    if (R <= 0 || matern_smem(R) > 200 * 1024) return -10;
+    if (!mu) return -11;
+    if (!var_diag) return -12;
+    if (!mvn_stats) return -15;
+    if (!info_fit) return -16;
+    if (!info_dist) return -17;
+    if (!workspace || workspace_bytes < be_gp_posterior_workspace_bytes(B, T, R)) return BE_ERR_WORKSPACE;
+    const int Tp = pad_dim(T), ld = Tp, nblk = num_blocks(Tp);
+    Carver cv(workspace, workspace_bytes);
+    double* Mw = cv.take<double>(padded_matrix_doubles(B, T));  // M -> C -> cov -> scale_tri
+    double* Vw = cv.take<double>(padded_matrix_doubles(B, T));  // V = C^-T
+    double* Dinv = cv.take<double>(dinv_doubles(B, T));
+    double* u = cv.take<double>((size_t)B * Tp);
+    if (!Mw || !Vw || !Dinv || !u) return BE_ERR_WORKSPACE;
+    BE_CUDA(cudaMemsetAsync(info_fit, 0, sizeof(int) * B, ctx->stream));
+    BE_CUDA(cudaMemsetAsync(info_dist, 0, sizeof(int) * B, ctx->stream));
+
+    // 1. M = K + D + jitter I (lower tiles), row T = y_mean
+    const int ntl = nblk * (nblk + 1) / 2;
+    k_matern32<1><<<(unsigned)((size_t)ntl * B), 256, matern_smem(R), ctx->stream>>>(
+        X, B, T, R, variance, lengthscale, y_mean, y_var, jitter, Mw, Tp, ld, ntl);
+    BE_LAUNCHED();
+    // 2. C = chol(M); row T becomes u = C^-1 y; V diagonal tiles
+    int rc = potrf_padded(ctx, Mw, Tp, T, B, Dinv, Vw, info_fit);
+    if (rc != BE_OK) return rc;
+    k_extract_row<<<grid1d((size_t)B * T, 256), 256, 0, ctx->stream>>>(Mw, ld, Tp, T, T, u, B, 1);
+    BE_LAUNCHED();
+    // 3. V = C^-T
+    rc = trtri_padded(ctx, Vw, Mw, Tp, B, Dinv);
+    if (rc != BE_OK) return rc;
+    // 4. mean = y - E V u
+    k_posterior_mean<<<grid1d((size_t)B * T, 8), 256, 0, ctx->stream>>>(Vw, ld, Tp, T, u, y_mean, y_var, jitter, mu,
+                                                                        B);
+    BE_LAUNCHED();
+    // 5. cov = D + E - E (V V^T) E  -> Mw (padded, rows T/T+1 = 1, mu), var_diag, dense cov
+    k_lauum_cov<<<(unsigned)((size_t)ntl * B), GEMM_THREADS, GEMM_SMEM_BYTES, ctx->stream>>>(
+        Vw, ld, Tp, T, y_var, jitter, mu, Mw, var_diag, cov, B);
+    BE_LAUNCHED();
+    // 6. scale_tri = chol(cov) (data.py:38-39); rows T/T+1 become a = L^-1 1, b = L^-1 mu
+    rc = potrf_padded(ctx, Mw, Tp, T, B, Dinv, nullptr, info_dist);
+    if (rc != BE_OK) return rc;
+    k_mvn_stats<<<B, 256, 0, ctx->stream>>>(Mw, ld, Tp, T, mvn_stats);
+    BE_LAUNCHED();
+    if (scale_tri) {
+        k_copy_out_tri<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(Mw, ld, Tp, T, scale_tri, B);
+        BE_LAUNCHED();
+    }
+    return BE_OK;
+}
+
+size_t be_mvn_from_cov_workspace_bytes(int B, int T) { return be_potrf_workspace_bytes(B, T); }
+
+int be_mvn_from_cov(be_ctx* ctx, const double* mu, const double* cov, int B, int T, double* scale_tri,
+                    double* var_diag, double* mvn_stats, int* info, void* workspace, size_t workspace_bytes) {
+    if (!ctx) return -1;
+    if (!mu) return -2;
+    if (!cov) return -3;
+    if (B <= 0) return -4;
+    if (T <= 0) return -5;
+    if (!mvn_stats) return -8;
+    if (!info) return -9;
+    if (!workspace || workspace_bytes < be_mvn_from_cov_workspace_bytes(B, T)) return BE_ERR_WORKSPACE;
+    const int Tp = pad_dim(T);
+    Carver cv(workspace, workspace_bytes);
+    double* W = cv.take<double>(padded_matrix_doubles(B, T));
+    double* Dinv = cv.take<double>(dinv_doubles(B, T));
+    if (!W || !Dinv) return BE_ERR_WORKSPACE;
+    BE_CUDA(cudaMemsetAsync(info, 0, sizeof(int) * B, ctx->stream));
+    k_pad_from_dense<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(cov, mu, B, T, Tp, Tp, W, 1);
+    BE_LAUNCHED();
+    if (var_diag) {
+        k_diag_from_dense<<<grid1d((size_t)B * T, 256), 256, 0, ctx->stream>>>(cov, B, T, var_diag);
+        BE_LAUNCHED();
+    }
+    int rc = potrf_padded(ctx, W, Tp, T, B, Dinv, nullptr, info);
+    if (rc != BE_OK) return rc;
+    k_mvn_stats<<<B, 256, 0, ctx->stream>>>(W, Tp, Tp, T, mvn_stats);
+    BE_LAUNCHED();
+    if (scale_tri) {
+        k_copy_out_tri<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(W, Tp, Tp, T, scale_tri, B);
+        BE_LAUNCHED();
+    }
+    return BE_OK;
+}
+
+int be_loglik_weights_mvn(be_ctx* ctx, const double* mvn_stats, const double* obs, int C, int M, int Ro, int T,
+                          double standardisation_constant, double* weights, double* lls_exp, double* lls_mean) {
+    if (!ctx) return -1;
+    if (!mvn_stats) return -2;
+    if (!obs) return -3;
+    if (C <= 0) return -4;
+    if (M <= 0) return -5;
+    if (Ro <= 0) return -6;
+    if (T <= 0) return -7;
+    if (!weights) return -9;
+    k_loglik_weights_mvn<<<grid1d((size_t)C * T, 128), 128, 0, ctx->stream>>>(
+        mvn_stats, obs, C, M, Ro, T, standardisation_constant, weights, lls_exp, lls_mean);
+    BE_LAUNCHED();
+    return BE_OK;
+}
+
+int be_mvn_constvec_logprob(be_ctx* ctx, const double* mvn_stats, const double* obs, int C, int M, int Ro, int T,
+                            double* ll) {
+    if (!ctx) return -1;
+    if (!mvn_stats) return -2;
+    if (!obs) return -3;
+    if (C <= 0) return -4;
+    if (M <= 0) return -5;
+    if (Ro <= 0) return -6;
+    if (T <= 0) return -7;
+    if (!ll) return -8;
+    k_mvn_constvec_logprob<<<grid1d((size_t)C * M * Ro * T, 256), 256, 0, ctx->stream>>>(mvn_stats, obs, C, M, Ro, T,
+                                                                                         ll);
+    BE_LAUNCHED();
+    return BE_OK;
+}
+
+int be_normal_logprob(be_ctx* ctx, const double* loc, const double* scale, const double* x, size_t n, double* ll) {
+    if (!ctx) return -1;
+    if (!loc) return -2;
+    if (!scale) return -3;
+    if (!x) return -4;
+    if (n == 0) return -5;
+    if (!ll) return -6;
+    k_normal_logprob<<<grid1d(n, 256), 256, 0, ctx->stream>>>(loc, scale, x, n, ll);
+    BE_LAUNCHED();
+    return BE_OK;
+}
+
+int be_loglik_weights_normal(be_ctx* ctx, const double* loc, const double* scale, const double* obs, int C, int M,
+                             int Ro, int N, double standardisation_constant, double* weights, double* lls_exp,
+                             double* lls_mean) {
+    if (!ctx) return -1;
+    if (!loc) return -2;
+    if (!scale) return -3;
+    if (!obs) return -4;
+    if (C <= 0) return -5;
+    if (M <= 0) return -6;
+    if (Ro <= 0) return -7;
+    if (N <= 0) return -8;
+    if (!weights) return -10;
+    k_loglik_weights_normal<<<grid1d((size_t)C * N, 128), 128, 0, ctx->stream>>>(
+        loc, scale, obs, C, M, Ro, N, standardisation_constant, weights, lls_exp, lls_mean);
+    BE_LAUNCHED();
+    return BE_OK;
+}
+
+int be_weights_time_mean(be_ctx* ctx, const double* weights, int C, int M, int T, double* w_bar) {
+    if (!ctx) return -1;
+    if (!weights) return -2;
+    if (C <= 0) return -3;
+    if (M <= 0) return -4;
+    if (T <= 0) return -5;
+    if (!w_bar) return -6;
+    k_weights_time_mean<<<(unsigned)((size_t)C * M), 256, 0, ctx->stream>>>(weights, C * M, T, w_bar);
+    BE_LAUNCHED();
+    return BE_OK;
+}
+
+int be_barycentre_1d(be_ctx* ctx, const double* means, const double* variances, const double* weights, int C, int M,
+                     int N, double tolerance, double init_var, int max_iters, double* mu, double* sigma, int* iters) {
+    if (!ctx) return -1;
+    if (!means) return -2;
+    if (!variances) return -3;
+    if (!weights) return -4;
+    if (C <= 0) return -5;
+    if (M <= 0) return -6;
+    if (N <= 0) return -7;
+    if (!mu) return -11;
+    if (!sigma) return -12;
+    k_barycentre_1d<<<grid1d((size_t)C * N, 128), 128, 0, ctx->stream>>>(means, variances, weights, C, M, N, tolerance,
+                                                                         init_var, max_iters, mu, sigma, iters);
+    BE_LAUNCHED();
+    return BE_OK;
+}
+
+int be_barycentre_1d_partial(be_ctx* ctx, const double* means, const double* variances, const double* lls_exp, int C,
+                             int M_local, int N, double* partial) {
+    if (!ctx) return -1;
+    if (!means) return -2;
+    if (!variances) return -3;
+    if (!lls_exp) return -4;
+    if (C <= 0) return -5;
+    if (M_local <= 0) return -6;
+    if (N <= 0) return -7;
+    if (!partial) return -8;
+    k_barycentre_partial<<<grid1d((size_t)C * N, 128), 128, 0, ctx->stream>>>(means, variances, lls_exp, C, M_local, N,
+                                                                              partial);
+    BE_LAUNCHED();
+    return BE_OK;
+}
+
+int be_barycentre_1d_finish(be_ctx* ctx, const double* partial, int C, int N, double tolerance, double init_var,
+                            int max_iters, double* mu, double* sigma, int* iters) {
+    if (!ctx) return -1;
+    if (!partial) return -2;
+    if (C <= 0) return -3;
+    if (N <= 0) return -4;
+    if (!mu) return -8;
+    if (!sigma) return -9;
+    k_barycentre_finish<<<grid1d((size_t)C * N, 128), 128, 0, ctx->stream>>>(partial, C, N, tolerance, init_var,
+                                                                             max_iters, mu, sigma, iters);
+    BE_LAUNCHED();
+    return BE_OK;
+}
+
+}  // extern "C"

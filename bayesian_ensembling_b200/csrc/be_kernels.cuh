@@ -1,0 +1,691 @@
+// Kernels of the fit -> weight -> barycentre hot path (sm_100a, fp64).
+//
+// Internal matrix layout ("padded"): every T x T problem lives in a [Tp, ld] row-major buffer
+// with Tp = ld = round_up(T + 2, 16).  Rows/cols >= T are padding: identity on the diagonal,
+// zero elsewhere -- EXCEPT that rows T and T+1 (cols < T) may carry right-hand sides.  The
+// blocked Cholesky never pivots on a padded column but applies every update to the padded
+// rows, so after the factorisation those rows hold (L^-1 rhs)^T: forward substitution rides
+// along inside the tensor-core updates instead of being a separate latency-bound TRSV.
+#pragma once
+#include <math.h>
+
+#include "dmma_gemm.cuh"
+
+namespace be {
+
+constexpr int NB = 128;  // block size of the blocked algorithms == GEMM tile edge
+constexpr int DIAG_LD = 129;
+constexpr int DIAG_SMEM_BYTES = NB * DIAG_LD * 8 + 2 * NB * 8;
+constexpr double SQRT3 = 1.7320508075688772;
+constexpr double LOG_2PI = 1.8378770664093453;
+
+__host__ __device__ inline int pad_dim(int T) { return ((T + 2 + 15) / 16) * 16; }
+__host__ __device__ inline int num_blocks(int Tp) { return (Tp + NB - 1) / NB; }
+__device__ __forceinline__ int blk_rows(int Tp, int kb) { return min(NB, Tp - kb * NB); }
+
+// --------------------------------------------------------------------------------------
+// models.py:175-182: X = realisation_set.T, y_mean (arithmetic), y_var = np.var(axis=0)
+// --------------------------------------------------------------------------------------
+__global__ void k_gpdtw1d_inputs(const double* __restrict__ reals, int B, int R, int T, double* __restrict__ X,
+                                 double* __restrict__ y_mean, double* __restrict__ y_var) {
+    size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= (size_t)B * T) return;
+    int b = (int)(gid / T), t = (int)(gid % T);
+    const double* src = reals + (size_t)b * R * T + t;
+    double s = 0.0;
+    for (int r = 0; r < R; ++r) s += src[(size_t)r * T];
+    double mean = s / R;
+    double v = 0.0;
+    for (int r = 0; r < R; ++r) {
+        double x = src[(size_t)r * T];
+        double d = x - mean;
+        v += d * d;
+        if (X) X[((size_t)b * T + t) * R + r] = x;
+    }
+    if (y_mean) y_mean[gid] = mean;
+    if (y_var) y_var[gid] = v / R;
+}
+
+// --------------------------------------------------------------------------------------
+// Matern-3/2 gram (gpflow Matern32 on X/l with the |x|^2+|y|^2-2xy expansion, r2 clamped at
+// 1e-36).  One CTA per 128 x 128 tile.  MODE 0: dense symmetric K [B,T,T].
+// MODE 1: padded lower tiles of M = K + diag(y_var + jitter), padding identity, row T = y_mean.
+// --------------------------------------------------------------------------------------
+template <int MODE>
+__global__ void __launch_bounds__(256) k_matern32(const double* __restrict__ X, int B, int T, int R,
+                                                  const double* __restrict__ variance,
+                                                  const double* __restrict__ lengthscale,
+                                                  const double* __restrict__ y_mean, const double* __restrict__ y_var,
+                                                  double jitter, double* __restrict__ out, int Tp, int ld,
+                                                  int ntiles) {
+    extern __shared__ double sm[];
+    const int Rp = R | 1;
+    double* xi = sm;
+    double* xj = xi + NB * Rp;
+    double* si = xj + NB * Rp;
+    double* sj = si + NB;
+    int tile = blockIdx.x / B, b = blockIdx.x % B;
+    int ti, tj;
+    if (MODE == 1) {
+        tri_decode(tile, ti, tj);
+    } else {
+        int nt = (T + NB - 1) / NB;
+        ti = tile / nt;
+        tj = tile % nt;
+    }
+    const double ls = lengthscale[b], var = variance[b];
+    const double* Xb = X + (size_t)b * T * R;
+    for (int e = threadIdx.x; e < NB * R; e += blockDim.x) {
+        int r = e / R, k = e % R;
+        int gi = ti * NB + r, gj = tj * NB + r;
+        xi[r * Rp + k] = gi < T ? Xb[(size_t)gi * R + k] / ls : 0.0;
+        xj[r * Rp + k] = gj < T ? Xb[(size_t)gj * R + k] / ls : 0.0;
+    }
+    __syncthreads();
+    if (threadIdx.x < NB) {
+        double s = 0.0;
+        for (int k = 0; k < R; ++k) s += xi[threadIdx.x * Rp + k] * xi[threadIdx.x * Rp + k];
+        si[threadIdx.x] = s;
+    } else {
+        int r = threadIdx.x - NB;
+        double s = 0.0;
+        for (int k = 0; k < R; ++k) s += xj[r * Rp + k] * xj[r * Rp + k];
+        sj[r] = s;
+    }
+    __syncthreads();
+    const int lim = MODE == 1 ? Tp : T;
+    for (int e = threadIdx.x; e < NB * NB; e += blockDim.x) {
+        int i = e >> 7, j = e & 127;
+        int gi = ti * NB + i, gj = tj * NB + j;
+        if (gi >= lim || gj >= lim) continue;
+        double val;
+        if (gi < T && gj < T) {
+            double dot = 0.0;
+            for (int k = 0; k < R; ++k) dot += xi[i * Rp + k] * xj[j * Rp + k];
+            double r2 = (-2.0 * dot + si[i]) + sj[j];
+            double r = sqrt(fmax(r2, 1e-36));
+            val = var * (1.0 + SQRT3 * r) * exp(-SQRT3 * r);
+            if (MODE == 1 && gi == gj) val += y_var[(size_t)b * T + gi] + jitter;
+        } else if (MODE == 1 && gi == T && gj < T) {
+            val = y_mean[(size_t)b * T + gj];
+        } else {
+            val = gi == gj ? 1.0 : 0.0;
+        }
+        if (MODE == 1)
+            out[(size_t)b * Tp * ld + (size_t)gi * ld + gj] = val;
+        else
+            out[(size_t)b * T * T + (size_t)gi * T + gj] = val;
+    }
+}
+
+// dense lower triangle -> padded buffer; rows T / T+1 optionally carry (1, mu)
+__global__ void k_pad_from_dense(const double* __restrict__ A, const double* __restrict__ mu, int B, int T, int Tp,
+                                 int ld, double* __restrict__ W, int with_rhs) {
+    size_t n = (size_t)B * Tp * ld;
+    for (size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x; gid < n; gid += (size_t)gridDim.x * blockDim.x) {
+        int b = (int)(gid / ((size_t)Tp * ld));
+        size_t rem = gid % ((size_t)Tp * ld);
+        int i = (int)(rem / ld), j = (int)(rem % ld);
+        double v;
+        if (i < T && j < T)
+            v = j <= i ? A[(size_t)b * T * T + (size_t)i * T + j] : 0.0;
+        else if (with_rhs && i == T && j < T)
+            v = 1.0;
+        else if (with_rhs && i == T + 1 && j < T)
+            v = mu[(size_t)b * T + j];
+        else
+            v = i == j ? 1.0 : 0.0;
+        W[gid] = v;
+    }
+}
+
+// --------------------------------------------------------------------------------------
+// Diagonal block: unblocked Cholesky of the (<=128)^2 block kb in shared memory, then its
+// inverse (in place) -> Dinv[b][kb] (row-major 128 x 128, identity on padding), and
+// optionally V tile (kb,kb) = Dinv^T.  Columns >= T are never pivots (see file header).
+// --------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_diag_block(double* __restrict__ Mat, int ld, int Tp, int T, int kb,
+                                                    double* __restrict__ Dinv, int nblk, double* __restrict__ V,
+                                                    int* __restrict__ info) {
+    extern __shared__ double sm[];
+    double* s = sm;                         // [128][129]
+    double* red = sm + NB * DIAG_LD;        // [2][128]
+    const int b = blockIdx.x;
+    const int tid = threadIdx.x;
+    const int r0 = kb * NB;
+    const int n = min(NB, Tp - r0);
+    const int nr = max(0, min(n, T - r0));
+    double* Mb = Mat + (size_t)b * Tp * ld;
+    for (int e = tid; e < NB * NB; e += 256) {
+        int i = e >> 7, j = e & 127;
+        double v = i == j ? 1.0 : 0.0;
+        if (i < n && j <= i) v = Mb[(size_t)(r0 + i) * ld + r0 + j];
+        s[i * DIAG_LD + j] = v;
+    }
+    __syncthreads();
+    const int i = tid & 127, h = tid >> 7;
+    int bad = 0;
+    for (int j = 0; j < nr; ++j) {
+        double piv = s[j * DIAG_LD + j];
+        if (!(piv > 0.0) && bad == 0) bad = r0 + j + 1;
+        double aij = 0.0;
+        if (i > j && i < n) {
+            aij = s[i * DIAG_LD + j];
+            double f = aij / piv;
+            int kmax = min(i, nr - 1);
+            for (int k = j + 1 + h; k <= kmax; k += 2) s[i * DIAG_LD + k] -= f * s[k * DIAG_LD + j];
+        }
+        __syncthreads();
+        if (h == 0 && i < n) {
+            double d = sqrt(piv);
+            if (i == j) s[i * DIAG_LD + j] = d;
+            else if (i > j) s[i * DIAG_LD + j] = aij / d;
+        }
+    }
+    __syncthreads();
+    if (tid == 0 && bad != 0 && info) {
+        if (info[b] == 0) info[b] = bad;
+    }
+    // write the factor back (lower part of the block, all n rows, real columns only)
+    for (int e = tid; e < NB * NB; e += 256) {
+        int r = e >> 7, c = e & 127;
+        if (r < n && c <= r && c < nr) Mb[(size_t)(r0 + r) * ld + r0 + c] = s[r * DIAG_LD + c];
+    }
+    __syncthreads();
+    // in-place inverse of the real nr x nr lower triangle (columns from last to first)
+    for (int j = nr - 1; j >= 0; --j) {
+        double wjj = 1.0 / s[j * DIAG_LD + j];
+        double part = 0.0;
+        if (i > j && i < nr) {
+            for (int k = j + 1 + h; k <= i; k += 2) part += s[i * DIAG_LD + k] * s[k * DIAG_LD + j];
+        }
+        red[h * NB + i] = part;
+        __syncthreads();
+        if (h == 0) {
+            if (i == j) s[j * DIAG_LD + j] = wjj;
+            else if (i > j && i < nr) s[i * DIAG_LD + j] = -(red[i] + red[NB + i]) * wjj;
+        }
+        __syncthreads();
+    }
+    double* Db = Dinv + ((size_t)b * nblk + kb) * NB * NB;
+    for (int e = tid; e < NB * NB; e += 256) {
+        int r = e >> 7, c = e & 127;
+        double v = r == c ? 1.0 : 0.0;
+        if (r < nr && c < nr) v = c <= r ? s[r * DIAG_LD + c] : 0.0;
+        Db[e] = v;
+    }
+    if (V) {
+        double* Vb = V + (size_t)b * Tp * ld;
+        for (int e = tid; e < NB * NB; e += 256) {
+            int r = e >> 7, c = e & 127;
+            if (r >= n || c >= n) continue;
+            double v = r == c ? 1.0 : 0.0;
+            if (r < nr && c < nr) v = c >= r ? s[c * DIAG_LD + r] : 0.0;
+            Vb[(size_t)(r0 + r) * ld + r0 + c] = v;
+        }
+    }
+}
+
+// --------------------------------------------------------------------------------------
+// Tensor-core tile kernels (all share gemm_nt_mainloop)
+// --------------------------------------------------------------------------------------
+
+// Trailing update of the right-looking Cholesky: for block rows ti >= tj > kb
+//   Mat[ti, tj] -= Mat[ti, kb] * Mat[tj, kb]^T
+__global__ void __launch_bounds__(GEMM_THREADS, 1) k_syrk_trailing(double* __restrict__ Mat, int ld, int Tp, int kb,
+                                                                   int B) {
+    extern __shared__ __align__(16) double2 smem2[];
+    int tile = blockIdx.x / B, b = blockIdx.x % B;
+    int ti, tj;
+    tri_decode(tile, ti, tj);
+    ti += kb + 1;
+    tj += kb + 1;
+    double* Mb = Mat + (size_t)b * Tp * ld;
+    const int a_rows = blk_rows(Tp, ti), b_rows = blk_rows(Tp, tj);
+    TileAcc acc;
+    gemm_nt_mainloop(Mb + (size_t)ti * NB * ld + kb * NB, ld, a_rows, Mb + (size_t)tj * NB * ld + kb * NB, ld, b_rows,
+                     NB, smem2, acc);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double* Cb = Mb + (size_t)ti * NB * ld + tj * NB;
+#pragma unroll
+    for (int mi = 0; mi < 8; ++mi) {
+        int r = acc_row(warp, lane, mi);
+        if (r >= a_rows) continue;
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni) {
+            int c = acc_col(warp, lane, ni);
+            if (c >= b_rows) continue;
+            double2* p = reinterpret_cast<double2*>(Cb + (size_t)r * ld + c);
+            double2 v = *p;
+            v.x -= acc.v[mi][ni][0];
+            v.y -= acc.v[mi][ni][1];
+            *p = v;
+        }
+    }
+}
+
+// In-place right-multiplication of tiles (row block row_blk0 + x, column block cb) by the
+// transposed inverse diagonal block:  Mat[ti, cb] <- sign * Mat[ti, cb] * Dinv[cb]^T
+// (panel TRSM of the Cholesky with sign=+1; second half of the trtri column step with -1).
+__global__ void __launch_bounds__(GEMM_THREADS, 1) k_panel_scale(double* __restrict__ Mat, int ld, int Tp,
+                                                                 int row_blk0, int cb, const double* __restrict__ Dinv,
+                                                                 int nblk, double sign, int B) {
+    extern __shared__ __align__(16) double2 smem2[];
+    int tile = blockIdx.x / B, b = blockIdx.x % B;
+    int ti = row_blk0 + tile;
+    double* Mb = Mat + (size_t)b * Tp * ld;
+    const int a_rows = blk_rows(Tp, ti), kw = blk_rows(Tp, cb);
+    const double* Db = Dinv + ((size_t)b * nblk + cb) * NB * NB;
+    TileAcc acc;
+    double* Cb = Mb + (size_t)ti * NB * ld + cb * NB;
+    gemm_nt_mainloop(Cb, ld, a_rows, Db, NB, kw, kw, smem2, acc);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int mi = 0; mi < 8; ++mi) {
+        int r = acc_row(warp, lane, mi);
+        if (r >= a_rows) continue;
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni) {
+            int c = acc_col(warp, lane, ni);
+            if (c >= kw) continue;
+            double2 v;
+            v.x = sign * acc.v[mi][ni][0];
+            v.y = sign * acc.v[mi][ni][1];
+            *reinterpret_cast<double2*>(Cb + (size_t)r * ld + c) = v;
+        }
+    }
+}
+
+// trtri column step i, first half:  V[j, i] = sum_{p=j}^{i-1} V[j, p] * C[i, p]^T   (j < i)
+// with V = C^-T (upper, row-major) so that every contraction is K-contiguous.
+__global__ void __launch_bounds__(GEMM_THREADS, 1) k_trtri_accum(double* __restrict__ V, const double* __restrict__ Cm,
+                                                                 int ld, int Tp, int i, int B) {
+    extern __shared__ __align__(16) double2 smem2[];
+    int j = blockIdx.x / B, b = blockIdx.x % B;
+    double* Vb = V + (size_t)b * Tp * ld;
+    const double* Cb = Cm + (size_t)b * Tp * ld;
+    const int b_rows = blk_rows(Tp, i);
+    TileAcc acc;
+    gemm_nt_mainloop(Vb + (size_t)j * NB * ld + j * NB, ld, NB, Cb + (size_t)i * NB * ld + j * NB, ld, b_rows,
+                     (i - j) * NB, smem2, acc);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double* Ob = Vb + (size_t)j * NB * ld + i * NB;
+#pragma unroll
+    for (int mi = 0; mi < 8; ++mi) {
+        int r = acc_row(warp, lane, mi);
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni) {
+            int c = acc_col(warp, lane, ni);
+            if (c >= b_rows) continue;
+            double2 v;
+            v.x = acc.v[mi][ni][0];
+            v.y = acc.v[mi][ni][1];
+            *reinterpret_cast<double2*>(Ob + (size_t)r * ld + c) = v;
+        }
+    }
+}
+
+// lauum with the posterior epilogue.  Minv = V V^T (V = C^-T, C = chol(K + E), E = D + jitter I);
+//   cov = D + E - E Minv E            ( == K - K (K+E)^-1 K + D, see DESIGN.md )
+// written to: Work (padded, lower; aliases the buffer that held C), var_diag, and optionally
+// the dense symmetric cov [B,T,T].  Rows T / T+1 of Work get the right-hand sides (1, mu) of
+// the log-likelihood stage; the rest of the padding is identity.
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+    k_lauum_cov(const double* __restrict__ V, int ld, int Tp, int T, const double* __restrict__ y_var, double jitter,
+                const double* __restrict__ mu, double* __restrict__ Work, double* __restrict__ var_diag,
+                double* __restrict__ cov_dense, int B) {
+    extern __shared__ __align__(16) double2 smem2[];
+    int tile = blockIdx.x / B, b = blockIdx.x % B;
+    int ti, tj;
+    tri_decode(tile, ti, tj);
+    const double* Vb = V + (size_t)b * Tp * ld;
+    const int a_rows = blk_rows(Tp, ti), b_rows = blk_rows(Tp, tj);
+    TileAcc acc;
+    gemm_nt_mainloop(Vb + (size_t)ti * NB * ld + ti * NB, ld, a_rows, Vb + (size_t)tj * NB * ld + ti * NB, ld, b_rows,
+                     Tp - ti * NB, smem2, acc);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double* Wb = Work + (size_t)b * Tp * ld;
+    const double* yv = y_var + (size_t)b * T;
+    const double* mub = mu + (size_t)b * T;
+    double* cd = cov_dense ? cov_dense + (size_t)b * T * T : nullptr;
+#pragma unroll
+    for (int mi = 0; mi < 8; ++mi) {
+        int r = acc_row(warp, lane, mi);
+        if (r >= a_rows) continue;
+        int gr = ti * NB + r;
+        double dr = gr < T ? yv[gr] : 0.0;
+        double er = dr + jitter;
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni) {
+            int c = acc_col(warp, lane, ni);
+            if (c >= b_rows) continue;
+            double out[2];
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                int gc = tj * NB + c + e;
+                double val;
+                if (gr < T && gc < T) {
+                    double ec = yv[gc] + jitter;
+                    val = -er * ec * acc.v[mi][ni][e];
+                    if (gr == gc) {
+                        val += dr + er;
+                        var_diag[(size_t)b * T + gr] = val;
+                    }
+                    if (cd && gc <= gr) {
+                        cd[(size_t)gr * T + gc] = val;
+                        cd[(size_t)gc * T + gr] = val;
+                    }
+                } else if (gr == T && gc < T) {
+                    val = 1.0;
+                } else if (gr == T + 1 && gc < T) {
+                    val = mub[gc];
+                } else {
+                    val = gr == gc ? 1.0 : 0.0;
+                }
+                out[e] = val;
+            }
+            *reinterpret_cast<double2*>(Wb + (size_t)gr * ld + tj * NB + c) = make_double2(out[0], out[1]);
+        }
+    }
+}
+
+// --------------------------------------------------------------------------------------
+// small memory-bound helpers
+// --------------------------------------------------------------------------------------
+
+// copy padded row `row` (cols < T) to out[b, 0:T] and zero it in the matrix
+__global__ void k_extract_row(double* __restrict__ Mat, int ld, int Tp, int T, int row, double* __restrict__ out,
+                              int B, int zero_after) {
+    size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= (size_t)B * T) return;
+    int b = (int)(gid / T), j = (int)(gid % T);
+    double* p = Mat + (size_t)b * Tp * ld + (size_t)row * ld + j;
+    out[gid] = *p;
+    if (zero_after) *p = 0.0;
+}
+
+// mean = y - E * (V u),  u = C^-1 y (rode along as row T of the first factorisation).
+// One warp per row: alpha_i = sum_{k>=i} V[i,k] u[k]   (V upper, K-contiguous => coalesced).
+__global__ void __launch_bounds__(256) k_posterior_mean(const double* __restrict__ V, int ld, int Tp, int T,
+                                                        const double* __restrict__ u, const double* __restrict__ y_mean,
+                                                        const double* __restrict__ y_var, double jitter,
+                                                        double* __restrict__ mu, int B) {
+    int warp_global = blockIdx.x * 8 + (threadIdx.x >> 5);
+    int lane = threadIdx.x & 31;
+    if (warp_global >= B * T) return;
+    int b = warp_global / T, i = warp_global % T;
+    const double* row = V + (size_t)b * Tp * ld + (size_t)i * ld;
+    const double* ub = u + (size_t)b * T;
+    double s0 = 0.0, s1 = 0.0;
+    int k0 = i & ~1;  // aligned start; element k0 < i (if any) is an explicit zero of the upper factor
+    for (int k = k0 + 2 * lane; k < T; k += 64) {
+        double2 v = *reinterpret_cast<const double2*>(row + k);
+        if (k >= i) s0 += v.x * ub[k];
+        if (k + 1 < T && k + 1 >= i) s1 += v.y * ub[k + 1];
+    }
+    double s = s0 + s1;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) {
+        size_t g = (size_t)b * T + i;
+        mu[g] = y_mean[g] - (y_var[g] + jitter) * s;
+    }
+}
+
+// mvn_stats[b] = (|a|^2, a.b, |b|^2, sum log diag L) from rows T, T+1 and the diagonal
+__global__ void __launch_bounds__(256) k_mvn_stats(const double* __restrict__ Work, int ld, int Tp, int T,
+                                                   double* __restrict__ stats) {
+    __shared__ double red[4][8];
+    int b = blockIdx.x;
+    const double* Wb = Work + (size_t)b * Tp * ld;
+    const double* ra = Wb + (size_t)T * ld;
+    const double* rb = Wb + (size_t)(T + 1) * ld;
+    double aa = 0, ab = 0, bb = 0, ld_ = 0;
+    for (int j = threadIdx.x; j < T; j += 256) {
+        double a = ra[j], bq = rb[j];
+        aa += a * a;
+        ab += a * bq;
+        bb += bq * bq;
+        ld_ += log(fabs(Wb[(size_t)j * ld + j]));
+    }
+    double v[4] = {aa, ab, bb, ld_};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v[q] += __shfl_xor_sync(0xffffffffu, v[q], o);
+        if ((threadIdx.x & 31) == 0) red[q][threadIdx.x >> 5] = v[q];
+    }
+    __syncthreads();
+    if (threadIdx.x < 4) {
+        double s = 0;
+        for (int w = 0; w < 8; ++w) s += red[threadIdx.x][w];
+        stats[(size_t)b * 4 + threadIdx.x] = s;
+    }
+}
+
+// padded lower factor -> dense [B,T,T] with the strict upper triangle zeroed
+__global__ void k_copy_out_tri(const double* __restrict__ Work, int ld, int Tp, int T, double* __restrict__ L, int B) {
+    size_t n = (size_t)B * T * T;
+    for (size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x; gid < n; gid += (size_t)gridDim.x * blockDim.x) {
+        int b = (int)(gid / ((size_t)T * T));
+        size_t rem = gid % ((size_t)T * T);
+        int i = (int)(rem / T), j = (int)(rem % T);
+        L[gid] = j <= i ? Work[(size_t)b * Tp * ld + (size_t)i * ld + j] : 0.0;
+    }
+}
+
+__global__ void k_diag_from_dense(const double* __restrict__ A, int B, int T, double* __restrict__ d) {
+    size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= (size_t)B * T) return;
+    int b = (int)(gid / T), i = (int)(gid % T);
+    d[gid] = A[(size_t)b * T * T + (size_t)i * T + i];
+}
+
+// --------------------------------------------------------------------------------------
+// a4: log-likelihood weights.  weights.py:97-100 evaluates the MVN density at the CONSTANT
+// vector o*1_T (quirk Q-LL):  -1/2 |L^-1 (o 1 - mu)|^2 = -1/2 (o^2 |a|^2 - 2 o a.b + |b|^2).
+// --------------------------------------------------------------------------------------
+__device__ __forceinline__ double constvec_ll(const double* __restrict__ st, double o, int T) {
+    double maha = (o * o) * st[0] - 2.0 * o * st[1] + st[2];
+    return -0.5 * maha - 0.5 * (double)T * LOG_2PI - st[3];
+}
+
+__global__ void k_mvn_constvec_logprob(const double* __restrict__ stats, const double* __restrict__ obs, int C, int M,
+                                       int Ro, int T, double* __restrict__ ll) {
+    size_t n = (size_t)C * M * Ro * T;
+    size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= n) return;
+    int i = (int)(gid % T);
+    size_t q = gid / T;
+    int r = (int)(q % Ro);
+    q /= Ro;
+    int m = (int)(q % M);
+    int c = (int)(q / M);
+    ll[gid] = constvec_ll(stats + ((size_t)c * M + m) * 4, obs[((size_t)c * Ro + r) * T + i], T);
+}
+
+// one thread per (cell, time): mean over obs realisations (weights.py:103-104), exp(c .) (:107),
+// normalise over models (:122-123).  Sequential sums in the reference's order.
+__global__ void k_loglik_weights_mvn(const double* __restrict__ stats, const double* __restrict__ obs, int C, int M,
+                                     int Ro, int T, double cst, double* __restrict__ w, double* __restrict__ lls_exp,
+                                     double* __restrict__ lls_mean) {
+    size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= (size_t)C * T) return;
+    int c = (int)(gid / T), i = (int)(gid % T);
+    const double* ob = obs + (size_t)c * Ro * T + i;
+    double total = 0.0;
+    for (int m = 0; m < M; ++m) {
+        const double* st = stats + ((size_t)c * M + m) * 4;
+        double s = 0.0;
+        for (int r = 0; r < Ro; ++r) s += constvec_ll(st, ob[(size_t)r * T], T);
+        double mean = s / Ro;
+        double e = exp(cst * mean);
+        size_t o = ((size_t)c * M + m) * T + i;
+        if (lls_mean) lls_mean[o] = mean;
+        if (lls_exp) lls_exp[o] = e;
+        w[o] = e;
+        total += e;
+    }
+    for (int m = 0; m < M; ++m) {
+        size_t o = ((size_t)c * M + m) * T + i;
+        w[o] = w[o] / total;
+    }
+}
+
+__global__ void k_normal_logprob(const double* __restrict__ loc, const double* __restrict__ scale,
+                                 const double* __restrict__ x, size_t n, double* __restrict__ ll) {
+    size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= n) return;
+    double z = (x[gid] - loc[gid]) / scale[gid];
+    ll[gid] = -0.5 * z * z - 0.5 * LOG_2PI - log(scale[gid]);
+}
+
+__global__ void k_loglik_weights_normal(const double* __restrict__ loc, const double* __restrict__ scale,
+                                        const double* __restrict__ obs, int C, int M, int Ro, int N, double cst,
+                                        double* __restrict__ w, double* __restrict__ lls_exp,
+                                        double* __restrict__ lls_mean) {
+    size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= (size_t)C * N) return;
+    int c = (int)(gid / N), i = (int)(gid % N);
+    const double* ob = obs + (size_t)c * Ro * N + i;
+    double total = 0.0;
+    for (int m = 0; m < M; ++m) {
+        size_t o = ((size_t)c * M + m) * N + i;
+        double l = loc[o], sc = scale[o];
+        double lsc = log(sc);
+        double s = 0.0;
+        for (int r = 0; r < Ro; ++r) {
+            double z = (ob[(size_t)r * N] - l) / sc;
+            s += -0.5 * z * z - 0.5 * LOG_2PI - lsc;
+        }
+        double mean = s / Ro;
+        double e = exp(cst * mean);
+        if (lls_mean) lls_mean[o] = mean;
+        if (lls_exp) lls_exp[o] = e;
+        w[o] = e;
+        total += e;
+    }
+    for (int m = 0; m < M; ++m) {
+        size_t o = ((size_t)c * M + m) * N + i;
+        w[o] = w[o] / total;
+    }
+}
+
+// xarray .mean('time') skips NaN (utils.py:111); broadcast back over time (utils.py:133)
+__global__ void __launch_bounds__(256) k_weights_time_mean(const double* __restrict__ w, int CM, int T,
+                                                           double* __restrict__ out) {
+    __shared__ double rs[8];
+    __shared__ double rc[8];
+    int row = blockIdx.x;
+    const double* p = w + (size_t)row * T;
+    double s = 0.0, cnt = 0.0;
+    for (int i = threadIdx.x; i < T; i += 256) {
+        double v = p[i];
+        if (!isnan(v)) {
+            s += v;
+            cnt += 1.0;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        s += __shfl_xor_sync(0xffffffffu, s, o);
+        cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        rs[threadIdx.x >> 5] = s;
+        rc[threadIdx.x >> 5] = cnt;
+    }
+    __syncthreads();
+    double S = 0, Cn = 0;
+    for (int q = 0; q < 8; ++q) {
+        S += rs[q];
+        Cn += rc[q];
+    }
+    double m = S / Cn;  // all-NaN row -> 0/0 = NaN, as xarray
+    for (int i = threadIdx.x; i < T; i += 256) out[(size_t)row * T + i] = m;
+}
+
+// --------------------------------------------------------------------------------------
+// a5/a6: 1-D Gaussian W2 barycentre with the reference's SIGNED stop rule (wasserstein.py:88)
+// --------------------------------------------------------------------------------------
+__device__ __forceinline__ void barycentre_iterate(double S_unit /* sum w s, or NaN */, bool use_unit,
+                                                   const double* __restrict__ w, const double* __restrict__ var,
+                                                   size_t stride, int M, double tol, double init_var, int max_iters,
+                                                   double& sigma, int& iters) {
+    double bv = init_var;
+    int n_it = 0;
+    while (true) {
+        double cand = 0.0;
+        double sq = sqrt(bv);
+        if (use_unit) {
+            cand = sq * S_unit;
+        } else {
+            for (int m = 0; m < M; ++m) cand += w[m * stride] * sq * sqrt(var[m * stride]);
+        }
+        if (cand - bv < tol) {
+            bv = cand;
+            break;
+        }
+        bv = cand;
+        ++n_it;
+        if (n_it > max_iters) break;
+    }
+    sigma = sqrt(bv);
+    iters = n_it;
+}
+
+__global__ void k_barycentre_1d(const double* __restrict__ means, const double* __restrict__ variances,
+                                const double* __restrict__ weights, int C, int M, int N, double tol, double init_var,
+                                int max_iters, double* __restrict__ mu, double* __restrict__ sigma,
+                                int* __restrict__ iters) {
+    size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= (size_t)C * N) return;
+    int c = (int)(gid / N), i = (int)(gid % N);
+    size_t base = (size_t)c * M * N + i;
+    double m_acc = 0.0;
+    for (int m = 0; m < M; ++m) m_acc += weights[base + (size_t)m * N] * means[base + (size_t)m * N];
+    double sg;
+    int it;
+    barycentre_iterate(0.0, false, weights + base, variances + base, (size_t)N, M, tol, init_var, max_iters, sg, it);
+    mu[gid] = m_acc;
+    sigma[gid] = sg;
+    if (iters) iters[gid] = it;
+}
+
+__global__ void k_barycentre_partial(const double* __restrict__ means, const double* __restrict__ variances,
+                                     const double* __restrict__ lls_exp, int C, int M, int N,
+                                     double* __restrict__ partial) {
+    size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t CN = (size_t)C * N;
+    if (gid >= CN) return;
+    int c = (int)(gid / N), i = (int)(gid % N);
+    size_t base = (size_t)c * M * N + i;
+    double s0 = 0, s1 = 0, s2 = 0;
+    for (int m = 0; m < M; ++m) {
+        double w = lls_exp[base + (size_t)m * N];
+        s0 += w;
+        s1 += w * means[base + (size_t)m * N];
+        s2 += w * sqrt(variances[base + (size_t)m * N]);
+    }
+    partial[gid] = s0;
+    partial[CN + gid] = s1;
+    partial[2 * CN + gid] = s2;
+}
+
+__global__ void k_barycentre_finish(const double* __restrict__ partial, int C, int N, double tol, double init_var,
+                                    int max_iters, double* __restrict__ mu, double* __restrict__ sigma,
+                                    int* __restrict__ iters) {
+    size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t CN = (size_t)C * N;
+    if (gid >= CN) return;
+    double s0 = partial[gid];
+    double S = partial[2 * CN + gid] / s0;
+    double sg;
+    int it;
+    barycentre_iterate(S, true, nullptr, nullptr, 0, 0, tol, init_var, max_iters, sg, it);
+    mu[gid] = partial[CN + gid] / s0;
+    sigma[gid] = sg;
+    if (iters) iters[gid] = it;
+}
+
+}  // namespace be

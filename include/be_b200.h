@@ -1,0 +1,142 @@
+/*
+ * be_b200.h -- C ABI of the B200-native fit -> weight -> barycentre hot path of
+ * mattramos/bayesian_ensembling.
+ *
+ * The reference is pure Python and has NO FFI; its numerics are calls into
+ * GPflow/TensorFlow, distrax/JAX and NumPy made from the files cited below
+ * (paths relative to the reference repo).  Every entry point here replaces one
+ * of those call sites; INTEGRATION.md shows the ctypes binding a maintainer of
+ * the reference would add at each site.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes; no torch / CUDA types in signatures
+ *     (a cudaStream_t travels as void*).
+ *   - all arrays are fp64, C-order, contiguous, DEVICE pointers unless the
+ *     parameter name ends in _host.
+ *   - B enumerates independent (cell, member) problems, b = cell * M + member.
+ *   - return value: 0 ok; <0 = -(index of the bad argument, 1-based);
+ *     BE_ERR_CUDA / BE_ERR_WORKSPACE for runtime failures.  Numerical
+ *     conditions (non-PD matrix) are NOT errors: they are reported per problem
+ *     in the LAPACK-style `info` arrays (0 ok, k>0 = leading minor k not PD)
+ *     and NaNs propagate exactly as in the reference (jnp.linalg.cholesky
+ *     returns NaN silently).
+ *   - the caller owns every buffer including workspace (query *_workspace_bytes);
+ *     the ctx owns only its stream handle.  Calls on one ctx are stream-ordered
+ *     and asynchronous; be_ctx_sync() waits.  One ctx per (process, device).
+ */
+#ifndef BE_B200_H
+#define BE_B200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BE_OK 0
+#define BE_ERR_CUDA 1000
+#define BE_ERR_WORKSPACE 1001
+#define BE_ERR_UNSUPPORTED 1002
+
+#define BE_DEFAULT_JITTER 1e-6 /* gpflow.config.default_jitter() */
+
+typedef struct be_ctx be_ctx;
+
+int be_version(void);
+/* stream may be NULL (legacy default stream) or a cudaStream_t owned by the caller */
+int be_ctx_create(int device, void* stream, be_ctx** out);
+int be_ctx_set_stream(be_ctx* ctx, void* stream);
+int be_ctx_destroy(be_ctx* ctx);
+int be_ctx_sync(be_ctx* ctx);
+/* text of the last CUDA error seen on this ctx ("" if none) */
+const char* be_ctx_last_error(be_ctx* ctx);
+/* number of kernels this ctx has launched since creation (bench.py's gpu_launches) */
+long long be_ctx_launch_count(be_ctx* ctx);
+
+/* ---- a1 inputs: ensembles/models.py:175-182 -------------------------------------------
+ * realisations [B,R,T] -> X [B,T,R] (= realisation_set.T), y_mean [B,T] (arithmetic mean
+ * over realisations; the reference's DBA mean, models.py:176-178, is supplied by the caller
+ * instead when wanted), y_var [B,T] (np.var, ddof=0, models.py:179). */
+int be_gpdtw1d_inputs(be_ctx* ctx, const double* realisations, int B, int R, int T,
+                      double* X, double* y_mean, double* y_var);
+
+/* ---- a1 kernel matrix: gpf.kernels.Matern32() built at models.py:186 -------------------
+ * K [B,T,T] dense symmetric; variance/lengthscale [B]. */
+int be_matern32_gram(be_ctx* ctx, const double* X, int B, int T, int R,
+                     const double* variance, const double* lengthscale, double* K);
+
+/* ---- a3 Cholesky: jnp.linalg.cholesky inside distrax, ensembles/data.py:38-39 ----------
+ * A [B,T,T] dense (lower triangle read) -> L [B,T,T] lower, strict upper zeroed. */
+size_t be_potrf_workspace_bytes(int B, int T);
+int be_potrf_batched(be_ctx* ctx, const double* A, int B, int T, double* L, int* info,
+                     void* workspace, size_t workspace_bytes);
+
+/* ---- a1 L1: posterior GPDTW1D.fit converges to for fixed kernel hyper-parameters -------
+ * (models.py:185-220 at the natural-gradient fixed point).
+ * Outputs: mu [B,T]; var_diag [B,T] = diag(cov); cov [B,T,T] (may be NULL);
+ * scale_tri [B,T,T] = chol(cov), data.py:38-39 (may be NULL);
+ * mvn_stats [B,4] = (|a|^2, a.b, |b|^2, sum log diag L) with a = L^-1 1, b = L^-1 mu --
+ * everything LogLikelihoodWeight needs from a member (weights.py:97-100);
+ * info_fit [B] (Cholesky of K + D + jitter I), info_dist [B] (Cholesky of cov). */
+size_t be_gp_posterior_workspace_bytes(int B, int T, int R);
+int be_gp_posterior(be_ctx* ctx, const double* X, const double* y_mean, const double* y_var,
+                    const double* variance, const double* lengthscale, double jitter,
+                    int B, int T, int R,
+                    double* mu, double* var_diag, double* cov, double* scale_tri,
+                    double* mvn_stats, int* info_fit, int* info_dist,
+                    void* workspace, size_t workspace_bytes);
+
+/* ---- a3: Distribution(mu, cov, MultivariateNormalFullCovariance), data.py:38-39 ---------
+ * from an arbitrary covariance: scale_tri, diag and the log-prob statistics. */
+size_t be_mvn_from_cov_workspace_bytes(int B, int T);
+int be_mvn_from_cov(be_ctx* ctx, const double* mu, const double* cov, int B, int T,
+                    double* scale_tri, double* var_diag, double* mvn_stats, int* info,
+                    void* workspace, size_t workspace_bytes);
+
+/* ---- a4: LogLikelihoodWeight._compute, ensembles/weights.py:87-123 ----------------------
+ * MVN branch (:97-100, quirk Q-LL): ll[c,m,r,i] = log N(obs[c,r,i] * 1_T | mu, Sigma).
+ * obs [C,Ro,T]; mvn_stats [C*M,4].  lls_mean [C,M,T] = mean over r (:103-104);
+ * lls_exp = exp(c * lls_mean) (:107, no max-subtraction, Q-EXP);
+ * weights [C,M,T] = lls_exp / sum_m lls_exp (:122-123; 0/0 -> NaN kept).
+ * lls_mean / lls_exp may be NULL. */
+int be_loglik_weights_mvn(be_ctx* ctx, const double* mvn_stats, const double* obs,
+                          int C, int M, int Ro, int T, double standardisation_constant,
+                          double* weights, double* lls_exp, double* lls_mean);
+/* per-realisation log-probs of the same branch, ll [C,M,Ro,T] (distribution.log_prob, :98-100) */
+int be_mvn_constvec_logprob(be_ctx* ctx, const double* mvn_stats, const double* obs,
+                            int C, int M, int Ro, int T, double* ll);
+/* dx.Normal branch (:95-96): elementwise log N(x | loc, scale) -- 2nd argument is a SCALE
+ * (quirk Q-SCALE).  n elements. */
+int be_normal_logprob(be_ctx* ctx, const double* loc, const double* scale, const double* x,
+                      size_t n, double* ll);
+/* Normal branch weights: loc/scale [C,M,N], obs [C,Ro,N] -> weights [C,M,N] */
+int be_loglik_weights_normal(be_ctx* ctx, const double* loc, const double* scale,
+                             const double* obs, int C, int M, int Ro, int N,
+                             double standardisation_constant,
+                             double* weights, double* lls_exp, double* lls_mean);
+/* mean over the time axis skipping NaN (xarray .mean('time'), ensembles/utils.py:111),
+ * broadcast back over time (utils.py:133): w [C,M,T] -> w_bar [C,M,T] */
+int be_weights_time_mean(be_ctx* ctx, const double* weights, int C, int M, int T, double* w_bar);
+
+/* ---- a5/a6: Barycentre._compute + gaussian_barycentre ----------------------------------
+ * ensembles/ensemble_scheme.py:54-72 and ensembles/wasserstein.py:61-100 (signed stop
+ * rule, quirk Q-BARY).  means, variances, weights [C,M,N] -> mu, sigma [C,N]; iters [C,N]
+ * (may be NULL) = iterations taken, > max_iters means "not converged" (the reference
+ * warns, :94-97).  std = sqrt(variance) is taken inside (ensemble_scheme.py:65). */
+int be_barycentre_1d(be_ctx* ctx, const double* means, const double* variances,
+                     const double* weights, int C, int M, int N,
+                     double tolerance, double init_var, int max_iters,
+                     double* mu, double* sigma, int* iters);
+/* member-sharded form (multi-GPU): partial sums over the local members
+ *   partial [3,C,N] = (sum_m w~, sum_m w~ mu, sum_m w~ sqrt(var)) from UN-normalised w~;
+ * all-reduce partial over ranks (NCCL), then be_barycentre_1d_finish divides and iterates. */
+int be_barycentre_1d_partial(be_ctx* ctx, const double* means, const double* variances,
+                             const double* lls_exp, int C, int M_local, int N, double* partial);
+int be_barycentre_1d_finish(be_ctx* ctx, const double* partial, int C, int N,
+                            double tolerance, double init_var, int max_iters,
+                            double* mu, double* sigma, int* iters);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BE_B200_H */

@@ -1,2 +1,11 @@
-"""B200-native fit -> weight -> barycentre hot path of mattramos/bayesian_ensembling."""
+"""B200-native fit -> weight -> barycentre hot path of mattramos/bayesian_ensembling.
+
+Mirrors the reference's public names (ensembles/__init__.py:1-6) for the path in scope."""
+from .data import Distribution, ModelCollection, ProcessModel  # noqa: F401
+from .ensemble_scheme import Barycentre  # noqa: F401
+from .labelled import DataArray  # noqa: F401
+from .models import GPDTW1D  # noqa: F401
+from .wasserstein import gaussian_barycentre  # noqa: F401
+from .weights import LogLikelihoodWeight, UniformWeight  # noqa: F401
+
 __version__ = "0.1.0"

@@ -34,6 +34,11 @@ SIGNATURES = {
     "be_ctx_sync": (_I, [_P]),
     "be_ctx_last_error": (ctypes.c_char_p, [_P]),
     "be_ctx_launch_count": (ctypes.c_longlong, [_P]),
+    "be_ctx_profile_enable": (_I, [_P, _I]),
+    "be_ctx_profile_reset": (_I, [_P]),
+    "be_ctx_profile_families": (_I, []),
+    "be_ctx_profile_get": (_I, [_P, _I, ctypes.c_char_p, _Z, ctypes.POINTER(_D), ctypes.POINTER(ctypes.c_longlong),
+                                ctypes.POINTER(_D), ctypes.POINTER(_D)]),
     "be_gpdtw1d_inputs": (_I, [_P, _P, _I, _I, _I, _P, _P, _P]),
     "be_matern32_gram": (_I, [_P, _P, _I, _I, _I, _P, _P, _P]),
     "be_potrf_workspace_bytes": (_Z, [_I, _I]),
@@ -47,6 +52,7 @@ SIGNATURES = {
     "be_normal_logprob": (_I, [_P, _P, _P, _P, _Z, _P]),
     "be_loglik_weights_normal": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _D, _P, _P, _P]),
     "be_weights_time_mean": (_I, [_P, _P, _I, _I, _I, _P]),
+    "be_weights_normalise": (_I, [_P, _P, _P, _I, _I, _I, _P]),
     "be_barycentre_1d": (_I, [_P, _P, _P, _P, _I, _I, _I, _D, _D, _I, _P, _P, _P]),
     "be_barycentre_1d_partial": (_I, [_P, _P, _P, _P, _I, _I, _I, _P]),
     "be_barycentre_1d_finish": (_I, [_P, _P, _I, _I, _D, _D, _I, _P, _P, _P]),

@@ -95,6 +95,27 @@ class Backend:
     def launch_count(self) -> int:
         return int(self.lib.be_ctx_launch_count(self.ctx))
 
+    # ------------------------------------------------------------------ per-kernel timing
+    def profile(self, on: bool = True):
+        _lib.check(self.ctx, self.lib.be_ctx_profile_enable(self.ctx, int(on)), "be_ctx_profile_enable")
+
+    def profile_reset(self):
+        _lib.check(self.ctx, self.lib.be_ctx_profile_reset(self.ctx), "be_ctx_profile_reset")
+
+    def profile_read(self) -> dict:
+        """{kernel family: dict(ms, launches, flops, bytes)} since the last reset (synchronises)."""
+        out = {}
+        name = ctypes.create_string_buffer(64)
+        ms, fl, by = ctypes.c_double(), ctypes.c_double(), ctypes.c_double()
+        n = ctypes.c_longlong()
+        for f in range(self.lib.be_ctx_profile_families()):
+            rc = self.lib.be_ctx_profile_get(self.ctx, f, name, 64, ctypes.byref(ms), ctypes.byref(n),
+                                             ctypes.byref(fl), ctypes.byref(by))
+            _lib.check(self.ctx, rc, "be_ctx_profile_get")
+            if n.value:
+                out[name.value.decode()] = dict(ms=ms.value, launches=n.value, flops=fl.value, bytes=by.value)
+        return out
+
     def posterior_workspace_bytes(self, B, T, R) -> int:
         return int(self.lib.be_gp_posterior_workspace_bytes(B, T, R))
 
@@ -231,6 +252,16 @@ class Backend:
         rc = self.lib.be_weights_time_mean(self.ctx, _ptr(w), C, M, T, _ptr(out))
         _lib.check(self.ctx, rc, "be_weights_time_mean")
         return out
+
+    def weights_normalise(self, lls_exp, total):
+        le = self._in(lls_exp)
+        C, M, T = le.shape
+        total = self._in(total, (C, T), "total")
+        w = torch.empty_like(le)
+        self._sync_stream()
+        rc = self.lib.be_weights_normalise(self.ctx, _ptr(le), _ptr(total), C, M, T, _ptr(w))
+        _lib.check(self.ctx, rc, "be_weights_normalise")
+        return w
 
     # ------------------------------------------------------------------ a5 / a6
     def barycentre_1d(self, means, variances, weights, tolerance=1e-6, init_var=1.0, max_iters=200):

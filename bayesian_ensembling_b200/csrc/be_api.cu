@@ -3,11 +3,27 @@
 #include <cstdio>
 #include <cstring>
 #include <new>
+#include <vector>
 
 #include "../../include/be_b200.h"
 #include "be_kernels.cuh"
 
 using namespace be;
+
+// kernel families of the profiler (be_ctx_profile_*): one per kernel of be_kernels.cuh
+enum Family {
+    F_INPUTS = 0, F_GRAM, F_DIAG, F_PANEL, F_SYRK, F_TRTRI, F_LAUUM, F_MEAN, F_STATS, F_COPY, F_WEIGHTS, F_BARY,
+    F_COUNT
+};
+static const char* const kFamilyName[F_COUNT] = {
+    "k_gpdtw1d_inputs", "k_matern32", "k_diag_block", "k_panel_scale", "k_syrk_trailing", "k_trtri_accum",
+    "k_lauum_cov", "k_posterior_mean", "k_mvn_stats", "copy/pad", "k_loglik_weights", "k_barycentre"};
+
+struct ProfRecord {
+    int family;
+    cudaEvent_t e0, e1;
+    double flops, bytes;
+};
 
 struct be_ctx {
     int device;
@@ -15,6 +31,11 @@ struct be_ctx {
     int sm_count;
     long long launches;
     char err[256];
+    bool profiling;
+    std::vector<ProfRecord> records;   // launches bracketed since the last reset
+    std::vector<cudaEvent_t> ev_pool;  // recycled events
+    double fam_ms[F_COUNT], fam_flops[F_COUNT], fam_bytes[F_COUNT];
+    long long fam_launches[F_COUNT];
 };
 
 namespace {
@@ -53,6 +74,38 @@ struct Carver {
     }
 };
 
+// Brackets ONE kernel launch with CUDA events on the ctx stream when profiling is on, and books
+// the launch's ALGORITHMIC flops / HBM bytes (DESIGN.md "Roofline accounting") to its family.
+struct Prof {
+    be_ctx* ctx;
+    ProfRecord rec;
+    bool on;
+    Prof(be_ctx* c, int family, double flops, double bytes) : ctx(c), on(c->profiling) {
+        if (!on) return;
+        rec.family = family;
+        rec.flops = flops;
+        rec.bytes = bytes;
+        rec.e0 = take();
+        rec.e1 = take();
+        cudaEventRecord(rec.e0, ctx->stream);
+    }
+    ~Prof() {
+        if (!on) return;
+        cudaEventRecord(rec.e1, ctx->stream);
+        ctx->records.push_back(rec);
+    }
+    cudaEvent_t take() {
+        cudaEvent_t e;
+        if (!ctx->ev_pool.empty()) {
+            e = ctx->ev_pool.back();
+            ctx->ev_pool.pop_back();
+        } else {
+            cudaEventCreate(&e);
+        }
+        return e;
+    }
+};
+
 inline unsigned grid1d(size_t n, int block) { return (unsigned)((n + block - 1) / block); }
 
 bool g_attr_done = false;
@@ -77,16 +130,27 @@ inline size_t matern_smem(int R) { return ((size_t)2 * NB * (R | 1) + 2 * NB) * 
 int potrf_padded(be_ctx* ctx, double* Mat, int Tp, int T, int B, double* Dinv, double* V, int* info) {
     const int ld = Tp, nblk = num_blocks(Tp);
     for (int kb = 0; kb < nblk; ++kb) {
-        k_diag_block<<<B, 256, DIAG_SMEM_BYTES, ctx->stream>>>(Mat, ld, Tp, T, kb, Dinv, nblk, V, info);
-        BE_LAUNCHED();
+        const double kw = (double)(Tp - kb * NB < NB ? Tp - kb * NB : NB);
+        const double nrem = (double)Tp - kb * NB - kw;  // rows below the diagonal block
+        {
+            Prof pr(ctx, F_DIAG, B * (2.0 / 3.0) * kw * kw * kw, B * 3.0 * kw * kw * 8);
+            k_diag_block<<<B, 256, DIAG_SMEM_BYTES, ctx->stream>>>(Mat, ld, Tp, T, kb, Dinv, nblk, V, info);
+            BE_LAUNCHED();
+        }
         int t = nblk - kb - 1;
         if (t > 0) {
-            k_panel_scale<<<(unsigned)((size_t)t * B), GEMM_THREADS, GEMM_SMEM_BYTES, ctx->stream>>>(
-                Mat, ld, Tp, kb + 1, kb, Dinv, nblk, 1.0, B);
-            BE_LAUNCHED();
-            k_syrk_trailing<<<(unsigned)((size_t)t * (t + 1) / 2 * B), GEMM_THREADS, GEMM_SMEM_BYTES, ctx->stream>>>(
-                Mat, ld, Tp, kb, B);
-            BE_LAUNCHED();
+            {
+                Prof pr(ctx, F_PANEL, B * nrem * kw * kw, B * (2.0 * nrem * kw + kw * kw) * 8);
+                k_panel_scale<<<(unsigned)((size_t)t * B), GEMM_THREADS, GEMM_SMEM_BYTES, ctx->stream>>>(
+                    Mat, ld, Tp, kb + 1, kb, Dinv, nblk, 1.0, B);
+                BE_LAUNCHED();
+            }
+            {
+                Prof pr(ctx, F_SYRK, B * nrem * (nrem + 1.0) * kw, B * (nrem * (nrem + 1.0) + nrem * kw) * 8);
+                k_syrk_trailing<<<(unsigned)((size_t)t * (t + 1) / 2 * B), GEMM_THREADS, GEMM_SMEM_BYTES,
+                                  ctx->stream>>>(Mat, ld, Tp, kb, B);
+                BE_LAUNCHED();
+            }
         }
     }
     return BE_OK;
@@ -96,11 +160,21 @@ int potrf_padded(be_ctx* ctx, double* Mat, int Tp, int T, int B, double* Dinv, d
 int trtri_padded(be_ctx* ctx, double* V, const double* Cm, int Tp, int B, const double* Dinv) {
     const int ld = Tp, nblk = num_blocks(Tp);
     for (int i = 1; i < nblk; ++i) {
-        k_trtri_accum<<<(unsigned)((size_t)i * B), GEMM_THREADS, GEMM_SMEM_BYTES, ctx->stream>>>(V, Cm, ld, Tp, i, B);
-        BE_LAUNCHED();
-        k_panel_scale<<<(unsigned)((size_t)i * B), GEMM_THREADS, GEMM_SMEM_BYTES, ctx->stream>>>(V, ld, Tp, 0, i, Dinv,
-                                                                                               nblk, -1.0, B);
-        BE_LAUNCHED();
+        const double kw = (double)(Tp - i * NB < NB ? Tp - i * NB : NB);
+        const double above = (double)i * NB;  // rows of V above block i
+        {
+            // algorithmic: triangular (above x above, upper) times (above x kw): above^2 * kw flops
+            Prof pr(ctx, F_TRTRI, B * above * above * kw, B * (0.5 * above * above + 2.0 * above * kw) * 8);
+            k_trtri_accum<<<(unsigned)((size_t)i * B), GEMM_THREADS, GEMM_SMEM_BYTES, ctx->stream>>>(V, Cm, ld, Tp, i,
+                                                                                                   B);
+            BE_LAUNCHED();
+        }
+        {
+            Prof pr(ctx, F_PANEL, B * above * kw * kw, B * (2.0 * above * kw + kw * kw) * 8);
+            k_panel_scale<<<(unsigned)((size_t)i * B), GEMM_THREADS, GEMM_SMEM_BYTES, ctx->stream>>>(
+                V, ld, Tp, 0, i, Dinv, nblk, -1.0, B);
+            BE_LAUNCHED();
+        }
     }
     return BE_OK;
 }
@@ -125,6 +199,8 @@ int be_ctx_create(int device, void* stream, be_ctx** out) {
     ctx->stream = (cudaStream_t)stream;
     ctx->launches = 0;
     ctx->err[0] = 0;
+    ctx->profiling = false;
+    for (int f = 0; f < F_COUNT; ++f) ctx->fam_ms[f] = ctx->fam_flops[f] = ctx->fam_bytes[f] = 0.0, ctx->fam_launches[f] = 0;
     cudaError_t e = cudaSetDevice(device);
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
     if (e != cudaSuccess) {
@@ -148,7 +224,64 @@ int be_ctx_set_stream(be_ctx* ctx, void* stream) {
 }
 
 int be_ctx_destroy(be_ctx* ctx) {
+    if (ctx) {
+        for (auto& r : ctx->records) {
+            cudaEventDestroy(r.e0);
+            cudaEventDestroy(r.e1);
+        }
+        for (auto e : ctx->ev_pool) cudaEventDestroy(e);
+    }
     delete ctx;
+    return BE_OK;
+}
+
+int be_ctx_profile_enable(be_ctx* ctx, int on) {
+    if (!ctx) return -1;
+    ctx->profiling = on != 0;
+    return BE_OK;
+}
+
+// folds the pending event pairs into the per-family totals (synchronises the stream)
+static int profile_collect(be_ctx* ctx) {
+    if (ctx->records.empty()) return BE_OK;
+    BE_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (auto& r : ctx->records) {
+        float ms = 0.f;
+        BE_CUDA(cudaEventElapsedTime(&ms, r.e0, r.e1));
+        ctx->fam_ms[r.family] += ms;
+        ctx->fam_flops[r.family] += r.flops;
+        ctx->fam_bytes[r.family] += r.bytes;
+        ctx->fam_launches[r.family] += 1;
+        ctx->ev_pool.push_back(r.e0);
+        ctx->ev_pool.push_back(r.e1);
+    }
+    ctx->records.clear();
+    return BE_OK;
+}
+
+int be_ctx_profile_reset(be_ctx* ctx) {
+    if (!ctx) return -1;
+    int rc = profile_collect(ctx);
+    for (int f = 0; f < F_COUNT; ++f) ctx->fam_ms[f] = ctx->fam_flops[f] = ctx->fam_bytes[f] = 0.0, ctx->fam_launches[f] = 0;
+    return rc;
+}
+
+int be_ctx_profile_families(void) { return F_COUNT; }
+
+int be_ctx_profile_get(be_ctx* ctx, int family, char* name, size_t name_len, double* ms_total,
+                       long long* launches, double* flops, double* bytes) {
+    if (!ctx) return -1;
+    if (family < 0 || family >= F_COUNT) return -2;
+    int rc = profile_collect(ctx);
+    if (rc != BE_OK) return rc;
+    if (name && name_len) {
+        strncpy(name, kFamilyName[family], name_len - 1);
+        name[name_len - 1] = 0;
+    }
+    if (ms_total) *ms_total = ctx->fam_ms[family];
+    if (launches) *launches = ctx->fam_launches[family];
+    if (flops) *flops = ctx->fam_flops[family];
+    if (bytes) *bytes = ctx->fam_bytes[family];
     return BE_OK;
 }
 
@@ -168,6 +301,7 @@ int be_gpdtw1d_inputs(be_ctx* ctx, const double* realisations, int B, int R, int
     if (B <= 0) return -3;
     if (R <= 0) return -4;
     if (T <= 0) return -5;
+    Prof pr(ctx, F_INPUTS, 4.0 * B * R * T, (2.0 * B * R * T + 2.0 * B * T) * 8);
     k_gpdtw1d_inputs<<<grid1d((size_t)B * T, 256), 256, 0, ctx->stream>>>(realisations, B, R, T, X, y_mean, y_var);
     BE_LAUNCHED();
     return BE_OK;
@@ -184,6 +318,7 @@ int be_matern32_gram(be_ctx* ctx, const double* X, int B, int T, int R, const do
     if (!lengthscale) return -7;
     if (!K) return -8;
     int nt = (T + NB - 1) / NB;
+    Prof pr(ctx, F_GRAM, (double)B * T * T * (2.0 * R + 12.0), ((double)B * T * R + (double)B * T * T) * 8);
     k_matern32<0><<<(unsigned)((size_t)nt * nt * B), 256, matern_smem(R), ctx->stream>>>(
         X, B, T, R, variance, lengthscale, nullptr, nullptr, 0.0, K, 0, 0, nt * nt);
     BE_LAUNCHED();
@@ -257,31 +392,50 @@ int be_gp_posterior(be_ctx* ctx, const double* X, const double* y_mean, const do
 
     // 1. M = K + D + jitter I (lower tiles), row T = y_mean
     const int ntl = nblk * (nblk + 1) / 2;
-    k_matern32<1><<<(unsigned)((size_t)ntl * B), 256, matern_smem(R), ctx->stream>>>(
-        X, B, T, R, variance, lengthscale, y_mean, y_var, jitter, Mw, Tp, ld, ntl);
-    BE_LAUNCHED();
+    const double dT = (double)T, dB = (double)B;
+    {
+        // lower triangle only: T^2/2 entries computed and written
+        Prof pr(ctx, F_GRAM, dB * 0.5 * dT * dT * (2.0 * R + 12.0), (dB * dT * R + dB * 0.5 * dT * dT) * 8);
+        k_matern32<1><<<(unsigned)((size_t)ntl * B), 256, matern_smem(R), ctx->stream>>>(
+            X, B, T, R, variance, lengthscale, y_mean, y_var, jitter, Mw, Tp, ld, ntl);
+        BE_LAUNCHED();
+    }
     // 2. C = chol(M); row T becomes u = C^-1 y; V diagonal tiles
     int rc = potrf_padded(ctx, Mw, Tp, T, B, Dinv, Vw, info_fit);
     if (rc != BE_OK) return rc;
-    k_extract_row<<<grid1d((size_t)B * T, 256), 256, 0, ctx->stream>>>(Mw, ld, Tp, T, T, u, B, 1);
-    BE_LAUNCHED();
+    {
+        Prof pr(ctx, F_COPY, 0.0, dB * dT * 16);
+        k_extract_row<<<grid1d((size_t)B * T, 256), 256, 0, ctx->stream>>>(Mw, ld, Tp, T, T, u, B, 1);
+        BE_LAUNCHED();
+    }
     // 3. V = C^-T
     rc = trtri_padded(ctx, Vw, Mw, Tp, B, Dinv);
     if (rc != BE_OK) return rc;
     // 4. mean = y - E V u
-    k_posterior_mean<<<grid1d((size_t)B * T, 8), 256, 0, ctx->stream>>>(Vw, ld, Tp, T, u, y_mean, y_var, jitter, mu,
-                                                                        B);
-    BE_LAUNCHED();
+    {
+        Prof pr(ctx, F_MEAN, dB * dT * dT, dB * (0.5 * dT * dT + 4.0 * dT) * 8);
+        k_posterior_mean<<<grid1d((size_t)B * T, 8), 256, 0, ctx->stream>>>(Vw, ld, Tp, T, u, y_mean, y_var, jitter,
+                                                                            mu, B);
+        BE_LAUNCHED();
+    }
     // 5. cov = D + E - E (V V^T) E  -> Mw (padded, rows T/T+1 = 1, mu), var_diag, dense cov
-    k_lauum_cov<<<(unsigned)((size_t)ntl * B), GEMM_THREADS, GEMM_SMEM_BYTES, ctx->stream>>>(
-        Vw, ld, Tp, T, y_var, jitter, mu, Mw, var_diag, cov, B);
-    BE_LAUNCHED();
+    {
+        // lauum: T^3/3 flops; reads V (upper, T^2/2), writes the padded lower cov (+ dense cov if asked)
+        Prof pr(ctx, F_LAUUM, dB * dT * dT * dT / 3.0, dB * dT * dT * (cov ? 2.0 : 1.0) * 8);
+        k_lauum_cov<<<(unsigned)((size_t)ntl * B), GEMM_THREADS, GEMM_SMEM_BYTES, ctx->stream>>>(
+            Vw, ld, Tp, T, y_var, jitter, mu, Mw, var_diag, cov, B);
+        BE_LAUNCHED();
+    }
     // 6. scale_tri = chol(cov) (data.py:38-39); rows T/T+1 become a = L^-1 1, b = L^-1 mu
     rc = potrf_padded(ctx, Mw, Tp, T, B, Dinv, nullptr, info_dist);
     if (rc != BE_OK) return rc;
-    k_mvn_stats<<<B, 256, 0, ctx->stream>>>(Mw, ld, Tp, T, mvn_stats);
-    BE_LAUNCHED();
+    {
+        Prof pr(ctx, F_STATS, 8.0 * dB * dT, dB * 3.0 * dT * 8);
+        k_mvn_stats<<<B, 256, 0, ctx->stream>>>(Mw, ld, Tp, T, mvn_stats);
+        BE_LAUNCHED();
+    }
     if (scale_tri) {
+        Prof pr(ctx, F_COPY, 0.0, dB * 1.5 * dT * dT * 8);
         k_copy_out_tri<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(Mw, ld, Tp, T, scale_tri, B);
         BE_LAUNCHED();
     }
@@ -333,6 +487,9 @@ int be_loglik_weights_mvn(be_ctx* ctx, const double* mvn_stats, const double* ob
     if (Ro <= 0) return -6;
     if (T <= 0) return -7;
     if (!weights) return -9;
+    const int nout = 1 + (lls_exp ? 1 : 0) + (lls_mean ? 1 : 0);
+    Prof pr(ctx, F_WEIGHTS, (double)C * M * T * (8.0 * Ro + 24.0),
+            ((double)C * Ro * T + (double)C * M * 4 + (double)(nout + 1) * C * M * T) * 8);
     k_loglik_weights_mvn<<<grid1d((size_t)C * T, 128), 128, 0, ctx->stream>>>(
         mvn_stats, obs, C, M, Ro, T, standardisation_constant, weights, lls_exp, lls_mean);
     BE_LAUNCHED();
@@ -397,6 +554,19 @@ int be_weights_time_mean(be_ctx* ctx, const double* weights, int C, int M, int T
     return BE_OK;
 }
 
+int be_weights_normalise(be_ctx* ctx, const double* lls_exp, const double* total, int C, int M, int T, double* weights) {
+    if (!ctx) return -1;
+    if (!lls_exp) return -2;
+    if (!total) return -3;
+    if (C <= 0) return -4;
+    if (M <= 0) return -5;
+    if (T <= 0) return -6;
+    if (!weights) return -7;
+    k_weights_normalise<<<grid1d((size_t)C * M * T, 256), 256, 0, ctx->stream>>>(lls_exp, total, C, M, T, weights);
+    BE_LAUNCHED();
+    return BE_OK;
+}
+
 int be_barycentre_1d(be_ctx* ctx, const double* means, const double* variances, const double* weights, int C, int M,
                      int N, double tolerance, double init_var, int max_iters, double* mu, double* sigma, int* iters) {
     if (!ctx) return -1;
@@ -408,6 +578,8 @@ int be_barycentre_1d(be_ctx* ctx, const double* means, const double* variances, 
     if (N <= 0) return -7;
     if (!mu) return -11;
     if (!sigma) return -12;
+    // 24*M + 16 bytes per (cell, time) point
+    Prof pr(ctx, F_BARY, 4.0 * C * M * N, (double)C * N * (24.0 * M + 16.0));
     k_barycentre_1d<<<grid1d((size_t)C * N, 128), 128, 0, ctx->stream>>>(means, variances, weights, C, M, N, tolerance,
                                                                          init_var, max_iters, mu, sigma, iters);
     BE_LAUNCHED();

@@ -571,6 +571,16 @@ __global__ void k_loglik_weights_normal(const double* __restrict__ loc, const do
     }
 }
 
+// member-sharded normalisation: w = lls_exp / total  (weights.py:122-123 after an all-reduce of the sum)
+__global__ void k_weights_normalise(const double* __restrict__ lls_exp, const double* __restrict__ total, int C, int M,
+                                    int T, double* __restrict__ w) {
+    size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= (size_t)C * M * T) return;
+    int i = (int)(gid % T);
+    int c = (int)(gid / ((size_t)M * T));
+    w[gid] = lls_exp[gid] / total[(size_t)c * T + i];
+}
+
 // xarray .mean('time') skips NaN (utils.py:111); broadcast back over time (utils.py:133)
 __global__ void __launch_bounds__(256) k_weights_time_mean(const double* __restrict__ w, int CM, int T,
                                                            double* __restrict__ out) {

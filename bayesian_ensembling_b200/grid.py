@@ -1,0 +1,140 @@
+"""Batched entry point: fit -> weight -> barycentre for many grid cells at once.
+
+The reference fits one member at a time in a Python loop (ensembles/data.py:391-395) and has
+no per-cell driver at all; a B200 needs thousands of independent (cell, member) problems in
+flight, so this module adds the batched call SURVEY 8b asks for.  Cells never interact, so
+work is sharded across GPUs BY CELL with no collective; when there are fewer cells than GPUs
+(BASELINE configs 1, 2, 5) members are sharded instead and ONE all-reduce of three partial
+sums per (cell, time) joins them.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+
+from .backend import Backend, DEFAULT_JITTER
+
+
+@dataclass
+class CellBatchResult:
+    weights: torch.Tensor  # [C,M,T]  LogLikelihoodWeight
+    bary_mu: torch.Tensor  # [C,T]    Barycentre mean
+    bary_std: torch.Tensor  # [C,T]   Barycentre std (the reference stores std**2 as "covariance")
+    bary_iters: torch.Tensor  # [C,T] int32
+    mu: torch.Tensor  # [C,M,T] posterior means
+    var_diag: torch.Tensor  # [C,M,T] posterior variances
+    info_fit: torch.Tensor  # [C,M] int32
+    info_dist: torch.Tensor  # [C,M] int32
+    cov: torch.Tensor | None = None  # [C,M,T,T] if keep_posteriors
+    scale_tri: torch.Tensor | None = None
+
+
+def shard_range(n: int, rank: int, world: int):
+    """Static block partition of ``n`` uniform work items (cells or members)."""
+    base, rem = divmod(n, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def _per_problem(x, C, M, device):
+    """scalar | [M] | [C,M]  ->  [C*M] device tensor"""
+    t = torch.as_tensor(x, dtype=torch.float64, device=device)
+    if t.ndim == 0:
+        t = t.expand(C, M)
+    elif t.ndim == 1:
+        t = t[None, :].expand(C, M)
+    return t.reshape(C * M).contiguous()
+
+
+def wave_size(be: Backend, C: int, M: int, R: int, T: int, keep_posteriors: bool, budget_bytes: int | None = None):
+    """Cells per wave so that workspace + outputs stay inside the memory budget (180 GB HBM3e
+    holds ~1400 T=1980 problems with both work matrices resident)."""
+    if budget_bytes is None:
+        free, _total = torch.cuda.mem_get_info(be.device)
+        budget_bytes = int(free * 0.8)
+    per_cell = be.posterior_workspace_bytes(M, T, R) + (2 * M * T * T * 8 if keep_posteriors else 0) + 64 * M * T
+    return max(1, min(C, budget_bytes // max(per_cell, 1)))
+
+
+def fit_weight_barycentre(realisations, observations, variance, lengthscale, *, jitter=DEFAULT_JITTER,
+                          standardisation_constant=1.0, time_mean_weights=False, keep_posteriors=False,
+                          cells_per_wave=None, tolerance=1e-6, init_var=1.0) -> CellBatchResult:
+    """realisations [C,M,R,T], observations [C,Ro,T] (host arrays or device tensors);
+    variance / lengthscale: scalar, [M] or [C,M] kernel hyper-parameters (fixed-theta posterior,
+    the fixed point of models.py:208-215).  Order of operations follows
+    ``PerfectModelTest._run_single_test`` (utils.py:102-135); ``time_mean_weights`` reproduces
+    utils.py:111,133 (NaN-skipping mean over time, broadcast back)."""
+    be = Backend.get()
+    r = be._in(realisations)
+    o = be._in(observations)
+    C, M, R, T = r.shape
+    Ro = o.shape[1]
+    var = _per_problem(variance, C, M, be.device)
+    ls = _per_problem(lengthscale, C, M, be.device)
+    if cells_per_wave is None:
+        cells_per_wave = wave_size(be, C, M, R, T, keep_posteriors)
+    outs = []
+    for c0 in range(0, C, cells_per_wave):
+        c1 = min(C, c0 + cells_per_wave)
+        Cw = c1 - c0
+        X, ym, yv = be.gpdtw1d_inputs(r[c0:c1].reshape(Cw * M, R, T))
+        post = be.gp_posterior(X, ym, yv, var[c0 * M:c1 * M], ls[c0 * M:c1 * M], jitter,
+                               want_cov=keep_posteriors, want_scale_tri=keep_posteriors)
+        w = be.loglik_weights_mvn(post.mvn_stats, o[c0:c1], M, standardisation_constant)
+        w_used = be.weights_time_mean(w) if time_mean_weights else w
+        mu3, var3 = post.mu.view(Cw, M, T), post.var_diag.view(Cw, M, T)
+        bmu, bsd, bit = be.barycentre_1d(mu3, var3, w_used, tolerance, init_var, 200)
+        outs.append(CellBatchResult(
+            weights=w, bary_mu=bmu, bary_std=bsd, bary_iters=bit, mu=mu3, var_diag=var3,
+            info_fit=post.info_fit.view(Cw, M), info_dist=post.info_dist.view(Cw, M),
+            cov=post.cov.view(Cw, M, T, T) if keep_posteriors else None,
+            scale_tri=post.scale_tri.view(Cw, M, T, T) if keep_posteriors else None))
+    if len(outs) == 1:
+        return outs[0]
+    cat = lambda name: (None if getattr(outs[0], name) is None else torch.cat([getattr(x, name) for x in outs]))  # noqa: E731
+    return CellBatchResult(**{k: cat(k) for k in CellBatchResult.__dataclass_fields__})
+
+
+def fit_weight_barycentre_member_sharded(realisations_local, observations, variance_local, lengthscale_local, *,
+                                         group=None, jitter=DEFAULT_JITTER, standardisation_constant=1.0,
+                                         time_mean_weights=False, tolerance=1e-6, init_var=1.0,
+                                         all_reduce=None) -> CellBatchResult:
+    """Member-sharded form for few-cell configs: every rank holds ``M_local`` members of ALL C
+    cells.  The only exchange is one all-reduce (sum, fp64) of the packed partial sums
+    ``[3,C,T] = (sum w~, sum w~ mu, sum w~ sigma)`` -- NCCL over NVLink when launched under
+    torchrun; ``all_reduce`` can be injected (tests use gloo on CPU tensors).  With
+    ``time_mean_weights`` the normaliser must be known before the time mean, so there are two
+    small all-reduces."""
+    import torch.distributed as dist
+
+    be = Backend.get()
+    r = be._in(realisations_local)
+    o = be._in(observations)
+    C, Ml, R, T = r.shape
+    if all_reduce is None:
+        def all_reduce(t):
+            if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+            return t
+    var = _per_problem(variance_local, C, Ml, be.device)
+    ls = _per_problem(lengthscale_local, C, Ml, be.device)
+    X, ym, yv = be.gpdtw1d_inputs(r.reshape(C * Ml, R, T))
+    post = be.gp_posterior(X, ym, yv, var, ls, jitter, want_cov=False, want_scale_tri=False)
+    _, lls_exp, _ = be.loglik_weights_mvn(post.mvn_stats, o, Ml, standardisation_constant, want_lls=True)
+    mu3, var3 = post.mu.view(C, Ml, T), post.var_diag.view(C, Ml, T)
+    partial = be.barycentre_1d_partial(mu3, var3, lls_exp)
+    if not time_mean_weights:
+        partial = all_reduce(partial)
+        w = be.weights_normalise(lls_exp, partial[0])
+    else:
+        total = all_reduce(partial[0].clone())
+        w = be.weights_normalise(lls_exp, total)
+        w_bar = be.weights_time_mean(w)
+        partial = be.barycentre_1d_partial(mu3, var3, w_bar)
+        partial = all_reduce(partial)
+        partial[0].fill_(1.0)  # utils.py:119: time-mean weights are used un-renormalised
+    bmu, bsd, bit = be.barycentre_1d_finish(partial, tolerance, init_var, 200)
+    return CellBatchResult(weights=w, bary_mu=bmu, bary_std=bsd, bary_iters=bit, mu=mu3, var_diag=var3,
+                           info_fit=post.info_fit.view(C, Ml), info_dist=post.info_dist.view(C, Ml))

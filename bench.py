@@ -1,0 +1,367 @@
+#!/usr/bin/env python
+"""Benchmark of the fit -> weight -> barycentre hot path (BASELINE.json metric: grid-cells/s).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --steps K --warmup W     # the CPU arm (oracle port, host cores)
+
+Workload (N=1 and every N, weak scaling): BASELINE.json configs[1] -- single-location monthly
+series, 24 CMIP6-shaped members x 5 realisations x 3012 months, full-covariance GP posterior per
+member, 10 observation realisations -- batched ``--cells-per-step`` cells per GPU per step.  A
+"step" is one pass of gpdtw1d_inputs -> gp_posterior (gram, Cholesky, inverse, covariance,
+distribution Cholesky) -> LogLikelihoodWeight -> Barycentre over that batch.  Cells are sharded
+across ranks (they never interact), so there is no collective on the data path.
+
+One JSON line on stdout (rank 0).  ``value`` = cells/s with inputs resident in HBM; ``e2e`` = the
+same through the public batched API with pinned HOST buffers (H2D + D2H inside the timed region).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "grid_cells_per_sec_fit_weight_barycentre"
+UNIT = "cells/s"
+FP64_PEAK_TFLOPS = 37.15  # DMMA issue-rate peak measured on this pool: profiles/r01_ubench_fp64.txt
+
+
+def _hbm_peak():
+    try:
+        return float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+def workload_config(cfg, cells_per_step, n_gpus):
+    return {
+        "workload": f"{cfg.name}: {cfg.description}",
+        "cells_per_step_per_gpu": cells_per_step,
+        "members": cfg.members, "realisations": cfg.realisations, "time_steps": cfg.steps,
+        "obs_realisations": cfg.obs_realisations,
+        "fit_level": "L1 fixed kernel hyper-parameters (variance 0.5, lengthscale 6.0): posterior + "
+                     "distribution Cholesky + LogLikelihoodWeight + Barycentre",
+        "sharding": "cells across ranks, no collective" if n_gpus > 1 else "single GPU",
+        "l2": "inputs+workspace per step >> 126 MB L2 (each member's work matrices are 2 x 73 MB)",
+    }
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons of one GPU every 200 ms while the timed region runs."""
+
+    REASONS = {
+        0x2: "applications_clocks_setting", 0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x10: "sync_boost",
+        0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown", 0x80: "hw_power_brake_slowdown",
+        0x100: "display_clock_setting",
+    }
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.stop_flag = index, [], set(), threading.Event()
+        self.max_mhz = None
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        while not self.stop_flag.is_set():
+            try:
+                self.samples.append(float(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM)))
+                mask = int(self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                for bit, name in self.REASONS.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
+
+    def summary(self):
+        self.stop_flag.set()
+        if self.nv is None or not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["unavailable"]}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference arithmetic, all host threads
+# ------------------------------------------------------------------------------------------------
+def _blas_threads():
+    try:
+        from threadpoolctl import threadpool_info
+
+        infos = [i for i in threadpool_info() if i.get("user_api") == "blas"]
+        return max([i.get("num_threads", 1) for i in infos] or [1]), (infos[0].get("internal_api") if infos else "?")
+    except Exception:
+        return os.cpu_count() or 1, "?"
+
+
+def cpu_sample_seconds(cfg, members, repeats=1):
+    """Oracle fit -> weight -> barycentre on ``members`` members of cell 0 (bounded sample)."""
+    from bayesian_ensembling_b200 import synthetic
+    from oracle import reference_path as rp
+
+    reals, obs = synthetic.make_cells(cfg, n_cells=1)
+    best = float("inf")
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        rp.cell_pipeline_L1(reals[0, :members], obs[0], synthetic.L1_VARIANCE, synthetic.L1_LENGTHSCALE)
+        best = min(best, time.perf_counter() - t0)
+    return best
+
+
+def run_reference(args, cfg):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads, blas = _blas_threads()
+    m = args.cpu_members
+    for _ in range(args.warmup):
+        cpu_sample_seconds(cfg, m)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_sample_seconds(cfg, m)
+    dt = (time.perf_counter() - t0) / args.steps
+    cell_s = dt * cfg.members / m
+    value = 1.0 / cell_s
+    sample = (f"{m} of {cfg.members} members of one {cfg.name} cell per step (T={cfg.steps}, Ro={cfg.obs_realisations}), "
+              f"scaled x{cfg.members / m:.0f} to a cell")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(cfg, args.cells_per_step, args.gpus),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
+                         "blas": blas, "host_cpus": os.cpu_count(),
+                         "note": "NumPy/SciPy oracle restating the reference arithmetic; the reference itself "
+                                 "(GPflow/TF/JAX) cannot be installed here"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+TENSOR_FAMILIES = {"k_syrk_trailing", "k_trtri_accum", "k_lauum_cov", "k_panel_scale", "k_diag_block",
+                   "k_chol_update", "k_tri_gemm"}
+
+
+def run_ours(args, cfg):
+    import torch
+    import torch.distributed as dist
+
+    from bayesian_ensembling_b200 import grid, synthetic
+    from bayesian_ensembling_b200.backend import Backend
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    be = Backend.get()
+    dev = be.device
+    cps = args.cells_per_step
+    reals, obs = synthetic.make_cells(cfg, n_cells=cps, cell_offset=rank * cps)
+    var, ls = synthetic.L1_VARIANCE, synthetic.L1_LENGTHSCALE
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    # ---- device-resident arm -------------------------------------------------------------------
+    r_dev = torch.as_tensor(reals, device=dev)
+    o_dev = torch.as_tensor(obs, device=dev)
+
+    def step_device():
+        return grid.fit_weight_barycentre(r_dev, o_dev, var, ls, cells_per_wave=cps)
+
+    for _ in range(args.warmup):
+        res = step_device()
+    barrier()
+    assert int(res.info_fit.abs().sum()) == 0 and int(res.info_dist.abs().sum()) == 0, "non-PD matrix in the bench"
+    be.profile(True)
+    be.profile_reset()
+    sampler = ClockSampler(local)
+    sampler.start()
+    l0 = be.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        res = step_device()
+    e1.record()
+    barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1))
+    launches = be.launch_count - l0
+    clocks = sampler.summary()
+    prof = be.profile_read()
+    be.profile(False)
+    value = world * cps * args.steps / (ms * 1e-3)
+
+    # ---- end-to-end arm: pinned host buffers through the public batched API ------------------------
+    r_pin = torch.as_tensor(reals).pin_memory()
+    o_pin = torch.as_tensor(obs).pin_memory()
+    out_w = torch.empty((cps, cfg.members, cfg.steps), dtype=torch.float64).pin_memory()
+    out_mu = torch.empty((cps, cfg.steps), dtype=torch.float64).pin_memory()
+    out_sd = torch.empty((cps, cfg.steps), dtype=torch.float64).pin_memory()
+
+    def step_e2e():
+        r = grid.fit_weight_barycentre(r_pin, o_pin, var, ls, cells_per_wave=cps)
+        out_w.copy_(r.weights, non_blocking=True)
+        out_mu.copy_(r.bary_mu, non_blocking=True)
+        out_sd.copy_(r.bary_std, non_blocking=True)
+        torch.cuda.synchronize()
+
+    step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_e2e()
+    barrier()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    e2e_value = world * cps * args.steps / e2e_s
+    h2d = (r_pin.numel() + o_pin.numel()) * 8
+    d2h = (out_w.numel() + out_mu.numel() + out_sd.numel()) * 8
+    nan_frac = float(np.isnan(out_w.numpy()).mean())
+
+    # ---- roofline of the dominant kernel -------------------------------------------------------
+    hbm_peak, hbm_src = _hbm_peak()
+    stages = {}
+    for name, p in prof.items():
+        per_launch_ms = p["ms"] / p["launches"]
+        tensor = name in TENSOR_FAMILIES
+        stages[name] = {
+            "ms_per_step": p["ms"] / args.steps, "launches_per_step": p["launches"] / args.steps,
+            "share": p["ms"] / max(sum(q["ms"] for q in prof.values()), 1e-30),
+            "tflops": p["flops"] / p["ms"] / 1e9 if p["ms"] > 0 else None,
+            "gbs": p["bytes"] / p["ms"] / 1e6 if p["ms"] > 0 else None,
+            "bound": "tensor" if tensor else "hbm", "avg_launch_ms": per_launch_ms,
+        }
+    top = max(prof, key=lambda k: prof[k]["ms"]) if prof else None
+    roofline = None
+    if top:
+        p = prof[top]
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(top)
+        except Exception:
+            pass
+        if top in TENSOR_FAMILIES:
+            achieved = p["flops"] / p["ms"] / 1e9
+            roofline = {"kernel": top, "bound": "tensor", "achieved": achieved, "peak": FP64_PEAK_TFLOPS,
+                        "unit": "TFLOP/s", "frac": achieved / FP64_PEAK_TFLOPS, "traffic": traffic,
+                        "peak_source": "FP64 DMMA issue-rate measured on this pool by tools/ubench_fp64.cu "
+                                       "(profiles/r01_ubench_fp64.txt); MEASURED_PEAKS.json carries no fp64 figure; "
+                                       "cuBLAS DGEMM 8192^3 measured 35.5 (profiles/r01_peak_fp64.json)",
+                        "flops_per_launch": p["flops"] / p["launches"], "avg_launch_ms": p["ms"] / p["launches"],
+                        "share_of_step": stages[top]["share"]}
+        else:
+            achieved = p["bytes"] / p["ms"] / 1e6
+            roofline = {"kernel": top, "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                        "frac": achieved / hbm_peak, "traffic": traffic, "peak_source": f"MEASURED_PEAKS.json ({hbm_src})",
+                        "bytes_per_launch": p["bytes"] / p["launches"], "avg_launch_ms": p["ms"] / p["launches"],
+                        "share_of_step": stages[top]["share"]}
+    tensor_ms = sum(p["ms"] for n, p in prof.items() if n in TENSOR_FAMILIES)
+    tensor_flops = sum(p["flops"] for n, p in prof.items() if n in TENSOR_FAMILIES)
+    total_launches = sum_over_ranks(float(launches))
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        threads, blas = _blas_threads()
+        m = args.cpu_members
+        dt = cpu_sample_seconds(cfg, m)
+        cpu_baseline = {
+            "value": 1.0 / (dt * cfg.members / m), "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": f"{m} of {cfg.members} members of one {cfg.name} cell (T={cfg.steps}, Ro={cfg.obs_realisations}): "
+                      f"{dt:.1f} s, scaled x{cfg.members / m:.0f} to a cell",
+            "blas": blas, "host_cpus": os.cpu_count()}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(cfg, cps, world),
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "weights_nan_fraction": nan_frac,
+                    "note": "at T=3012 every member's constant-vector log-likelihood is < -745, so exp() underflows "
+                            "and the reference's un-guarded normalisation gives 0/0 = NaN (quirk Q-EXP, "
+                            "weights.py:107,122-123) -- reproduced, not repaired"},
+            "gpu_launches": int(total_launches),
+            "roofline": roofline,
+            "fp64_tensor_stage": {"tflops": tensor_flops / tensor_ms / 1e9 if tensor_ms else None,
+                                  "frac_of_peak": tensor_flops / tensor_ms / 1e9 / FP64_PEAK_TFLOPS if tensor_ms else None,
+                                  "share_of_step": tensor_ms / max(sum(q["ms"] for q in prof.values()), 1e-30),
+                                  "note": "all factorisation kernels (Cholesky x2, triangular inverse, lauum) together, "
+                                          "algorithmic flops = 4/3 T^3 per member"},
+            "stages": stages,
+            "cpu_baseline": cpu_baseline,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg2")
+    ap.add_argument("--cells-per-step", type=int, default=6)
+    ap.add_argument("--cpu-members", type=int, default=2, help="members of one cell the CPU arm times per step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 0)
+    from bayesian_ensembling_b200 import synthetic
+
+    cfg = synthetic.CONFIGS[args.workload]
+    if args.impl == "reference":
+        run_reference(args, cfg)
+    else:
+        if args.warmup < 3:
+            args.warmup = 3
+        run_ours(args, cfg)
+
+
+if __name__ == "__main__":
+    main()

@@ -53,6 +53,17 @@ const char* be_ctx_last_error(be_ctx* ctx);
 /* number of kernels this ctx has launched since creation (bench.py's gpu_launches) */
 long long be_ctx_launch_count(be_ctx* ctx);
 
+/* ---- per-kernel timing (bench.py's roofline object) --------------------------------------
+ * While enabled, every kernel launch is bracketed by CUDA events on the ctx stream and its
+ * ALGORITHMIC flops / HBM bytes are booked to the kernel's family (DESIGN.md "Roofline
+ * accounting").  be_ctx_profile_get synchronises the stream and returns the totals since the
+ * last reset for family 0 <= family < be_ctx_profile_families(). */
+int be_ctx_profile_enable(be_ctx* ctx, int on);
+int be_ctx_profile_reset(be_ctx* ctx);
+int be_ctx_profile_families(void);
+int be_ctx_profile_get(be_ctx* ctx, int family, char* name, size_t name_len, double* ms_total,
+                       long long* launches, double* flops, double* bytes);
+
 /* ---- a1 inputs: ensembles/models.py:175-182 -------------------------------------------
  * realisations [B,R,T] -> X [B,T,R] (= realisation_set.T), y_mean [B,T] (arithmetic mean
  * over realisations; the reference's DBA mean, models.py:176-178, is supplied by the caller
@@ -117,6 +128,11 @@ int be_loglik_weights_normal(be_ctx* ctx, const double* loc, const double* scale
 /* mean over the time axis skipping NaN (xarray .mean('time'), ensembles/utils.py:111),
  * broadcast back over time (utils.py:133): w [C,M,T] -> w_bar [C,M,T] */
 int be_weights_time_mean(be_ctx* ctx, const double* weights, int C, int M, int T, double* w_bar);
+
+/* member-sharded normalisation (weights.py:122-123 when the sum over models spans ranks):
+ * weights [C,M_local,T] = lls_exp [C,M_local,T] / total [C,T] */
+int be_weights_normalise(be_ctx* ctx, const double* lls_exp, const double* total, int C, int M, int T,
+                         double* weights);
 
 /* ---- a5/a6: Barycentre._compute + gaussian_barycentre ----------------------------------
  * ensembles/ensemble_scheme.py:54-72 and ensembles/wasserstein.py:61-100 (signed stop

@@ -1,0 +1,357 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle, the reference's golden
+fixtures, and size-independent properties at BASELINE sizes.  Needs a B200: ``-m gpu``.
+
+Tolerances (BASELINE.json north_star): <= 1e-8 relative on posterior mean / variance,
+<= 1e-6 on normalised weights and barycentre moments.  Most checks are far tighter and say so.
+"""
+import warnings
+
+import numpy as np
+import pytest
+
+from bayesian_ensembling_b200 import synthetic
+from oracle import reference_path as rp
+from conftest import rel_err
+
+pytestmark = pytest.mark.gpu
+
+TOL_POSTERIOR = 1e-8
+TOL_WEIGHTS = 1e-6
+
+
+def _t(backend, a):
+    import torch
+
+    return torch.as_tensor(np.ascontiguousarray(a), dtype=torch.float64, device=backend.device)
+
+
+def _cell(M, R, T, Ro, seed, monthly=False):
+    cfg = synthetic.Config("t", 9, 1, M, R, T, Ro, monthly, "")
+    reals, obs = synthetic.make_cells(cfg, seed=seed)
+    return reals[0], obs[0]
+
+
+def _nan_equal_close(got, want, tol, name=""):
+    got, want = np.asarray(got), np.asarray(want)
+    assert got.shape == want.shape, (name, got.shape, want.shape)
+    assert (np.isnan(got) == np.isnan(want)).all(), f"{name}: NaN pattern differs"
+    ok = ~np.isnan(want)
+    if ok.any():
+        err = np.abs(got[ok] - want[ok]).max() / max(np.abs(want[ok]).max(), 1e-300)
+        assert err <= tol, (name, err)
+
+
+# ------------------------------------------------------------------------------------ a1 inputs / gram
+@pytest.mark.parametrize("R,T", [(1, 5), (3, 24), (5, 251), (25, 165)])
+def test_gpdtw1d_inputs(backend, R, T):
+    reals, _ = _cell(3, R, T, 2, seed=R * 100 + T)
+    X, ym, yv = backend.gpdtw1d_inputs(_t(backend, reals))
+    for m in range(3):
+        Xo, yo, so = rp.gpdtw1d_inputs(reals[m])
+        assert np.array_equal(X[m].cpu().numpy(), Xo)
+        assert rel_err(ym[m].cpu().numpy(), yo) < 1e-15
+        assert np.abs(yv[m].cpu().numpy() - so).max() < 1e-17 + 1e-14 * so.max()
+
+
+@pytest.mark.parametrize("R,T", [(1, 7), (3, 24), (5, 130), (10, 251), (25, 300)])
+def test_matern32_gram(backend, R, T):
+    reals, _ = _cell(2, R, T, 2, seed=T)
+    X, _, _ = backend.gpdtw1d_inputs(_t(backend, reals))
+    var = np.array([0.5, 1.3])
+    ls = np.array([6.0, 0.9])
+    K = backend.matern32_gram(X, var, ls).cpu().numpy()
+    for m in range(2):
+        Xo, _, _ = rp.gpdtw1d_inputs(reals[m])
+        assert rel_err(K[m], rp.matern32_gram(Xo, var[m], ls[m])) < 1e-12
+        # (-2 x.y + |x|^2) + |y|^2 is not symmetric in rounding (neither is GPflow's): 1 ulp of r2
+        assert np.abs(K[m] - K[m].T).max() < 1e-13
+
+
+# ------------------------------------------------------------------------------------ a3 Cholesky
+@pytest.mark.parametrize("T", [1, 2, 15, 16, 17, 86, 127, 128, 129, 165, 251, 300, 515])
+def test_potrf_vs_lapack(backend, T):
+    rng = np.random.default_rng(T)
+    B = 3
+    A = rng.normal(size=(B, T, T + 3))
+    A = A @ A.transpose(0, 2, 1) / T + 0.5 * np.eye(T)
+    L, info = backend.potrf(_t(backend, A))
+    assert info.cpu().numpy().tolist() == [0] * B
+    L = L.cpu().numpy()
+    for b in range(B):
+        assert rel_err(L[b], np.linalg.cholesky(A[b])) < 1e-12
+        assert np.abs(np.triu(L[b], 1)).max() == 0.0
+
+
+def test_potrf_reports_non_pd_like_lapack(backend):
+    T = 200
+    rng = np.random.default_rng(0)
+    A = rng.normal(size=(2, T, T))
+    A = A @ A.transpose(0, 2, 1) + T * np.eye(T)
+    A[1, 140, 140] = -1.0  # leading minor 141 is not PD
+    _, info = backend.potrf(_t(backend, A))
+    assert info.cpu().numpy().tolist() == [0, 141]
+
+
+def test_golden_scale_tri(backend, golden_members):
+    """a3 against the reference's stored distrax factor (pinned parity)."""
+    for T in (86, 165):
+        ms = [m for m in golden_members if m.mu.shape[0] == T]
+        cov = np.stack([m.cov for m in ms])
+        mu = np.stack([m.mu for m in ms])
+        tri, var_diag, stats, info = backend.mvn_from_cov(_t(backend, mu), _t(backend, cov))
+        assert int(info.abs().sum()) == 0
+        tri = tri.cpu().numpy()
+        for k, m in enumerate(ms):
+            assert np.abs(tri[k] - m.scale_tri).max() <= 1e-13, m.key
+            assert np.array_equal(var_diag[k].cpu().numpy(), np.diag(m.cov))
+
+
+# ------------------------------------------------------------------------------------ a1 posterior
+@pytest.mark.parametrize("T,R,M", [(3, 2, 2), (24, 3, 5), (86, 5, 3), (126, 4, 2), (128, 4, 2), (165, 10, 4),
+                                   (251, 3, 10), (300, 5, 3), (600, 5, 2)])
+def test_gp_posterior_vs_oracle(backend, T, R, M):
+    reals, _ = _cell(M, R, T, 2, seed=T + R)
+    X, ym, yv = backend.gpdtw1d_inputs(_t(backend, reals))
+    var = np.linspace(0.3, 1.1, M)
+    ls = np.linspace(4.0, 8.0, M)
+    post = backend.gp_posterior(X, ym, yv, var, ls)
+    assert int(post.info_fit.abs().sum()) == 0 and int(post.info_dist.abs().sum()) == 0
+    for m in range(M):
+        Xo, yo, so = rp.gpdtw1d_inputs(reals[m])
+        mean, cov = rp.gp_posterior_closed_form(Xo, yo, so, var[m], ls[m])
+        assert rel_err(post.mu[m].cpu().numpy(), mean) <= TOL_POSTERIOR
+        assert np.abs(post.var_diag[m].cpu().numpy() / np.diag(cov) - 1).max() <= TOL_POSTERIOR
+        assert rel_err(post.cov[m].cpu().numpy(), cov) <= TOL_POSTERIOR
+        assert rel_err(post.scale_tri[m].cpu().numpy(), np.linalg.cholesky(cov)) <= TOL_POSTERIOR
+        c = post.cov[m].cpu().numpy()
+        assert np.array_equal(c, c.T)
+
+
+def test_gp_posterior_on_golden_inputs(backend, golden_members):
+    """The reference's own inputs with the hyper-parameters recovered from its fits: the
+    CUDA posterior reproduces the reference's stored covariance to the structural-pin level
+    (~1e-6 abs) and the oracle to 1e-8."""
+    for T in (86, 165):
+        for m in [g for g in golden_members if g.mu.shape[0] == T]:
+            X, ym, yv = backend.gpdtw1d_inputs(_t(backend, m.realisations[None]))
+            post = backend.gp_posterior(X, ym, yv, [m.variance], [m.lengthscale])
+            cov = post.cov[0].cpu().numpy()
+            assert np.abs(cov - m.cov).max() <= 6e-6, m.key
+            Xo, yo, so = rp.gpdtw1d_inputs(m.realisations)
+            mean_o, cov_o = rp.gp_posterior_closed_form(Xo, yo, so, m.variance, m.lengthscale)
+            assert rel_err(cov, cov_o) <= TOL_POSTERIOR and rel_err(post.mu[0].cpu().numpy(), mean_o) <= TOL_POSTERIOR
+
+
+# ------------------------------------------------------------------------------------ a4 weights
+def test_constvec_logprob_and_weights_on_golden(backend, golden_members):
+    """Reference posteriors + leave-one-out pseudo-observations (utils.py:196-200): log-probs,
+    exp underflow and the 0/0 -> NaN columns (Q-EXP) must match the oracle exactly in pattern."""
+    group = [m for m in golden_members if m.tag == "histssp460"]
+    obs = group[2].realisations  # [10,165]
+    members = group[:2]
+    mus = np.stack([m.mu for m in members])
+    covs = np.stack([m.cov for m in members])
+    tri, _, stats, _ = backend.mvn_from_cov(_t(backend, mus), _t(backend, covs))
+    w_o, e_o, l_o = rp.loglik_weights_mvn(mus, tri.cpu().numpy(), obs)
+    ll = backend.mvn_constvec_logprob(stats, _t(backend, obs[None]), 2)[0].cpu().numpy()  # [M,Ro,T]
+    for m in range(2):
+        for r in range(obs.shape[0]):
+            want = rp.mvn_log_prob(mus[m], members[m].scale_tri, obs[r][:, None])
+            assert rel_err(ll[m, r], want) < 1e-10
+    w, le, lm = backend.loglik_weights_mvn(stats, _t(backend, obs[None]), 2, want_lls=True)
+    _nan_equal_close(lm[0].cpu().numpy(), l_o, 1e-10, "lls_mean")
+    _nan_equal_close(le[0].cpu().numpy(), e_o, 1e-7, "lls_exp")
+    _nan_equal_close(w[0].cpu().numpy(), w_o, TOL_WEIGHTS, "weights")
+    assert np.isnan(w_o).any()
+
+
+@pytest.mark.parametrize("M,Ro", [(2, 1), (5, 2), (10, 5), (10, 10)])
+def test_weights_reference_test_shapes(backend, M, Ro):
+    """Shapes of the reference's tests/test_weights.py:71-101 (24 monthly steps)."""
+    reals, obs = _cell(M, 3, 24, Ro, seed=M * 10 + Ro, monthly=True)
+    o = rp.cell_pipeline_L1(reals, obs, 0.5, 6.0)
+    X, ym, yv = backend.gpdtw1d_inputs(_t(backend, reals))
+    post = backend.gp_posterior(X, ym, yv, np.full(M, 0.5), np.full(M, 6.0))
+    w = backend.loglik_weights_mvn(post.mvn_stats, _t(backend, obs[None]), M)[0].cpu().numpy()
+    assert w.shape == (M, 24)
+    _nan_equal_close(w, o["weights"], TOL_WEIGHTS, "weights")
+    ok = ~np.isnan(w).any(axis=0)
+    assert np.allclose(w[:, ok].sum(axis=0), 1.0, atol=1e-6)
+
+
+def test_normal_branch(backend):
+    rng = np.random.default_rng(5)
+    C, M, Ro, N = 2, 4, 3, 77
+    loc = rng.normal(size=(C, M, N))
+    scale = rng.uniform(0.05, 0.4, size=(C, M, N))
+    obs = rng.normal(size=(C, Ro, N))
+    w, le, lm = backend.loglik_weights_normal(_t(backend, loc), _t(backend, scale), _t(backend, obs), want_lls=True)
+    for c in range(C):
+        wo, eo, lo = rp.loglik_weights_normal(loc[c], scale[c], obs[c])
+        _nan_equal_close(lm[c].cpu().numpy(), lo, 1e-12, "lls_mean")
+        _nan_equal_close(w[c].cpu().numpy(), wo, TOL_WEIGHTS, "weights")
+    ll = backend.normal_logprob(_t(backend, loc), _t(backend, scale), _t(backend, loc + 0.1)).cpu().numpy()
+    assert rel_err(ll, rp.normal_log_prob(loc, scale, loc + 0.1)) < 1e-13
+
+
+def test_weights_time_mean_skips_nan(backend):
+    rng = np.random.default_rng(6)
+    w = rng.uniform(size=(2, 3, 50))
+    w[0, :, 5:9] = np.nan
+    w[1, 2, :] = np.nan
+    out = backend.weights_time_mean(_t(backend, w)).cpu().numpy()
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        want = np.broadcast_to(np.nanmean(w, axis=2)[..., None], w.shape)
+    _nan_equal_close(out, want, 1e-14, "time mean")
+
+
+# ------------------------------------------------------------------------------------ a5/a6 barycentre
+def test_barycentre_vs_oracle_all_regimes(backend):
+    rng = np.random.default_rng(7)
+    C, M, N = 2, 6, 40
+    means = rng.normal(size=(C, M, N))
+    variances = rng.uniform(0.001, 0.05, size=(C, M, N))
+    variances[1] = rng.uniform(1.5, 30.0, size=(M, N))  # S > 1: the iteration really runs
+    w = rng.uniform(size=(C, M, N))
+    w /= w.sum(axis=1, keepdims=True)
+    w[0, :, 3] = np.nan  # a 0/0 column from the weights stage
+    mu, sd, it = backend.barycentre_1d(_t(backend, means), _t(backend, variances), _t(backend, w))
+    for c in range(C):
+        bmu, bsd, bit = rp.barycentre_points(means[c], variances[c], w[c])
+        _nan_equal_close(mu[c].cpu().numpy(), bmu, 1e-13, "bary mu")
+        _nan_equal_close(sd[c].cpu().numpy(), bsd, 1e-13, "bary sd")
+        assert np.array_equal(it[c].cpu().numpy(), bit)
+    assert int(it[0].max()) == 201 and int(it[1].min()) > 3
+
+
+def test_single_point_gaussian_barycentre(backend):
+    from bayesian_ensembling_b200 import gaussian_barycentre
+
+    for stds in ([0.1, 0.3], [2.0, 4.0]):
+        mu, sd = gaussian_barycentre([1.0, 3.0], stds, [0.25, 0.75])
+        mo, so, _ = rp.gaussian_barycentre([1.0, 3.0], stds, [0.25, 0.75])
+        assert abs(mu - mo) < 1e-14 and abs(sd - so) < 1e-14
+
+
+def test_member_sharded_partials_equal_direct(backend):
+    """Emulates 2 ranks on one GPU: partial sums over each half of the members, summed, give
+    the single-GPU weights / barycentre (the NCCL all-reduce is a plain sum of these buffers)."""
+    reals, obs = _cell(6, 3, 60, 4, seed=8)
+    X, ym, yv = backend.gpdtw1d_inputs(_t(backend, reals))
+    post = backend.gp_posterior(X, ym, yv, np.full(6, 0.5), np.full(6, 6.0), want_cov=False, want_scale_tri=False)
+    ob = _t(backend, obs[None])
+    w, le, _ = backend.loglik_weights_mvn(post.mvn_stats, ob, 6, want_lls=True)
+    mu_d, sd_d, _ = backend.barycentre_1d(post.mu[None], post.var_diag[None], w)
+    parts = []
+    for lo, hi in ((0, 3), (3, 6)):
+        _, le_l, _ = backend.loglik_weights_mvn(post.mvn_stats[lo:hi], ob, hi - lo, want_lls=True)
+        parts.append(backend.barycentre_1d_partial(post.mu[None, lo:hi], post.var_diag[None, lo:hi], le_l))
+    total = parts[0] + parts[1]
+    mu_s, sd_s, _ = backend.barycentre_1d_finish(total)
+    w_s = backend.weights_normalise(le[:, 0:3].contiguous(), total[0])
+    _nan_equal_close(mu_s.cpu().numpy(), mu_d.cpu().numpy(), 1e-12, "mu")
+    _nan_equal_close(sd_s.cpu().numpy(), sd_d.cpu().numpy(), 1e-12, "sd")
+    _nan_equal_close(w_s.cpu().numpy(), w[:, 0:3].cpu().numpy(), 1e-12, "w")
+
+
+# ------------------------------------------------------------------------------------ whole path
+@pytest.mark.parametrize("time_mean", [False, True])
+def test_cfg1_pipeline_vs_oracle(backend, time_mean):
+    """BASELINE config 1: 10 models x 3 realisations x 251 annual steps."""
+    from bayesian_ensembling_b200 import grid
+
+    cfg = synthetic.CONFIGS["cfg1"]
+    reals, obs = synthetic.make_cells(cfg)
+    res = grid.fit_weight_barycentre(reals, obs, synthetic.L1_VARIANCE, synthetic.L1_LENGTHSCALE,
+                                     keep_posteriors=True, time_mean_weights=time_mean)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        o = rp.cell_pipeline_L1(reals[0], obs[0], synthetic.L1_VARIANCE, synthetic.L1_LENGTHSCALE,
+                                time_mean_weights=time_mean)
+    assert rel_err(res.mu[0].cpu().numpy(), o["mu"]) <= TOL_POSTERIOR
+    assert rel_err(res.cov[0].cpu().numpy(), o["cov"]) <= TOL_POSTERIOR
+    _nan_equal_close(res.weights[0].cpu().numpy(), o["weights"], TOL_WEIGHTS, "weights")
+    _nan_equal_close(res.bary_mu[0].cpu().numpy(), o["bary_mu"], TOL_WEIGHTS, "bary_mu")
+    _nan_equal_close(res.bary_std[0].cpu().numpy(), o["bary_std"], TOL_WEIGHTS, "bary_std")
+
+
+def test_multi_cell_waves_equal_single_wave(backend):
+    from bayesian_ensembling_b200 import grid
+
+    cfg = synthetic.Config("t", 9, 5, 3, 3, 90, 2, False, "")
+    reals, obs = synthetic.make_cells(cfg, seed=77)
+    a = grid.fit_weight_barycentre(reals, obs, 0.5, 6.0)
+    b = grid.fit_weight_barycentre(reals, obs, 0.5, 6.0, cells_per_wave=2)
+    for name in ("weights", "bary_mu", "bary_std", "mu", "var_diag"):
+        x, y = getattr(a, name).cpu().numpy(), getattr(b, name).cpu().numpy()
+        assert np.array_equal(x, y, equal_nan=True), name
+
+
+def test_full_size_properties_T3012(backend):
+    """BASELINE config 2 size (T=3012): the oracle takes seconds per member here, so one member
+    is compared directly and the batch is checked through size-independent identities:
+    (K+E) * Minv == I with Minv recovered from cov, scale_tri scale_tri^T == cov, symmetry."""
+    import torch
+
+    cfg = synthetic.CONFIGS["cfg2"]
+    reals, obs = synthetic.make_cells(cfg)
+    M = 3
+    r = _t(backend, reals[0, :M])
+    X, ym, yv = backend.gpdtw1d_inputs(r)
+    var = torch.full((M,), synthetic.L1_VARIANCE, dtype=torch.float64, device=backend.device)
+    ls = torch.full((M,), synthetic.L1_LENGTHSCALE, dtype=torch.float64, device=backend.device)
+    post = backend.gp_posterior(X, ym, yv, var, ls)
+    assert int(post.info_fit.abs().sum()) == 0 and int(post.info_dist.abs().sum()) == 0
+    K = backend.matern32_gram(X, var, ls)
+    E = yv + 1e-6
+    P = post.cov - torch.diag_embed(yv)  # = E - E Minv E
+    Minv = (torch.diag_embed(E) - P) / E[:, :, None] / E[:, None, :]
+    I = torch.eye(cfg.steps, dtype=torch.float64, device=backend.device)
+    resid = ((K + torch.diag_embed(E)) @ Minv - I).abs().max().item()
+    assert resid < 1e-8, resid
+    llt = post.scale_tri @ post.scale_tri.transpose(1, 2)
+    assert ((llt - post.cov).abs().max() / post.cov.abs().max()).item() < 1e-13
+    assert torch.equal(post.cov, post.cov.transpose(1, 2))
+    # one member against the oracle at full size
+    Xo, yo, so = rp.gpdtw1d_inputs(reals[0, 0])
+    mean, cov = rp.gp_posterior_closed_form(Xo, yo, so, synthetic.L1_VARIANCE, synthetic.L1_LENGTHSCALE)
+    assert rel_err(post.mu[0].cpu().numpy(), mean) <= TOL_POSTERIOR
+    assert rel_err(post.cov[0].cpu().numpy(), cov) <= TOL_POSTERIOR
+    assert np.abs(post.var_diag[0].cpu().numpy() / np.diag(cov) - 1).max() <= TOL_POSTERIOR
+
+
+# ------------------------------------------------------------------------------------ the reference's API
+def test_reference_api_end_to_end(backend):
+    """ModelCollection.fit(GPDTW1D) -> LogLikelihoodWeight -> Barycentre with the reference's
+    call signatures (tests/test_weights.py:86-101, utils.py:102-135)."""
+    import bayesian_ensembling_b200 as es
+    from bayesian_ensembling_b200.labelled import DataArray
+
+    M, R, T, Ro = 5, 3, 24, 2
+    reals, obs = _cell(M, R, T, Ro, seed=21, monthly=True)
+    time = np.arange(T)
+    pms = [es.ProcessModel(DataArray(reals[m], ("realisation", "time"),
+                                     {"realisation": np.arange(R), "time": time}), f"model{m}") for m in range(M)]
+    obs_pm = es.ProcessModel(DataArray(obs, ("realisation", "time"), {"realisation": np.arange(Ro), "time": time}),
+                             "obs")
+    mc = es.ModelCollection(pms)
+    mc.fit(es.GPDTW1D(hyperparameters=(0.5, 6.0)), compile_objective=True, n_optim_nits=2, progress_bar=False)
+    weights = es.LogLikelihoodWeight()(mc, obs_pm)
+    assert weights.shape == (M, T) and weights.dims == ("model", "time")
+    o = rp.cell_pipeline_L1(reals, obs, 0.5, 6.0)
+    _nan_equal_close(weights.values, o["weights"], TOL_WEIGHTS, "weights")
+    for m in range(M):
+        d = mc[m].distribution
+        assert rel_err(d.mean.values, o["mu"][m]) <= TOL_POSTERIOR
+        assert rel_err(d.variance.values, np.diag(o["cov"][m])) <= TOL_POSTERIOR
+        assert rel_err(d._dist.covariance(), o["cov"][m]) <= TOL_POSTERIOR
+    bary = es.Barycentre()(mc, weights)
+    _nan_equal_close(bary.mean.values, o["bary_mu"], TOL_WEIGHTS, "bary mean")
+    # Q-SCALE: Distribution(mu, covariance=sd**2, MultivariateNormalDiag) => variance == sd**4
+    _nan_equal_close(bary.variance.values, o["bary_std"] ** 4, TOL_WEIGHTS, "bary variance")
+    # distribution.log_prob of a genuine [T] vector and of the [T,1] quirk input
+    ll = mc[0].distribution._dist.log_prob(obs[0][:, None])
+    assert rel_err(ll, rp.mvn_log_prob(o["mu"][0], o["scale_tri"][0], obs[0][:, None])) < 1e-9
+    ll1 = mc[0].distribution._dist.log_prob(obs[0])
+    assert abs(ll1 - rp.mvn_log_prob(o["mu"][0], o["scale_tri"][0], obs[0])) <= 1e-9 * abs(ll1)

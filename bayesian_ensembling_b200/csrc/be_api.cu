@@ -16,7 +16,7 @@ enum Family {
     F_COUNT
 };
 static const char* const kFamilyName[F_COUNT] = {
-    "k_gpdtw1d_inputs", "k_matern32", "k_diag_block", "k_panel_scale", "k_syrk_trailing", "k_trtri_accum",
+    "k_gpdtw1d_inputs", "k_matern32", "k_diag_block", "k_panel_scale", "k_chol_update", "k_trtri_accum",
     "k_lauum_cov", "k_posterior_mean", "k_mvn_stats", "copy/pad", "k_loglik_weights", "k_barycentre"};
 
 struct ProfRecord {
@@ -111,7 +111,7 @@ inline unsigned grid1d(size_t n, int block) { return (unsigned)((n + block - 1) 
 bool g_attr_done = false;
 int ensure_kernel_attrs(be_ctx* ctx) {
     if (g_attr_done) return BE_OK;
-    BE_CUDA(cudaFuncSetAttribute(k_syrk_trailing, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
+    BE_CUDA(cudaFuncSetAttribute(k_chol_update, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
     BE_CUDA(cudaFuncSetAttribute(k_panel_scale, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
     BE_CUDA(cudaFuncSetAttribute(k_trtri_accum, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
     BE_CUDA(cudaFuncSetAttribute(k_lauum_cov, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
@@ -129,28 +129,30 @@ inline size_t matern_smem(int R) { return ((size_t)2 * NB * (R | 1) + 2 * NB) * 
 // inverted diagonal blocks and, if V != nullptr, the diagonal tiles of V = C^-T.
 int potrf_padded(be_ctx* ctx, double* Mat, int Tp, int T, int B, double* Dinv, double* V, int* info) {
     const int ld = Tp, nblk = num_blocks(Tp);
+    // left-looking: column update (one long-K tensor-core GEMM per tile) -> diagonal block -> panel
     for (int kb = 0; kb < nblk; ++kb) {
         const double kw = (double)(Tp - kb * NB < NB ? Tp - kb * NB : NB);
         const double nrem = (double)Tp - kb * NB - kw;  // rows below the diagonal block
+        const double kdone = (double)kb * NB;           // columns already factorised
+        int t = nblk - kb - 1;
+        if (kb > 0) {
+            // algorithmic: (nrem x kw) gemm + (kw x kw) syrk, K = kdone
+            Prof pr(ctx, F_SYRK, B * (2.0 * nrem * kw + kw * (kw + 1.0)) * kdone,
+                    B * ((nrem + kw) * kdone + 2.0 * (nrem + 0.5 * kw) * kw) * 8);
+            k_chol_update<<<(unsigned)((size_t)(t + 1) * B), GEMM_THREADS, GEMM_SMEM_BYTES, ctx->stream>>>(Mat, ld, Tp,
+                                                                                                         kb, B);
+            BE_LAUNCHED();
+        }
         {
             Prof pr(ctx, F_DIAG, B * (2.0 / 3.0) * kw * kw * kw, B * 3.0 * kw * kw * 8);
             k_diag_block<<<B, 256, DIAG_SMEM_BYTES, ctx->stream>>>(Mat, ld, Tp, T, kb, Dinv, nblk, V, info);
             BE_LAUNCHED();
         }
-        int t = nblk - kb - 1;
         if (t > 0) {
-            {
-                Prof pr(ctx, F_PANEL, B * nrem * kw * kw, B * (2.0 * nrem * kw + kw * kw) * 8);
-                k_panel_scale<<<(unsigned)((size_t)t * B), GEMM_THREADS, GEMM_SMEM_BYTES, ctx->stream>>>(
-                    Mat, ld, Tp, kb + 1, kb, Dinv, nblk, 1.0, B);
-                BE_LAUNCHED();
-            }
-            {
-                Prof pr(ctx, F_SYRK, B * nrem * (nrem + 1.0) * kw, B * (nrem * (nrem + 1.0) + nrem * kw) * 8);
-                k_syrk_trailing<<<(unsigned)((size_t)t * (t + 1) / 2 * B), GEMM_THREADS, GEMM_SMEM_BYTES,
-                                  ctx->stream>>>(Mat, ld, Tp, kb, B);
-                BE_LAUNCHED();
-            }
+            Prof pr(ctx, F_PANEL, B * nrem * kw * kw, B * (2.0 * nrem * kw + kw * kw) * 8);
+            k_panel_scale<<<(unsigned)((size_t)t * B), GEMM_THREADS, GEMM_SMEM_BYTES, ctx->stream>>>(
+                Mat, ld, Tp, kb + 1, kb, Dinv, nblk, 1.0, B);
+            BE_LAUNCHED();
         }
     }
     return BE_OK;

@@ -10,12 +10,12 @@
 #include <math.h>
 
 #include "dmma_gemm.cuh"
+#include "chol_diag.cuh"
 
 namespace be {
 
 constexpr int NB = 128;  // block size of the blocked algorithms == GEMM tile edge
-constexpr int DIAG_LD = 129;
-constexpr int DIAG_SMEM_BYTES = NB * DIAG_LD * 8 + 2 * NB * 8;
+constexpr int DIAG_SMEM_BYTES = DG_SMEM_BYTES;
 constexpr double SQRT3 = 1.7320508075688772;
 constexpr double LOG_2PI = 1.8378770664093453;
 
@@ -140,113 +140,38 @@ __global__ void k_pad_from_dense(const double* __restrict__ A, const double* __r
 }
 
 // --------------------------------------------------------------------------------------
-// Diagonal block: unblocked Cholesky of the (<=128)^2 block kb in shared memory, then its
-// inverse (in place) -> Dinv[b][kb] (row-major 128 x 128, identity on padding), and
-// optionally V tile (kb,kb) = Dinv^T.  Columns >= T are never pivots (see file header).
-// --------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_diag_block(double* __restrict__ Mat, int ld, int Tp, int T, int kb,
-                                                    double* __restrict__ Dinv, int nblk, double* __restrict__ V,
-                                                    int* __restrict__ info) {
-    extern __shared__ double sm[];
-    double* s = sm;                         // [128][129]
-    double* red = sm + NB * DIAG_LD;        // [2][128]
-    const int b = blockIdx.x;
-    const int tid = threadIdx.x;
-    const int r0 = kb * NB;
-    const int n = min(NB, Tp - r0);
-    const int nr = max(0, min(n, T - r0));
-    double* Mb = Mat + (size_t)b * Tp * ld;
-    for (int e = tid; e < NB * NB; e += 256) {
-        int i = e >> 7, j = e & 127;
-        double v = i == j ? 1.0 : 0.0;
-        if (i < n && j <= i) v = Mb[(size_t)(r0 + i) * ld + r0 + j];
-        s[i * DIAG_LD + j] = v;
-    }
-    __syncthreads();
-    const int i = tid & 127, h = tid >> 7;
-    int bad = 0;
-    for (int j = 0; j < nr; ++j) {
-        double piv = s[j * DIAG_LD + j];
-        if (!(piv > 0.0) && bad == 0) bad = r0 + j + 1;
-        double aij = 0.0;
-        if (i > j && i < n) {
-            aij = s[i * DIAG_LD + j];
-            double f = aij / piv;
-            int kmax = min(i, nr - 1);
-            for (int k = j + 1 + h; k <= kmax; k += 2) s[i * DIAG_LD + k] -= f * s[k * DIAG_LD + j];
-        }
-        __syncthreads();
-        if (h == 0 && i < n) {
-            double d = sqrt(piv);
-            if (i == j) s[i * DIAG_LD + j] = d;
-            else if (i > j) s[i * DIAG_LD + j] = aij / d;
-        }
-    }
-    __syncthreads();
-    if (tid == 0 && bad != 0 && info) {
-        if (info[b] == 0) info[b] = bad;
-    }
-    // write the factor back (lower part of the block, all n rows, real columns only)
-    for (int e = tid; e < NB * NB; e += 256) {
-        int r = e >> 7, c = e & 127;
-        if (r < n && c <= r && c < nr) Mb[(size_t)(r0 + r) * ld + r0 + c] = s[r * DIAG_LD + c];
-    }
-    __syncthreads();
-    // in-place inverse of the real nr x nr lower triangle (columns from last to first)
-    for (int j = nr - 1; j >= 0; --j) {
-        double wjj = 1.0 / s[j * DIAG_LD + j];
-        double part = 0.0;
-        if (i > j && i < nr) {
-            for (int k = j + 1 + h; k <= i; k += 2) part += s[i * DIAG_LD + k] * s[k * DIAG_LD + j];
-        }
-        red[h * NB + i] = part;
-        __syncthreads();
-        if (h == 0) {
-            if (i == j) s[j * DIAG_LD + j] = wjj;
-            else if (i > j && i < nr) s[i * DIAG_LD + j] = -(red[i] + red[NB + i]) * wjj;
-        }
-        __syncthreads();
-    }
-    double* Db = Dinv + ((size_t)b * nblk + kb) * NB * NB;
-    for (int e = tid; e < NB * NB; e += 256) {
-        int r = e >> 7, c = e & 127;
-        double v = r == c ? 1.0 : 0.0;
-        if (r < nr && c < nr) v = c <= r ? s[r * DIAG_LD + c] : 0.0;
-        Db[e] = v;
-    }
-    if (V) {
-        double* Vb = V + (size_t)b * Tp * ld;
-        for (int e = tid; e < NB * NB; e += 256) {
-            int r = e >> 7, c = e & 127;
-            if (r >= n || c >= n) continue;
-            double v = r == c ? 1.0 : 0.0;
-            if (r < nr && c < nr) v = c >= r ? s[c * DIAG_LD + r] : 0.0;
-            Vb[(size_t)(r0 + r) * ld + r0 + c] = v;
-        }
-    }
-}
-
-// --------------------------------------------------------------------------------------
 // Tensor-core tile kernels (all share gemm_nt_mainloop)
 // --------------------------------------------------------------------------------------
 
-// Trailing update of the right-looking Cholesky: for block rows ti >= tj > kb
-//   Mat[ti, tj] -= Mat[ti, kb] * Mat[tj, kb]^T
-__global__ void __launch_bounds__(GEMM_THREADS, 1) k_syrk_trailing(double* __restrict__ Mat, int ld, int Tp, int kb,
-                                                                   int B) {
+// Left-looking column update of the blocked Cholesky: for block rows ti >= kb
+//   Mat[ti, kb] -= Mat[ti, 0:kb] * Mat[kb, 0:kb]^T        (one long-K GEMM per tile: K = kb * 128)
+// Each output tile is read and written ONCE per factorisation (the right-looking form re-reads
+// and re-writes it at every step with a K = 128 update, which left the tensor pipe ~55% idle).
+// -C is preloaded into the accumulators so the read overlaps the pipeline prologue.
+__global__ void __launch_bounds__(GEMM_THREADS, 1) k_chol_update(double* __restrict__ Mat, int ld, int Tp, int kb,
+                                                                 int B) {
     extern __shared__ __align__(16) double2 smem2[];
     int tile = blockIdx.x / B, b = blockIdx.x % B;
-    int ti, tj;
-    tri_decode(tile, ti, tj);
-    ti += kb + 1;
-    tj += kb + 1;
+    const int ti = kb + tile;
     double* Mb = Mat + (size_t)b * Tp * ld;
-    const int a_rows = blk_rows(Tp, ti), b_rows = blk_rows(Tp, tj);
-    TileAcc acc;
-    gemm_nt_mainloop(Mb + (size_t)ti * NB * ld + kb * NB, ld, a_rows, Mb + (size_t)tj * NB * ld + kb * NB, ld, b_rows,
-                     NB, smem2, acc);
+    const int a_rows = blk_rows(Tp, ti), b_rows = blk_rows(Tp, kb);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    double* Cb = Mb + (size_t)ti * NB * ld + tj * NB;
+    double* Cb = Mb + (size_t)ti * NB * ld + kb * NB;
+    TileAcc acc;
+#pragma unroll
+    for (int mi = 0; mi < 8; ++mi) {
+        int r = acc_row(warp, lane, mi);
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni) {
+            int c = acc_col(warp, lane, ni);
+            double2 v = make_double2(0.0, 0.0);
+            if (r < a_rows && c < b_rows) v = *reinterpret_cast<const double2*>(Cb + (size_t)r * ld + c);
+            acc.v[mi][ni][0] = -v.x;
+            acc.v[mi][ni][1] = -v.y;
+        }
+    }
+    gemm_nt_mainloop<false>(Mb + (size_t)ti * NB * ld, ld, a_rows, Mb + (size_t)kb * NB * ld, ld, b_rows, kb * NB,
+                            smem2, acc);
 #pragma unroll
     for (int mi = 0; mi < 8; ++mi) {
         int r = acc_row(warp, lane, mi);
@@ -255,11 +180,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_syrk_trailing(double* __res
         for (int ni = 0; ni < 4; ++ni) {
             int c = acc_col(warp, lane, ni);
             if (c >= b_rows) continue;
-            double2* p = reinterpret_cast<double2*>(Cb + (size_t)r * ld + c);
-            double2 v = *p;
-            v.x -= acc.v[mi][ni][0];
-            v.y -= acc.v[mi][ni][1];
-            *p = v;
+            *reinterpret_cast<double2*>(Cb + (size_t)r * ld + c) = make_double2(-acc.v[mi][ni][0], -acc.v[mi][ni][1]);
         }
     }
 }

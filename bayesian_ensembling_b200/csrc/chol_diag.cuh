@@ -1,0 +1,263 @@
+// Diagonal-block kernel of the blocked Cholesky / triangular inverse (sm_100a, fp64).
+//
+// One CTA (8 warps) factors one (<=128)^2 diagonal block in shared memory and inverts the
+// factor; this is the latency-bound serial spine of the factorisation, so it is organised to
+// keep the dependent chain short (an earlier version that factored 32 x 32 sub-blocks in one
+// warp with shuffles spent 480k cycles per block, all of it one warp's instruction stream):
+//   * 8-column steps.  Thread t owns row t.  Every row-owning thread REDUNDANTLY factors the
+//     8 x 8 pivot block in its own registers (36 values, 8 rsqrt, broadcast loads) and then
+//     eliminates its own row with it -- no shuffles, no inter-warp hand-off, one barrier.
+//   * The trailing columns are updated by ALL warps with FP64 tensor-core DMMA m8n8k4
+//     fragments read straight from shared memory (row stride 132 doubles == 4 mod 16 makes
+//     both the row-major and the transposed fragment loads bank-conflict free).
+//   * The 128 x 128 inverse is built in place by recursive doubling (8 -> 16 -> ... -> 128),
+//     inv([[A,0],[B,C]]) = [[A^-1,0],[-C^-1 B A^-1, C^-1]], each level two DMMA products.
+//
+// Padding semantics are those of be_kernels.cuh: columns >= T never pivot; rows >= T inside the
+// block (right-hand sides riding along) are treated as extra panel rows.
+#pragma once
+#include "dmma_gemm.cuh"
+
+namespace be {
+
+constexpr int DG_LD = 132;
+constexpr int DG_W = 8;        // columns per elimination step
+constexpr int DG_TMP_LD = 68;  // == 4 mod 16
+constexpr int DG_SMEM_DOUBLES = 128 * DG_LD + 64 * DG_TMP_LD;
+constexpr int DG_SMEM_BYTES = DG_SMEM_DOUBLES * 8;
+
+// out[f] += sum_k A[g][k] * B[f*8 + g][k]   ("NT": both operands k-contiguous rows)
+template <int NF, int K>
+__device__ __forceinline__ void frag_nt(const double* __restrict__ A, int lda, const double* __restrict__ B, int ldb,
+                                        double (&acc)[NF][2]) {
+    const int lane = threadIdx.x & 31, g = lane >> 2, q = lane & 3;
+#pragma unroll
+    for (int k = 0; k < K; k += 4) {
+        double a = A[g * lda + k + q];
+#pragma unroll
+        for (int f = 0; f < NF; ++f) dmma884(acc[f][0], acc[f][1], a, B[(f * 8 + g) * ldb + k + q]);
+    }
+}
+// out[f] += sum_k A[g][k] * B[k][f*8 + g]   ("NN")
+template <int NF>
+__device__ __forceinline__ void frag_nn(const double* __restrict__ A, int lda, const double* __restrict__ B, int ldb,
+                                        int K, double (&acc)[NF][2]) {
+    const int lane = threadIdx.x & 31, g = lane >> 2, q = lane & 3;
+#pragma unroll 4
+    for (int k = 0; k < K; k += 4) {
+        double a = A[g * lda + k + q];
+#pragma unroll
+        for (int f = 0; f < NF; ++f) dmma884(acc[f][0], acc[f][1], a, B[(k + q) * ldb + f * 8 + g]);
+    }
+}
+
+// One recursive-doubling product over all pairs of a level: for pair p (blocks of size s)
+//   OUT_p[s x s] = sign * X_p[s x s] * Y_p[s x s]        (row-major, "NN")
+// X_p = X + p * xs, etc.  Work is split in 8 x 16 output pieces over the 8 warps.
+__device__ __forceinline__ void level_product(const double* X, int ldx, int xs, const double* Y, int ldy, int ys,
+                                              double* OUT, int ldo, int os, int s, int npairs, double sign) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, q = lane & 3;
+    const int fr_n = s / 8, fc_n = (s + 15) / 16;
+    const int per_pair = fr_n * fc_n;
+    for (int task = warp; task < npairs * per_pair; task += 8) {
+        int p = task / per_pair, rem = task % per_pair;
+        int fr = rem / fc_n, fc = rem % fc_n;
+        const double* A = X + (size_t)p * xs + fr * 8 * ldx;
+        const double* Bm = Y + (size_t)p * ys + fc * 16;
+        double* O = OUT + (size_t)p * os + (fr * 8 + g) * ldo + fc * 16 + 2 * q;
+        if (s >= 16) {
+            double acc[2][2] = {};
+            frag_nn<2>(A, ldx, Bm, ldy, s, acc);
+            *reinterpret_cast<double2*>(O) = make_double2(sign * acc[0][0], sign * acc[0][1]);
+            *reinterpret_cast<double2*>(O + 8) = make_double2(sign * acc[1][0], sign * acc[1][1]);
+        } else {
+            double acc[1][2] = {};
+            frag_nn<1>(A, ldx, Bm, ldy, s, acc);
+            *reinterpret_cast<double2*>(O) = make_double2(sign * acc[0][0], sign * acc[0][1]);
+        }
+    }
+}
+
+// Mat block kb (rows/cols r0 .. r0+n) -> Cholesky factor in place (lower, real columns only),
+// Dinv[b][kb] = blockdiag(L11^-1, I) (row-major 128 x 128) and optionally V tile (kb,kb) = Dinv^T.
+__global__ void __launch_bounds__(256, 1) k_diag_block(double* __restrict__ Mat, int ld, int Tp, int T, int kb,
+                                                       double* __restrict__ Dinv, int nblk, double* __restrict__ V,
+                                                       int* __restrict__ info) {
+    extern __shared__ double sm[];
+    double* S = sm;                  // [128][132]
+    double* TMP = sm + 128 * DG_LD;  // [64][68]
+    const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g = lane >> 2, q = lane & 3;
+    const int r0 = kb * 128;
+    const int n = min(128, Tp - r0);        // rows present (multiple of 16)
+    const int nr = max(0, min(n, T - r0));  // real (pivoting) columns
+    double* Mb = Mat + (size_t)b * Tp * ld;
+    for (int e = tid; e < 128 * 128; e += 256) {
+        int i = e >> 7, j = e & 127;
+        double v = 0.0;
+        if (i < n && j < nr && j <= i) v = Mb[(size_t)(r0 + i) * ld + r0 + j];
+        S[i * DG_LD + j] = v;
+    }
+    __syncthreads();
+    const int nsteps = (nr + DG_W - 1) / DG_W;
+    int bad = 0;
+    __shared__ int s_bad;
+    if (tid == 0) s_bad = 0;
+    for (int st = 0; st < nsteps; ++st) {
+        const int c0 = st * DG_W;
+        const int w = min(DG_W, nr - c0);
+        // ---- phase A: redundant 8 x 8 pivot factorisation + elimination of the thread's own row
+        const bool act = tid < 128 && tid >= c0 && tid < n;
+        double Lb[DG_W][DG_W];
+        if (act) {
+#pragma unroll
+            for (int i = 0; i < DG_W; ++i)
+#pragma unroll
+                for (int k = 0; k <= i; ++k) {
+                    double v = S[(c0 + i) * DG_LD + c0 + k];
+                    if (i == k && i >= w) v = 1.0;  // padded columns: identity, never a pivot
+                    Lb[i][k] = v;
+                }
+        }
+        __syncthreads();  // every thread holds its copy of the pivot block before its rows are rewritten
+        if (act) {
+            double rs[DG_W];
+#pragma unroll
+            for (int j = 0; j < DG_W; ++j) {
+                double piv = Lb[j][j];
+                if (!(piv > 0.0) && bad == 0) bad = r0 + c0 + j + 1;
+                rs[j] = rsqrt(piv);
+                Lb[j][j] = piv * rs[j];
+#pragma unroll
+                for (int i = j + 1; i < DG_W; ++i) Lb[i][j] *= rs[j];
+#pragma unroll
+                for (int k = j + 1; k < DG_W; ++k)
+                    if (k < w) {  // padded columns stay identity: they are never pivots
+#pragma unroll
+                        for (int i = k; i < DG_W; ++i) Lb[i][k] = fma(-Lb[i][j], Lb[k][j], Lb[i][k]);
+                    }
+            }
+            if (tid == c0 && bad != 0 && s_bad == 0) s_bad = bad;
+            double* row = S + tid * DG_LD + c0;
+            if (tid < c0 + DG_W) {
+                const int i = tid - c0;
+#pragma unroll
+                for (int ii = 0; ii < DG_W; ++ii)
+                    if (ii == i) {
+#pragma unroll
+                        for (int k = 0; k <= ii; ++k)
+                            if (k < w) row[k] = Lb[ii][k];
+                    }
+            } else {
+                double pv[DG_W];
+#pragma unroll
+                for (int k = 0; k < DG_W; k += 2) {
+                    double2 t2 = *reinterpret_cast<const double2*>(row + k);
+                    pv[k] = t2.x;
+                    pv[k + 1] = t2.y;
+                }
+#pragma unroll
+                for (int j = 0; j < DG_W; ++j) {
+                    pv[j] *= rs[j];
+#pragma unroll
+                    for (int k = j + 1; k < DG_W; ++k)
+                        if (k < w) pv[k] = fma(-pv[j], Lb[k][j], pv[k]);
+                }
+#pragma unroll
+                for (int k = 0; k < DG_W; k += 2) *reinterpret_cast<double2*>(row + k) = make_double2(pv[k], pv[k + 1]);
+            }
+        }
+        __syncthreads();
+        // ---- phase B: trailing real columns [p0, nr): S[r][c] -= P[r][0:8] . P[c][0:8], r >= c
+        const int p0 = c0 + DG_W;
+        const int ncs = (nr - p0 + 7) / 8;  // column strips (<= 0: nothing left)
+        const int nrs = (n - p0) / 8;       // row strips
+        if (ncs > 0) {
+            for (int fr = warp; fr < nrs; fr += 8) {
+                const double* Pr = S + (p0 + fr * 8) * DG_LD + c0;
+                const double a0 = Pr[g * DG_LD + q], a1 = Pr[g * DG_LD + 4 + q];
+                const int fc_end = min(fr, ncs - 1);
+#pragma unroll 4
+                for (int fc = 0; fc <= fc_end; ++fc) {
+                    const double* Pc = S + (p0 + fc * 8) * DG_LD + c0;
+                    double c[2] = {0.0, 0.0};
+                    dmma884(c[0], c[1], a0, Pc[g * DG_LD + q]);
+                    dmma884(c[0], c[1], a1, Pc[g * DG_LD + 4 + q]);
+                    const int r = p0 + fr * 8 + g, cc = p0 + fc * 8 + 2 * q;
+                    double* dst = S + r * DG_LD + cc;
+                    if (cc + 1 < nr && cc + 1 <= r) {
+                        double2 v = *reinterpret_cast<double2*>(dst);
+                        *reinterpret_cast<double2*>(dst) = make_double2(v.x - c[0], v.y - c[1]);
+                    } else if (cc < nr && cc <= r) {
+                        dst[0] -= c[0];
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    if (tid == 0 && s_bad != 0 && info) {
+        if (info[b] == 0) info[b] = s_bad;
+    }
+    // the factor (lower, all n rows, real columns only)
+    for (int e = tid; e < 128 * 128; e += 256) {
+        int r = e >> 7, c = e & 127;
+        if (r < n && c <= r && c < nr) Mb[(size_t)(r0 + r) * ld + r0 + c] = S[r * DG_LD + c];
+    }
+    __syncthreads();
+    // ---- inverse of blockdiag(L11, I): rows >= nr become identity rows first
+    for (int e = tid; e < 128 * 128; e += 256) {
+        int r = e >> 7, c = e & 127;
+        if (r >= nr && c <= r) S[r * DG_LD + c] = r == c ? 1.0 : 0.0;
+    }
+    __syncthreads();
+    // level 0: the sixteen 8 x 8 diagonal blocks; thread t < 128 owns column (t & 7) of block (t >> 3)
+    {
+        double x[DG_W];
+        const int blk = tid >> 3, cidx = tid & 7;
+        if (tid < 128) {
+            const double* Lb = S + (blk * 8) * DG_LD + blk * 8;
+#pragma unroll
+            for (int i = 0; i < DG_W; ++i) {
+                double sacc = (i == cidx) ? 1.0 : 0.0;
+#pragma unroll
+                for (int k = 0; k < i; ++k) sacc = fma(-Lb[i * DG_LD + k], (k >= cidx) ? x[k] : 0.0, sacc);
+                x[i] = (i >= cidx) ? sacc / Lb[i * DG_LD + i] : 0.0;
+            }
+        }
+        __syncthreads();
+        if (tid < 128) {
+            double* Lb = S + (blk * 8) * DG_LD + blk * 8;
+#pragma unroll
+            for (int i = 0; i < DG_W; ++i)
+                if (i >= cidx) Lb[i * DG_LD + cidx] = x[i];
+        }
+        __syncthreads();
+    }
+    // levels s = 8, 16, 32, 64: B <- -C^-1 * (B * A^-1) for every pair [[A,0],[B,C]] of size 2s
+    for (int s = 8; s <= 64; s *= 2) {
+        const int npairs = 64 / s;
+        const int stride = 2 * s * DG_LD + 2 * s;  // from one pair's A to the next
+        // T_p = B_p * Ainv_p  -> TMP (pair p at column offset p * s ... rows 0..s)
+        level_product(S + s * DG_LD, DG_LD, stride, S, DG_LD, stride, TMP, DG_TMP_LD, s, s, npairs, 1.0);
+        __syncthreads();
+        // B_p = -Cinv_p * T_p
+        level_product(S + s * DG_LD + s, DG_LD, stride, TMP, DG_TMP_LD, s, S + s * DG_LD, DG_LD, stride, s, npairs, -1.0);
+        __syncthreads();
+    }
+    double* Db = Dinv + ((size_t)b * nblk + kb) * 128 * 128;
+    for (int e = tid; e < 128 * 128; e += 256) {
+        int r = e >> 7, c = e & 127;
+        Db[e] = c <= r ? S[r * DG_LD + c] : 0.0;
+    }
+    if (V) {
+        double* Vb = V + (size_t)b * Tp * ld;
+        for (int e = tid; e < 128 * 128; e += 256) {
+            int r = e >> 7, c = e & 127;  // V tile entry (r, c) = Dinv[c][r]
+            if (r >= n || c >= n) continue;
+            Vb[(size_t)(r0 + r) * ld + r0 + c] = r <= c ? S[c * DG_LD + r] : 0.0;
+        }
+    }
+}
+
+}  // namespace be

@@ -71,8 +71,11 @@ struct TileAcc {
 __device__ __forceinline__ int acc_row(int warp, int lane, int mi) { return (warp >> 2) * 64 + mi * 8 + (lane >> 2); }
 __device__ __forceinline__ int acc_col(int warp, int lane, int ni) { return (warp & 3) * 32 + ni * 8 + 2 * (lane & 3); }
 
-// acc = sum over k in [0, klen) of A[i,k] * B[j,k]; klen must be a multiple of BK (buffers are
-// padded so that it always is).  A, B point at (tile row 0, k 0).
+// acc (+)= sum over k in [0, klen) of A[i,k] * B[j,k]; klen must be a multiple of BK (buffers are
+// padded so that it always is).  A, B point at (tile row 0, k 0).  With ZERO_INIT = false the
+// caller has preloaded acc (e.g. with -C, so that the epilogue is a pure store and the C read
+// overlaps the pipeline prologue instead of serialising behind the mainloop).
+template <bool ZERO_INIT = true>
 __device__ __forceinline__ void gemm_nt_mainloop(const double* __restrict__ A, int lda, int a_rows,
                                                  const double* __restrict__ B, int ldb, int b_rows, int klen,
                                                  double2* smem, TileAcc& acc) {
@@ -81,10 +84,12 @@ __device__ __forceinline__ void gemm_nt_mainloop(const double* __restrict__ A, i
     const int warp = tid >> 5;
     const int wm = warp >> 2;
     const int wn = warp & 3;
+    if (ZERO_INIT) {
 #pragma unroll
-    for (int mi = 0; mi < 8; ++mi)
+        for (int mi = 0; mi < 8; ++mi)
 #pragma unroll
-        for (int ni = 0; ni < 4; ++ni) acc.v[mi][ni][0] = acc.v[mi][ni][1] = 0.0;
+            for (int ni = 0; ni < 4; ++ni) acc.v[mi][ni][0] = acc.v[mi][ni][1] = 0.0;
+    }
 
     const int ktiles = klen / BK;
 #pragma unroll

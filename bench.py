@@ -162,8 +162,7 @@ def run_reference(args, cfg):
 # ------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------
-TENSOR_FAMILIES = {"k_syrk_trailing", "k_trtri_accum", "k_lauum_cov", "k_panel_scale", "k_diag_block",
-                   "k_chol_update", "k_tri_gemm"}
+TENSOR_FAMILIES = {"k_chol_update", "k_trtri_accum", "k_lauum_cov", "k_panel_scale", "k_diag_block"}
 
 
 def run_ours(args, cfg):

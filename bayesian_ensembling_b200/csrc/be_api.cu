@@ -127,7 +127,7 @@ inline size_t matern_smem(int R) { return ((size_t)2 * NB * (R | 1) + 2 * NB) * 
 // Blocked right-looking Cholesky of B padded matrices, in place (lower).  Never pivots on
 // columns >= T; rows >= T ride along (file header of be_kernels.cuh).  Fills Dinv with the
 // inverted diagonal blocks and, if V != nullptr, the diagonal tiles of V = C^-T.
-int potrf_padded(be_ctx* ctx, double* Mat, int Tp, int T, int B, double* Dinv, double* V, int* info) {
+int potrf_padded(be_ctx* ctx, double* Mat, int Tp, int T, int B, double* Dinv, double* Pbuf, double* V, int* info) {
     const int ld = Tp, nblk = num_blocks(Tp);
     // left-looking: column update (one long-K tensor-core GEMM per tile) -> diagonal block -> panel
     for (int kb = 0; kb < nblk; ++kb) {
@@ -135,12 +135,12 @@ int potrf_padded(be_ctx* ctx, double* Mat, int Tp, int T, int B, double* Dinv, d
         const double nrem = (double)Tp - kb * NB - kw;  // rows below the diagonal block
         const double kdone = (double)kb * NB;           // columns already factorised
         int t = nblk - kb - 1;
-        if (kb > 0) {
-            // algorithmic: (nrem x kw) gemm + (kw x kw) syrk, K = kdone
+        {
+            // algorithmic: (nrem x kw) gemm + (kw x kw) syrk, K = kdone (kb == 0: moves the panel to Pbuf)
             Prof pr(ctx, F_SYRK, B * (2.0 * nrem * kw + kw * (kw + 1.0)) * kdone,
                     B * ((nrem + kw) * kdone + 2.0 * (nrem + 0.5 * kw) * kw) * 8);
-            k_chol_update<<<(unsigned)((size_t)(t + 1) * B), GEMM_THREADS, GEMM_SMEM_BYTES, ctx->stream>>>(Mat, ld, Tp,
-                                                                                                         kb, B);
+            k_chol_update<<<(unsigned)((size_t)(t + 1) * 2 * B), GEMM_THREADS, GEMM_SMEM_BYTES, ctx->stream>>>(
+                Mat, Pbuf, ld, Tp, kb, B);
             BE_LAUNCHED();
         }
         {
@@ -150,8 +150,8 @@ int potrf_padded(be_ctx* ctx, double* Mat, int Tp, int T, int B, double* Dinv, d
         }
         if (t > 0) {
             Prof pr(ctx, F_PANEL, B * nrem * kw * kw, B * (2.0 * nrem * kw + kw * kw) * 8);
-            k_panel_scale<<<(unsigned)((size_t)t * B), GEMM_THREADS, GEMM_SMEM_BYTES, ctx->stream>>>(
-                Mat, ld, Tp, kb + 1, kb, Dinv, nblk, 1.0, B);
+            k_panel_scale<<<(unsigned)((size_t)t * 2 * B), GEMM_THREADS, GEMM_SMEM_BYTES, ctx->stream>>>(
+                Pbuf, Mat, ld, Tp, kb + 1, kb, Dinv, nblk, 1.0, B);
             BE_LAUNCHED();
         }
     }
@@ -159,7 +159,7 @@ int potrf_padded(be_ctx* ctx, double* Mat, int Tp, int T, int B, double* Dinv, d
 }
 
 // V = C^-T (upper, row-major); diagonal tiles already written by potrf_padded.
-int trtri_padded(be_ctx* ctx, double* V, const double* Cm, int Tp, int B, const double* Dinv) {
+int trtri_padded(be_ctx* ctx, double* V, const double* Cm, int Tp, int B, const double* Dinv, double* Pbuf) {
     const int ld = Tp, nblk = num_blocks(Tp);
     for (int i = 1; i < nblk; ++i) {
         const double kw = (double)(Tp - i * NB < NB ? Tp - i * NB : NB);
@@ -167,14 +167,14 @@ int trtri_padded(be_ctx* ctx, double* V, const double* Cm, int Tp, int B, const 
         {
             // algorithmic: triangular (above x above, upper) times (above x kw): above^2 * kw flops
             Prof pr(ctx, F_TRTRI, B * above * above * kw, B * (0.5 * above * above + 2.0 * above * kw) * 8);
-            k_trtri_accum<<<(unsigned)((size_t)i * B), GEMM_THREADS, GEMM_SMEM_BYTES, ctx->stream>>>(V, Cm, ld, Tp, i,
-                                                                                                   B);
+            k_trtri_accum<<<(unsigned)((size_t)i * 2 * B), GEMM_THREADS, GEMM_SMEM_BYTES, ctx->stream>>>(V, Cm, Pbuf, ld,
+                                                                                                       Tp, i, B);
             BE_LAUNCHED();
         }
         {
             Prof pr(ctx, F_PANEL, B * above * kw * kw, B * (2.0 * above * kw + kw * kw) * 8);
-            k_panel_scale<<<(unsigned)((size_t)i * B), GEMM_THREADS, GEMM_SMEM_BYTES, ctx->stream>>>(
-                V, ld, Tp, 0, i, Dinv, nblk, -1.0, B);
+            k_panel_scale<<<(unsigned)((size_t)i * 2 * B), GEMM_THREADS, GEMM_SMEM_BYTES, ctx->stream>>>(
+                Pbuf, V, ld, Tp, 0, i, Dinv, nblk, -1.0, B);
             BE_LAUNCHED();
         }
     }
@@ -186,6 +186,7 @@ size_t padded_matrix_doubles(int B, int T) {
     return (size_t)B * Tp * Tp;
 }
 size_t dinv_doubles(int B, int T) { return (size_t)B * num_blocks(pad_dim(T)) * NB * NB; }
+size_t pbuf_doubles(int B, int T) { return (size_t)B * pad_dim(T) * NB; }
 
 }  // namespace
 
@@ -328,7 +329,8 @@ int be_matern32_gram(be_ctx* ctx, const double* X, int B, int T, int R, const do
 }
 
 size_t be_potrf_workspace_bytes(int B, int T) {
-    return align_up(padded_matrix_doubles(B, T) * 8, 256) + align_up(dinv_doubles(B, T) * 8, 256) + 1024;
+    return align_up(padded_matrix_doubles(B, T) * 8, 256) + align_up(dinv_doubles(B, T) * 8, 256) +
+           align_up(pbuf_doubles(B, T) * 8, 256) + 1024;
 }
 
 int be_potrf_batched(be_ctx* ctx, const double* A, int B, int T, double* L, int* info, void* workspace,
@@ -344,11 +346,12 @@ int be_potrf_batched(be_ctx* ctx, const double* A, int B, int T, double* L, int*
     Carver cv(workspace, workspace_bytes);
     double* W = cv.take<double>(padded_matrix_doubles(B, T));
     double* Dinv = cv.take<double>(dinv_doubles(B, T));
-    if (!W || !Dinv) return BE_ERR_WORKSPACE;
+    double* Pbuf = cv.take<double>(pbuf_doubles(B, T));
+    if (!W || !Dinv || !Pbuf) return BE_ERR_WORKSPACE;
     BE_CUDA(cudaMemsetAsync(info, 0, sizeof(int) * B, ctx->stream));
     k_pad_from_dense<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(A, nullptr, B, T, Tp, Tp, W, 0);
     BE_LAUNCHED();
-    int rc = potrf_padded(ctx, W, Tp, T, B, Dinv, nullptr, info);
+    int rc = potrf_padded(ctx, W, Tp, T, B, Dinv, Pbuf, nullptr, info);
     if (rc != BE_OK) return rc;
     k_copy_out_tri<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(W, Tp, Tp, T, L, B);
     BE_LAUNCHED();
@@ -359,7 +362,7 @@ size_t be_gp_posterior_workspace_bytes(int B, int T, int R) {
     (void)R;
     size_t Tp = pad_dim(T);
     return 2 * align_up(padded_matrix_doubles(B, T) * 8, 256) + align_up(dinv_doubles(B, T) * 8, 256) +
-           align_up((size_t)B * Tp * 8, 256) + 1024;
+           align_up(pbuf_doubles(B, T) * 8, 256) + align_up((size_t)B * Tp * 8, 256) + 1024;
 }
 
 int be_gp_posterior(be_ctx* ctx, const double* X, const double* y_mean, const double* y_var, const double* variance,
@@ -387,8 +390,9 @@ int be_gp_posterior(be_ctx* ctx, const double* X, const double* y_mean, const do
     double* Mw = cv.take<double>(padded_matrix_doubles(B, T));  // M -> C -> cov -> scale_tri
     double* Vw = cv.take<double>(padded_matrix_doubles(B, T));  // V = C^-T
     double* Dinv = cv.take<double>(dinv_doubles(B, T));
+    double* Pbuf = cv.take<double>(pbuf_doubles(B, T));
     double* u = cv.take<double>((size_t)B * Tp);
-    if (!Mw || !Vw || !Dinv || !u) return BE_ERR_WORKSPACE;
+    if (!Mw || !Vw || !Dinv || !Pbuf || !u) return BE_ERR_WORKSPACE;
     BE_CUDA(cudaMemsetAsync(info_fit, 0, sizeof(int) * B, ctx->stream));
     BE_CUDA(cudaMemsetAsync(info_dist, 0, sizeof(int) * B, ctx->stream));
 
@@ -403,7 +407,7 @@ int be_gp_posterior(be_ctx* ctx, const double* X, const double* y_mean, const do
         BE_LAUNCHED();
     }
     // 2. C = chol(M); row T becomes u = C^-1 y; V diagonal tiles
-    int rc = potrf_padded(ctx, Mw, Tp, T, B, Dinv, Vw, info_fit);
+    int rc = potrf_padded(ctx, Mw, Tp, T, B, Dinv, Pbuf, Vw, info_fit);
     if (rc != BE_OK) return rc;
     {
         Prof pr(ctx, F_COPY, 0.0, dB * dT * 16);
@@ -411,7 +415,7 @@ int be_gp_posterior(be_ctx* ctx, const double* X, const double* y_mean, const do
         BE_LAUNCHED();
     }
     // 3. V = C^-T
-    rc = trtri_padded(ctx, Vw, Mw, Tp, B, Dinv);
+    rc = trtri_padded(ctx, Vw, Mw, Tp, B, Dinv, Pbuf);
     if (rc != BE_OK) return rc;
     // 4. mean = y - E V u
     {
@@ -424,12 +428,12 @@ int be_gp_posterior(be_ctx* ctx, const double* X, const double* y_mean, const do
     {
         // lauum: T^3/3 flops; reads V (upper, T^2/2), writes the padded lower cov (+ dense cov if asked)
         Prof pr(ctx, F_LAUUM, dB * dT * dT * dT / 3.0, dB * dT * dT * (cov ? 2.0 : 1.0) * 8);
-        k_lauum_cov<<<(unsigned)((size_t)ntl * B), GEMM_THREADS, GEMM_SMEM_BYTES, ctx->stream>>>(
+        k_lauum_cov<<<(unsigned)((size_t)ntl * 2 * B), GEMM_THREADS, GEMM_SMEM_BYTES, ctx->stream>>>(
             Vw, ld, Tp, T, y_var, jitter, mu, Mw, var_diag, cov, B);
         BE_LAUNCHED();
     }
     // 6. scale_tri = chol(cov) (data.py:38-39); rows T/T+1 become a = L^-1 1, b = L^-1 mu
-    rc = potrf_padded(ctx, Mw, Tp, T, B, Dinv, nullptr, info_dist);
+    rc = potrf_padded(ctx, Mw, Tp, T, B, Dinv, Pbuf, nullptr, info_dist);
     if (rc != BE_OK) return rc;
     {
         Prof pr(ctx, F_STATS, 8.0 * dB * dT, dB * 3.0 * dT * 8);
@@ -460,7 +464,8 @@ int be_mvn_from_cov(be_ctx* ctx, const double* mu, const double* cov, int B, int
     Carver cv(workspace, workspace_bytes);
     double* W = cv.take<double>(padded_matrix_doubles(B, T));
     double* Dinv = cv.take<double>(dinv_doubles(B, T));
-    if (!W || !Dinv) return BE_ERR_WORKSPACE;
+    double* Pbuf = cv.take<double>(pbuf_doubles(B, T));
+    if (!W || !Dinv || !Pbuf) return BE_ERR_WORKSPACE;
     BE_CUDA(cudaMemsetAsync(info, 0, sizeof(int) * B, ctx->stream));
     k_pad_from_dense<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(cov, mu, B, T, Tp, Tp, W, 1);
     BE_LAUNCHED();
@@ -468,7 +473,7 @@ int be_mvn_from_cov(be_ctx* ctx, const double* mu, const double* cov, int B, int
         k_diag_from_dense<<<grid1d((size_t)B * T, 256), 256, 0, ctx->stream>>>(cov, B, T, var_diag);
         BE_LAUNCHED();
     }
-    int rc = potrf_padded(ctx, W, Tp, T, B, Dinv, nullptr, info);
+    int rc = potrf_padded(ctx, W, Tp, T, B, Dinv, Pbuf, nullptr, info);
     if (rc != BE_OK) return rc;
     k_mvn_stats<<<B, 256, 0, ctx->stream>>>(W, Tp, Tp, T, mvn_stats);
     BE_LAUNCHED();

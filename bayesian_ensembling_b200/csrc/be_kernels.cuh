@@ -148,15 +148,21 @@ __global__ void k_pad_from_dense(const double* __restrict__ A, const double* __r
 // Each output tile is read and written ONCE per factorisation (the right-looking form re-reads
 // and re-writes it at every step with a K = 128 update, which left the tensor pipe ~55% idle).
 // -C is preloaded into the accumulators so the read overlaps the pipeline prologue.
-__global__ void __launch_bounds__(GEMM_THREADS, 1) k_chol_update(double* __restrict__ Mat, int ld, int Tp, int kb,
-                                                                 int B) {
+// The diagonal tile (ti == kb) is updated in place; the tiles below it go to the panel scratch
+// Pbuf ([B][Tp][128], tile ti at rows ti*128) from which k_panel_scale writes the scaled panel
+// back into Mat -- the scale cannot run in place because both 128 x 64 half-tile CTAs of a tile
+// read the whole tile.
+__global__ void __launch_bounds__(GEMM_THREADS, GEMM_CTAS_PER_SM)
+    k_chol_update(double* __restrict__ Mat, double* __restrict__ Pbuf, int ld, int Tp, int kb, int B) {
     extern __shared__ __align__(16) double2 smem2[];
-    int tile = blockIdx.x / B, b = blockIdx.x % B;
+    int tile = blockIdx.x / (2 * B), rem = blockIdx.x % (2 * B);
+    const int half = rem / B, b = rem % B;  // 128 x 64 half-tiles: columns half*64 .. half*64+63 of block kb
     const int ti = kb + tile;
     double* Mb = Mat + (size_t)b * Tp * ld;
-    const int a_rows = blk_rows(Tp, ti), b_rows = blk_rows(Tp, kb);
+    const int a_rows = blk_rows(Tp, ti), b_rows = min(BN, blk_rows(Tp, kb) - half * BN);
+    if (b_rows <= 0) return;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    double* Cb = Mb + (size_t)ti * NB * ld + kb * NB;
+    double* Cb = Mb + (size_t)ti * NB * ld + kb * NB + half * BN;
     TileAcc acc;
 #pragma unroll
     for (int mi = 0; mi < 8; ++mi) {
@@ -170,8 +176,14 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_chol_update(double* __restr
             acc.v[mi][ni][1] = -v.y;
         }
     }
-    gemm_nt_mainloop<false>(Mb + (size_t)ti * NB * ld, ld, a_rows, Mb + (size_t)kb * NB * ld, ld, b_rows, kb * NB,
-                            smem2, acc);
+    gemm_nt_mainloop<false>(Mb + (size_t)ti * NB * ld, ld, a_rows, Mb + (size_t)(kb * NB + half * BN) * ld, ld, b_rows,
+                            kb * NB, smem2, acc);
+    double* Ob = Cb;
+    int ldo = ld;
+    if (ti != kb) {
+        Ob = Pbuf + ((size_t)b * Tp + (size_t)ti * NB) * NB + half * BN;
+        ldo = NB;
+    }
 #pragma unroll
     for (int mi = 0; mi < 8; ++mi) {
         int r = acc_row(warp, lane, mi);
@@ -180,26 +192,31 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_chol_update(double* __restr
         for (int ni = 0; ni < 4; ++ni) {
             int c = acc_col(warp, lane, ni);
             if (c >= b_rows) continue;
-            *reinterpret_cast<double2*>(Cb + (size_t)r * ld + c) = make_double2(-acc.v[mi][ni][0], -acc.v[mi][ni][1]);
+            *reinterpret_cast<double2*>(Ob + (size_t)r * ldo + c) = make_double2(-acc.v[mi][ni][0], -acc.v[mi][ni][1]);
         }
     }
 }
 
-// In-place right-multiplication of tiles (row block row_blk0 + x, column block cb) by the
-// transposed inverse diagonal block:  Mat[ti, cb] <- sign * Mat[ti, cb] * Dinv[cb]^T
+// Right-multiplication of panel tiles (row block row_blk0 + x, column block cb) by the
+// transposed inverse diagonal block:  Mat[ti, cb] <- sign * Pbuf[ti] * Dinv[cb]^T
 // (panel TRSM of the Cholesky with sign=+1; second half of the trtri column step with -1).
-__global__ void __launch_bounds__(GEMM_THREADS, 1) k_panel_scale(double* __restrict__ Mat, int ld, int Tp,
-                                                                 int row_blk0, int cb, const double* __restrict__ Dinv,
-                                                                 int nblk, double sign, int B) {
+// The unscaled tiles live in the panel scratch Pbuf ([B][Tp][128]).
+__global__ void __launch_bounds__(GEMM_THREADS, GEMM_CTAS_PER_SM)
+    k_panel_scale(const double* __restrict__ Pbuf, double* __restrict__ Mat, int ld, int Tp, int row_blk0, int cb,
+                  const double* __restrict__ Dinv, int nblk, double sign, int B) {
     extern __shared__ __align__(16) double2 smem2[];
-    int tile = blockIdx.x / B, b = blockIdx.x % B;
+    int tile = blockIdx.x / (2 * B), rem = blockIdx.x % (2 * B);
+    const int half = rem / B, b = rem % B;
     int ti = row_blk0 + tile;
     double* Mb = Mat + (size_t)b * Tp * ld;
+    const double* Sb = Pbuf + ((size_t)b * Tp + (size_t)ti * NB) * NB;
     const int a_rows = blk_rows(Tp, ti), kw = blk_rows(Tp, cb);
-    const double* Db = Dinv + ((size_t)b * nblk + cb) * NB * NB;
+    const int b_rows = min(BN, kw - half * BN);
+    if (b_rows <= 0) return;
+    const double* Db = Dinv + ((size_t)b * nblk + cb) * NB * NB + (size_t)half * BN * NB;
     TileAcc acc;
-    double* Cb = Mb + (size_t)ti * NB * ld + cb * NB;
-    gemm_nt_mainloop(Cb, ld, a_rows, Db, NB, kw, kw, smem2, acc);
+    double* Cb = Mb + (size_t)ti * NB * ld + cb * NB + half * BN;
+    gemm_nt_mainloop(Sb, NB, a_rows, Db, NB, b_rows, kw, smem2, acc);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
     for (int mi = 0; mi < 8; ++mi) {
@@ -208,7 +225,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_panel_scale(double* __restr
 #pragma unroll
         for (int ni = 0; ni < 4; ++ni) {
             int c = acc_col(warp, lane, ni);
-            if (c >= kw) continue;
+            if (c >= b_rows) continue;
             double2 v;
             v.x = sign * acc.v[mi][ni][0];
             v.y = sign * acc.v[mi][ni][1];
@@ -217,20 +234,24 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_panel_scale(double* __restr
     }
 }
 
-// trtri column step i, first half:  V[j, i] = sum_{p=j}^{i-1} V[j, p] * C[i, p]^T   (j < i)
-// with V = C^-T (upper, row-major) so that every contraction is K-contiguous.
-__global__ void __launch_bounds__(GEMM_THREADS, 1) k_trtri_accum(double* __restrict__ V, const double* __restrict__ Cm,
-                                                                 int ld, int Tp, int i, int B) {
+// trtri column step i, first half:  Pbuf[j] = sum_{p=j}^{i-1} V[j, p] * C[i, p]^T   (j < i)
+// with V = C^-T (upper, row-major) so that every contraction is K-contiguous; k_panel_scale
+// then writes V[j, i] = -Pbuf[j] * Dinv[i]^T.
+__global__ void __launch_bounds__(GEMM_THREADS, GEMM_CTAS_PER_SM)
+    k_trtri_accum(const double* __restrict__ V, const double* __restrict__ Cm, double* __restrict__ Pbuf, int ld,
+                  int Tp, int i, int B) {
     extern __shared__ __align__(16) double2 smem2[];
-    int j = blockIdx.x / B, b = blockIdx.x % B;
-    double* Vb = V + (size_t)b * Tp * ld;
+    int j = blockIdx.x / (2 * B), rem = blockIdx.x % (2 * B);
+    const int half = rem / B, b = rem % B;
+    const double* Vb = V + (size_t)b * Tp * ld;
     const double* Cb = Cm + (size_t)b * Tp * ld;
-    const int b_rows = blk_rows(Tp, i);
+    const int b_rows = min(BN, blk_rows(Tp, i) - half * BN);
+    if (b_rows <= 0) return;
     TileAcc acc;
-    gemm_nt_mainloop(Vb + (size_t)j * NB * ld + j * NB, ld, NB, Cb + (size_t)i * NB * ld + j * NB, ld, b_rows,
-                     (i - j) * NB, smem2, acc);
+    gemm_nt_mainloop(Vb + (size_t)j * NB * ld + j * NB, ld, NB, Cb + (size_t)(i * NB + half * BN) * ld + j * NB, ld,
+                     b_rows, (i - j) * NB, smem2, acc);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    double* Ob = Vb + (size_t)j * NB * ld + i * NB;
+    double* Ob = Pbuf + ((size_t)b * Tp + (size_t)j * NB) * NB + half * BN;
 #pragma unroll
     for (int mi = 0; mi < 8; ++mi) {
         int r = acc_row(warp, lane, mi);
@@ -238,10 +259,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_trtri_accum(double* __restr
         for (int ni = 0; ni < 4; ++ni) {
             int c = acc_col(warp, lane, ni);
             if (c >= b_rows) continue;
-            double2 v;
-            v.x = acc.v[mi][ni][0];
-            v.y = acc.v[mi][ni][1];
-            *reinterpret_cast<double2*>(Ob + (size_t)r * ld + c) = v;
+            *reinterpret_cast<double2*>(Ob + (size_t)r * NB + c) = make_double2(acc.v[mi][ni][0], acc.v[mi][ni][1]);
         }
     }
 }
@@ -251,19 +269,21 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_trtri_accum(double* __restr
 // written to: Work (padded, lower; aliases the buffer that held C), var_diag, and optionally
 // the dense symmetric cov [B,T,T].  Rows T / T+1 of Work get the right-hand sides (1, mu) of
 // the log-likelihood stage; the rest of the padding is identity.
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+__global__ void __launch_bounds__(GEMM_THREADS, GEMM_CTAS_PER_SM)
     k_lauum_cov(const double* __restrict__ V, int ld, int Tp, int T, const double* __restrict__ y_var, double jitter,
                 const double* __restrict__ mu, double* __restrict__ Work, double* __restrict__ var_diag,
                 double* __restrict__ cov_dense, int B) {
     extern __shared__ __align__(16) double2 smem2[];
-    int tile = blockIdx.x / B, b = blockIdx.x % B;
+    int tile = blockIdx.x / (2 * B), rem = blockIdx.x % (2 * B);
+    const int half = rem / B, b = rem % B;
     int ti, tj;
     tri_decode(tile, ti, tj);
     const double* Vb = V + (size_t)b * Tp * ld;
-    const int a_rows = blk_rows(Tp, ti), b_rows = blk_rows(Tp, tj);
+    const int a_rows = blk_rows(Tp, ti), b_rows = min(BN, blk_rows(Tp, tj) - half * BN);
+    if (b_rows <= 0) return;
     TileAcc acc;
-    gemm_nt_mainloop(Vb + (size_t)ti * NB * ld + ti * NB, ld, a_rows, Vb + (size_t)tj * NB * ld + ti * NB, ld, b_rows,
-                     Tp - ti * NB, smem2, acc);
+    gemm_nt_mainloop(Vb + (size_t)ti * NB * ld + ti * NB, ld, a_rows, Vb + (size_t)(tj * NB + half * BN) * ld + ti * NB,
+                     ld, b_rows, Tp - ti * NB, smem2, acc);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double* Wb = Work + (size_t)b * Tp * ld;
     const double* yv = y_var + (size_t)b * T;
@@ -283,7 +303,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
             double out[2];
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
-                int gc = tj * NB + c + e;
+                int gc = tj * NB + half * BN + c + e;
                 double val;
                 if (gr < T && gc < T) {
                     double ec = yv[gc] + jitter;
@@ -305,7 +325,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
                 }
                 out[e] = val;
             }
-            *reinterpret_cast<double2*>(Wb + (size_t)gr * ld + tj * NB + c) = make_double2(out[0], out[1]);
+            *reinterpret_cast<double2*>(Wb + (size_t)gr * ld + tj * NB + half * BN + c) = make_double2(out[0], out[1]);
         }
     }
 }

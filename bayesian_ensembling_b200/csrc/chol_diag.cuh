@@ -51,6 +51,19 @@ __device__ __forceinline__ void frag_nn(const double* __restrict__ A, int lda, c
     }
 }
 
+// 1/sqrt(x) to ~1 ulp without the library's special-case branches: MUFU seed + two Newton
+// steps (x <= 0 gives NaN/inf, which propagates like a failed LAPACK pivot would).
+__device__ __forceinline__ double fast_rsqrt(double x) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+#pragma unroll
+    for (int it = 0; it < 2; ++it) {
+        double e = fma(-x * y, y, 1.0);
+        y = fma(0.5 * y, e, y);
+    }
+    return y;
+}
+
 // One recursive-doubling product over all pairs of a level: for pair p (blocks of size s)
 //   OUT_p[s x s] = sign * X_p[s x s] * Y_p[s x s]        (row-major, "NN")
 // X_p = X + p * xs, etc.  Work is split in 8 x 16 output pieces over the 8 warps.
@@ -92,79 +105,79 @@ __global__ void __launch_bounds__(256, 1) k_diag_block(double* __restrict__ Mat,
     const int n = min(128, Tp - r0);        // rows present (multiple of 16)
     const int nr = max(0, min(n, T - r0));  // real (pivoting) columns
     double* Mb = Mat + (size_t)b * Tp * ld;
-    for (int e = tid; e < 128 * 128; e += 256) {
-        int i = e >> 7, j = e & 127;
-        double v = 0.0;
-        if (i < n && j < nr && j <= i) v = Mb[(size_t)(r0 + i) * ld + r0 + j];
-        S[i * DG_LD + j] = v;
+    // load the block (lower part, real columns); 8 independent global loads in flight per thread
+#pragma unroll 1
+    for (int e0 = tid; e0 < 128 * 128; e0 += 256 * 8) {
+        double v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            int e = e0 + u * 256, i = e >> 7, j = e & 127;
+            v[u] = (i < n && j < nr && j <= i) ? Mb[(size_t)(r0 + i) * ld + r0 + j] : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            int e = e0 + u * 256;
+            S[(e >> 7) * DG_LD + (e & 127)] = v[u];
+        }
     }
+    __shared__ int s_bad;
+    if (tid == 0) s_bad = 0;
     __syncthreads();
     const int nsteps = (nr + DG_W - 1) / DG_W;
     int bad = 0;
-    __shared__ int s_bad;
-    if (tid == 0) s_bad = 0;
+#pragma unroll 1
     for (int st = 0; st < nsteps; ++st) {
         const int c0 = st * DG_W;
         const int w = min(DG_W, nr - c0);
-        // ---- phase A: redundant 8 x 8 pivot factorisation + elimination of the thread's own row
+        // ---- phase A: every row-owning thread factors the 8 x 8 pivot block redundantly in its
+        // registers and eliminates its own row with it.  Branch-free: pivot rows >= w (padding or
+        // right-hand-side rows inside the band) enter the local copy as identity rows, so padded
+        // columns are never touched; the pivot rows themselves are produced by the same
+        // elimination with the columns right of their diagonal masked at the store.
         const bool act = tid < 128 && tid >= c0 && tid < n;
         double Lb[DG_W][DG_W];
+        double pv[DG_W];
         if (act) {
 #pragma unroll
             for (int i = 0; i < DG_W; ++i)
 #pragma unroll
                 for (int k = 0; k <= i; ++k) {
                     double v = S[(c0 + i) * DG_LD + c0 + k];
-                    if (i == k && i >= w) v = 1.0;  // padded columns: identity, never a pivot
-                    Lb[i][k] = v;
+                    Lb[i][k] = (i < w) ? v : (i == k ? 1.0 : 0.0);
                 }
+            const double* row = S + tid * DG_LD + c0;
+#pragma unroll
+            for (int k = 0; k < DG_W; k += 2) {
+                double2 t2 = *reinterpret_cast<const double2*>(row + k);
+                pv[k] = t2.x;
+                pv[k + 1] = t2.y;
+            }
         }
-        __syncthreads();  // every thread holds its copy of the pivot block before its rows are rewritten
+        __syncthreads();  // every thread holds its copy of the pivot block before rows are rewritten
         if (act) {
-            double rs[DG_W];
 #pragma unroll
             for (int j = 0; j < DG_W; ++j) {
-                double piv = Lb[j][j];
-                if (!(piv > 0.0) && bad == 0) bad = r0 + c0 + j + 1;
-                rs[j] = rsqrt(piv);
-                Lb[j][j] = piv * rs[j];
+                const double piv = Lb[j][j];
+                bad = (bad == 0 && !(piv > 0.0)) ? r0 + c0 + j + 1 : bad;
+                const double rs = fast_rsqrt(piv);
 #pragma unroll
-                for (int i = j + 1; i < DG_W; ++i) Lb[i][j] *= rs[j];
+                for (int i = j + 1; i < DG_W; ++i) Lb[i][j] *= rs;
 #pragma unroll
                 for (int k = j + 1; k < DG_W; ++k)
-                    if (k < w) {  // padded columns stay identity: they are never pivots
 #pragma unroll
-                        for (int i = k; i < DG_W; ++i) Lb[i][k] = fma(-Lb[i][j], Lb[k][j], Lb[i][k]);
-                    }
+                    for (int i = k; i < DG_W; ++i) Lb[i][k] = fma(-Lb[i][j], Lb[k][j], Lb[i][k]);
+                pv[j] *= rs;
+#pragma unroll
+                for (int k = j + 1; k < DG_W; ++k) pv[k] = fma(-pv[j], Lb[k][j], pv[k]);
             }
             if (tid == c0 && bad != 0 && s_bad == 0) s_bad = bad;
             double* row = S + tid * DG_LD + c0;
-            if (tid < c0 + DG_W) {
-                const int i = tid - c0;
 #pragma unroll
-                for (int ii = 0; ii < DG_W; ++ii)
-                    if (ii == i) {
-#pragma unroll
-                        for (int k = 0; k <= ii; ++k)
-                            if (k < w) row[k] = Lb[ii][k];
-                    }
-            } else {
-                double pv[DG_W];
-#pragma unroll
-                for (int k = 0; k < DG_W; k += 2) {
-                    double2 t2 = *reinterpret_cast<const double2*>(row + k);
-                    pv[k] = t2.x;
-                    pv[k + 1] = t2.y;
-                }
-#pragma unroll
-                for (int j = 0; j < DG_W; ++j) {
-                    pv[j] *= rs[j];
-#pragma unroll
-                    for (int k = j + 1; k < DG_W; ++k)
-                        if (k < w) pv[k] = fma(-pv[j], Lb[k][j], pv[k]);
-                }
-#pragma unroll
-                for (int k = 0; k < DG_W; k += 2) *reinterpret_cast<double2*>(row + k) = make_double2(pv[k], pv[k + 1]);
+            for (int k = 0; k < DG_W; k += 2) {
+                double2 o;
+                o.x = (c0 + k <= tid) ? pv[k] : 0.0;
+                o.y = (c0 + k + 1 <= tid) ? pv[k + 1] : 0.0;
+                *reinterpret_cast<double2*>(row + k) = o;
             }
         }
         __syncthreads();
@@ -173,23 +186,37 @@ __global__ void __launch_bounds__(256, 1) k_diag_block(double* __restrict__ Mat,
         const int ncs = (nr - p0 + 7) / 8;  // column strips (<= 0: nothing left)
         const int nrs = (n - p0) / 8;       // row strips
         if (ncs > 0) {
+#pragma unroll 1
             for (int fr = warp; fr < nrs; fr += 8) {
                 const double* Pr = S + (p0 + fr * 8) * DG_LD + c0;
                 const double a0 = Pr[g * DG_LD + q], a1 = Pr[g * DG_LD + 4 + q];
                 const int fc_end = min(fr, ncs - 1);
-#pragma unroll 4
-                for (int fc = 0; fc <= fc_end; ++fc) {
-                    const double* Pc = S + (p0 + fc * 8) * DG_LD + c0;
-                    double c[2] = {0.0, 0.0};
-                    dmma884(c[0], c[1], a0, Pc[g * DG_LD + q]);
-                    dmma884(c[0], c[1], a1, Pc[g * DG_LD + 4 + q]);
-                    const int r = p0 + fr * 8 + g, cc = p0 + fc * 8 + 2 * q;
-                    double* dst = S + r * DG_LD + cc;
-                    if (cc + 1 < nr && cc + 1 <= r) {
-                        double2 v = *reinterpret_cast<double2*>(dst);
-                        *reinterpret_cast<double2*>(dst) = make_double2(v.x - c[0], v.y - c[1]);
-                    } else if (cc < nr && cc <= r) {
-                        dst[0] -= c[0];
+                const int r = p0 + fr * 8 + g;
+#pragma unroll 1
+                for (int fc0 = 0; fc0 <= fc_end; fc0 += 4) {
+                    double b0[4], b1[4];
+                    double2 cv[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {  // loads first: 4 independent fragments in flight
+                        const int fc = min(fc0 + u, fc_end);
+                        const double* Pc = S + (p0 + fc * 8) * DG_LD + c0;
+                        b0[u] = Pc[g * DG_LD + q];
+                        b1[u] = Pc[g * DG_LD + 4 + q];
+                        cv[u] = *reinterpret_cast<const double2*>(S + r * DG_LD + p0 + fc * 8 + 2 * q);
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        double c[2] = {0.0, 0.0};
+                        dmma884(c[0], c[1], a0, b0[u]);
+                        dmma884(c[0], c[1], a1, b1[u]);
+                        const int fc = fc0 + u;
+                        const int cc = p0 + fc * 8 + 2 * q;
+                        if (fc <= fc_end) {
+                            double2 o;
+                            o.x = (cc < nr && cc <= r) ? cv[u].x - c[0] : cv[u].x;
+                            o.y = (cc + 1 < nr && cc + 1 <= r) ? cv[u].y - c[1] : cv[u].y;
+                            *reinterpret_cast<double2*>(S + r * DG_LD + cc) = o;
+                        }
                     }
                 }
             }

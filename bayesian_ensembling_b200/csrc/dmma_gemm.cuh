@@ -1,7 +1,11 @@
 // FP64 tensor-core (DMMA m8n8k4) tile engine for sm_100a.
 //
-// One CTA (256 threads = 8 warps as 2 x 4) computes a 128 x 128 tile of
+// One CTA (128 threads = 4 warps as 2 x 2, warp tile 64 x 32) computes a 128 x 64 tile of
 //     acc[i, j] = sum_k A[i, k] * B[j, k]            ("NT": both operands K-contiguous)
+// TWO such CTAs are resident per SM (248 registers x 128 threads and 96 KB of shared memory
+// each): while one sits in its prologue, epilogue or a stage barrier the other keeps the FP64
+// tensor pipe busy -- with one 256-thread CTA per SM the pipe measured 82% busy (ncu,
+// profiles/r01c) because every bubble of the only resident CTA was a bubble of the SM.
 // A and B tiles are streamed global -> shared with 16-byte cp.async into a 4-stage ring
 // (BK = 16 per stage).  Shared memory holds each operand in FRAGMENT-MAJOR order
 //     [row-block of 8][k-pair of 8][lane 32] x double2
@@ -21,14 +25,16 @@
 namespace be {
 
 constexpr int BM = 128;
-constexpr int BN = 128;
+constexpr int BN = 64;
 constexpr int BK = 16;
 constexpr int KP = BK / 8;  // k-pairs per stage
 constexpr int STAGES = 4;
-constexpr int GEMM_THREADS = 256;
-constexpr int OPERAND_STAGE_D2 = BM * BK / 2;            // double2 slots per operand per stage
-constexpr int STAGE_D2 = 2 * OPERAND_STAGE_D2;           // A + B
-constexpr int GEMM_SMEM_BYTES = STAGES * STAGE_D2 * 16;  // 131072
+constexpr int GEMM_THREADS = 128;
+constexpr int GEMM_CTAS_PER_SM = 2;
+constexpr int A_STAGE_D2 = BM * BK / 2;                  // double2 slots of the A operand per stage
+constexpr int B_STAGE_D2 = BN * BK / 2;
+constexpr int STAGE_D2 = A_STAGE_D2 + B_STAGE_D2;
+constexpr int GEMM_SMEM_BYTES = STAGES * STAGE_D2 * 16;  // 98304
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src, bool valid) {
     unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
@@ -47,12 +53,13 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
                  : "d"(a), "d"(b));
 }
 
-// Copies one operand stage (128 rows x 16 k) into fragment-major shared memory.
+// Copies one operand stage (ROWS rows x 16 k) into fragment-major shared memory.
 // g points at (row 0, k 0) of the tile; rows >= rows_valid are zero-filled.
+template <int ROWS>
 __device__ __forceinline__ void load_operand_stage(double2* sdst, const double* __restrict__ g, int ld,
                                                    int rows_valid, int tid) {
 #pragma unroll
-    for (int i = 0; i < (BM * BK / 2) / GEMM_THREADS; ++i) {
+    for (int i = 0; i < (ROWS * BK / 2) / GEMM_THREADS; ++i) {
         int c = tid + i * GEMM_THREADS;
         int m = c >> 3;   // row in tile
         int kc = c & 7;   // 16-byte chunk along k
@@ -68,10 +75,10 @@ struct TileAcc {
 };
 
 // Thread's coordinates inside the 128 x 128 tile for accumulator (mi, ni, e).
-__device__ __forceinline__ int acc_row(int warp, int lane, int mi) { return (warp >> 2) * 64 + mi * 8 + (lane >> 2); }
-__device__ __forceinline__ int acc_col(int warp, int lane, int ni) { return (warp & 3) * 32 + ni * 8 + 2 * (lane & 3); }
+__device__ __forceinline__ int acc_row(int warp, int lane, int mi) { return (warp >> 1) * 64 + mi * 8 + (lane >> 2); }
+__device__ __forceinline__ int acc_col(int warp, int lane, int ni) { return (warp & 1) * 32 + ni * 8 + 2 * (lane & 3); }
 
-// acc (+)= sum over k in [0, klen) of A[i,k] * B[j,k]; klen must be a multiple of BK (buffers are
+// acc (+)= sum over k in [0, klen) of A[i,k] * B[j,k] for a 128 (i) x 64 (j) tile; klen must be a multiple of BK (buffers are
 // padded so that it always is).  A, B point at (tile row 0, k 0).  With ZERO_INIT = false the
 // caller has preloaded acc (e.g. with -C, so that the epilogue is a pure store and the C read
 // overlaps the pipeline prologue instead of serialising behind the mainloop).
@@ -82,8 +89,8 @@ __device__ __forceinline__ void gemm_nt_mainloop(const double* __restrict__ A, i
     const int tid = threadIdx.x;
     const int lane = tid & 31;
     const int warp = tid >> 5;
-    const int wm = warp >> 2;
-    const int wn = warp & 3;
+    const int wm = warp >> 1;
+    const int wn = warp & 1;
     if (ZERO_INIT) {
 #pragma unroll
         for (int mi = 0; mi < 8; ++mi)
@@ -95,8 +102,8 @@ __device__ __forceinline__ void gemm_nt_mainloop(const double* __restrict__ A, i
 #pragma unroll
     for (int s = 0; s < STAGES - 1; ++s) {
         if (s < ktiles) {
-            load_operand_stage(smem + s * STAGE_D2, A + s * BK, lda, a_rows, tid);
-            load_operand_stage(smem + s * STAGE_D2 + OPERAND_STAGE_D2, B + s * BK, ldb, b_rows, tid);
+            load_operand_stage<BM>(smem + s * STAGE_D2, A + s * BK, lda, a_rows, tid);
+            load_operand_stage<BN>(smem + s * STAGE_D2 + A_STAGE_D2, B + s * BK, ldb, b_rows, tid);
         }
         cp_async_commit();
     }
@@ -107,13 +114,13 @@ __device__ __forceinline__ void gemm_nt_mainloop(const double* __restrict__ A, i
             int nk = kt + STAGES - 1;
             if (nk < ktiles) {
                 int s = nk % STAGES;
-                load_operand_stage(smem + s * STAGE_D2, A + nk * BK, lda, a_rows, tid);
-                load_operand_stage(smem + s * STAGE_D2 + OPERAND_STAGE_D2, B + nk * BK, ldb, b_rows, tid);
+                load_operand_stage<BM>(smem + s * STAGE_D2, A + nk * BK, lda, a_rows, tid);
+                load_operand_stage<BN>(smem + s * STAGE_D2 + A_STAGE_D2, B + nk * BK, ldb, b_rows, tid);
             }
             cp_async_commit();
         }
         const double2* sA = smem + (kt % STAGES) * STAGE_D2;
-        const double2* sB = sA + OPERAND_STAGE_D2;
+        const double2* sB = sA + A_STAGE_D2;
 #pragma unroll
         for (int p = 0; p < KP; ++p) {
             double2 a[8], b[4];

@@ -177,6 +177,30 @@ class Backend:
         _lib.check(self.ctx, rc, "be_gp_posterior")
         return out
 
+    def vgp_fit(self, X, y_mean, y_var, n_iters, gamma=0.5, lr=0.01, train_hypers=True, init_variance=1.0,
+                init_lengthscale=1.0, jitter=DEFAULT_JITTER, want_scale_tri=True):
+        """The natgrad + Adam loop of models.py:185-220 on the device.  Returns (PosteriorBatch,
+        variance [B], lengthscale [B]) with the trained kernel hyper-parameters."""
+        X = self._in(X)
+        B, T, R = X.shape
+        ym = self._in(y_mean, (B, T), "y_mean")
+        yv = self._in(y_var, (B, T), "y_var")
+        var = torch.full((B,), float(init_variance), dtype=torch.float64, device=self.device)
+        ls = torch.full((B,), float(init_lengthscale), dtype=torch.float64, device=self.device)
+        out = PosteriorBatch(
+            mu=self._new(B, T), var_diag=self._new(B, T), mvn_stats=self._new(B, 4),
+            info_fit=self._new(B, dtype=torch.int32), info_dist=self._new(B, dtype=torch.int32),
+            cov=self._new(B, T, T), scale_tri=self._new(B, T, T) if want_scale_tri else None)
+        nbytes = int(self.lib.be_vgp_fit_workspace_bytes(B, T, R))
+        ws = self._ws(nbytes)
+        self._sync_stream()
+        rc = self.lib.be_vgp_fit(
+            self.ctx, _ptr(X), _ptr(ym), _ptr(yv), B, T, R, int(n_iters), float(gamma), float(lr), int(bool(train_hypers)),
+            float(jitter), _ptr(var), _ptr(ls), _ptr(out.mu), _ptr(out.var_diag), _ptr(out.cov), _ptr(out.scale_tri),
+            _ptr(out.mvn_stats), _ptr(out.info_fit), _ptr(out.info_dist), _ptr(ws), nbytes)
+        _lib.check(self.ctx, rc, "be_vgp_fit")
+        return out, var, ls
+
     # ------------------------------------------------------------------ a3
     def mvn_from_cov(self, mu, cov, want_scale_tri=True):
         cov = self._in(cov)

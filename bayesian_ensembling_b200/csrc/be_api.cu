@@ -7,17 +7,19 @@
 
 #include "../../include/be_b200.h"
 #include "be_kernels.cuh"
+#include "vgp_kernels.cuh"
 
 using namespace be;
 
 // kernel families of the profiler (be_ctx_profile_*): one per kernel of be_kernels.cuh
 enum Family {
     F_INPUTS = 0, F_GRAM, F_DIAG, F_PANEL, F_SYRK, F_TRTRI, F_LAUUM, F_MEAN, F_STATS, F_COPY, F_WEIGHTS, F_BARY,
-    F_COUNT
+    F_GEMM, F_VGP_MISC, F_COUNT
 };
 static const char* const kFamilyName[F_COUNT] = {
     "k_gpdtw1d_inputs", "k_matern32", "k_diag_block", "k_panel_scale", "k_chol_update", "k_trtri_accum",
-    "k_lauum_cov", "k_posterior_mean", "k_mvn_stats", "copy/pad", "k_loglik_weights", "k_barycentre"};
+    "k_lauum_cov", "k_posterior_mean", "k_mvn_stats", "copy/pad", "k_loglik_weights", "k_barycentre",
+    "k_gemm_nt", "vgp elementwise"};
 
 struct ProfRecord {
     int family;
@@ -118,6 +120,13 @@ int ensure_kernel_attrs(be_ctx* ctx) {
     BE_CUDA(cudaFuncSetAttribute(k_diag_block, cudaFuncAttributeMaxDynamicSharedMemorySize, DIAG_SMEM_BYTES));
     BE_CUDA(cudaFuncSetAttribute(k_matern32<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     BE_CUDA(cudaFuncSetAttribute(k_matern32<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    BE_CUDA(cudaFuncSetAttribute(k_matern32<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    BE_CUDA(cudaFuncSetAttribute(k_gemm_nt<EpiStore>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
+    BE_CUDA(cudaFuncSetAttribute(k_gemm_nt<EpiNatP>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
+    BE_CUDA(cudaFuncSetAttribute(k_gemm_nt<EpiLbarT>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
+    BE_CUDA(cudaFuncSetAttribute(k_gemm_nt<EpiPhi>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
+    BE_CUDA(cudaFuncSetAttribute(k_gemm_nt<EpiKbarGrad>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
+    BE_CUDA(cudaFuncSetAttribute(k_gemm_nt<EpiCov>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
     g_attr_done = true;
     return BE_OK;
 }
@@ -187,6 +196,116 @@ size_t padded_matrix_doubles(int B, int T) {
 }
 size_t dinv_doubles(int B, int T) { return (size_t)B * num_blocks(pad_dim(T)) * NB * NB; }
 size_t pbuf_doubles(int B, int T) { return (size_t)B * pad_dim(T) * NB; }
+
+template <class Epi>
+int launch_gemm(be_ctx* ctx, const GemmArgs& g, const Epi& epi) {
+    const unsigned grid = (unsigned)((size_t)gemm_tiles(g.nblk, g.shape) * 2 * g.B);
+    // executed flops (the contraction ranges already skip structural zeros at block level)
+    double kavg = g.klo == KLO_ZERO && g.khi == KHI_END ? (double)g.Tp : 0.5 * g.Tp;
+    Prof pr(ctx, F_GEMM, 2.0 * g.B * (double)gemm_tiles(g.nblk, g.shape) * NB * NB * kavg, 0.0);
+    k_gemm_nt<Epi><<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, ctx->stream>>>(g, epi);
+    BE_LAUNCHED();
+    return BE_OK;
+}
+
+inline GemmArgs gemm_args(const double* A, const double* Bm, int Tp, int B, int shape, int klo, int khi) {
+    GemmArgs g;
+    g.A = A;
+    g.Bm = Bm;
+    g.lda = g.ldb = Tp;
+    g.strideA = g.strideB = (size_t)Tp * Tp;
+    g.Tp = Tp;
+    g.nblk = num_blocks(Tp);
+    g.B = B;
+    g.shape = shape;
+    g.klo = klo;
+    g.khi = khi;
+    return g;
+}
+
+struct VgpBuffers {
+    double *Mk, *Ut, *Wt, *P, *M2, *VP, *VL, *S, *Zt;  // [B][Tp][Tp] each
+    double *DinvL, *DinvP, *Pbuf;
+    double *n1, *qmu, *r, *zeros;  // [B][T]
+    double *u, *am, *av, *partial;
+    int *step, *info_tmp;
+};
+
+// One natural-gradient step (models.py:209) followed, if train, by one Adam step (models.py:210).
+int vgp_iteration(be_ctx* ctx, const VgpBuffers& w, const double* X, const double* y_mean, const double* y_var,
+                  double* variance, double* lengthscale, double jitter, double gamma, double lr, int train, int B, int T,
+                  int R, int* info_fit) {
+    const int Tp = pad_dim(T), ld = Tp, nblk = num_blocks(Tp);
+    const int ntl = nblk * (nblk + 1) / 2;
+    const int nt32 = (Tp + 31) / 32;
+    const unsigned rows_grid = grid1d((size_t)B * T, 8);
+    int rc;
+    // L = chol(K + jitter I)
+    k_matern32<1><<<(unsigned)((size_t)ntl * B), 256, matern_smem(R), ctx->stream>>>(X, B, T, R, variance, lengthscale,
+                                                                                   w.zeros, w.zeros, jitter, w.Mk, Tp,
+                                                                                   ld, ntl);
+    BE_LAUNCHED();
+    if ((rc = potrf_padded(ctx, w.Mk, Tp, T, B, w.DinvL, w.Pbuf, w.VL, info_fit)) != BE_OK) return rc;
+    // Ut = L^T, Wt = L^T D^-1
+    k_transpose<<<(unsigned)((size_t)nt32 * nt32 * B), 256, 0, ctx->stream>>>(w.Mk, ld, Tp, T, 1, w.Ut, w.Wt, y_var, B);
+    BE_LAUNCHED();
+    // theta_1 <- (1-gamma) theta_1 + gamma L^T D^-1 y
+    k_rowdot<<<rows_grid, 256, 0, ctx->stream>>>(w.Ut, ld, Tp, T, 2, 1, nullptr, y_mean, y_var, gamma, w.n1, B);
+    BE_LAUNCHED();
+    // P <- (1-gamma) P + gamma (I + L^T D^-1 L)
+    {
+        EpiNatP e;
+        e.P = w.P; e.work = w.M2; e.ld = ld; e.Tp = Tp; e.T = T; e.gamma = gamma;
+        if ((rc = launch_gemm(ctx, gemm_args(w.Wt, w.Ut, Tp, B, SHAPE_LOWER, KLO_TA, KHI_END), e)) != BE_OK) return rc;
+    }
+    // S = P^-1 (potrf, trtri, lauum), q_mu = S theta_1
+    if ((rc = potrf_padded(ctx, w.M2, Tp, T, B, w.DinvP, w.Pbuf, w.VP, w.info_tmp)) != BE_OK) return rc;
+    if ((rc = trtri_padded(ctx, w.VP, w.M2, Tp, B, w.DinvP, w.Pbuf)) != BE_OK) return rc;
+    {
+        EpiStore e;
+        e.out = w.S; e.sub = nullptr; e.ld = ld; e.Tp = Tp; e.T = T; e.pad_diag = 1.0; e.mirror = 1;
+        if ((rc = launch_gemm(ctx, gemm_args(w.VP, w.VP, Tp, B, SHAPE_LOWER, KLO_TA, KHI_END), e)) != BE_OK) return rc;
+    }
+    k_rowdot<<<rows_grid, 256, 0, ctx->stream>>>(w.S, ld, Tp, T, 0, 0, w.n1, nullptr, nullptr, 0.0, w.qmu, B);
+    BE_LAUNCHED();
+    if (!train) return BE_OK;
+    // r = D^-1 (y - L q_mu)
+    k_rowdot<<<rows_grid, 256, 0, ctx->stream>>>(w.Mk, ld, Tp, T, 1, 2, w.qmu, y_mean, y_var, 0.0, w.r, B);
+    BE_LAUNCHED();
+    // LbarT = q_mu r^T - (S L^T) D^-1
+    {
+        EpiLbarT e;
+        e.out = w.Zt; e.q_mu = w.qmu; e.r = w.r; e.y_var = y_var; e.ld = ld; e.Tp = Tp; e.T = T;
+        if ((rc = launch_gemm(ctx, gemm_args(w.S, w.Mk, Tp, B, SHAPE_FULL, KLO_ZERO, KHI_TB), e)) != BE_OK) return rc;
+    }
+    // Phi = tril(L^T Lbar), halved diagonal  (M2 is free again)
+    {
+        EpiPhi e;
+        e.out = w.M2; e.ld = ld; e.Tp = Tp; e.T = T;
+        if ((rc = launch_gemm(ctx, gemm_args(w.Ut, w.Zt, Tp, B, SHAPE_LOWER, KLO_TA, KHI_END), e)) != BE_OK) return rc;
+    }
+    // VL = L^-T
+    if ((rc = trtri_padded(ctx, w.VL, w.Mk, Tp, B, w.DinvL, w.Pbuf)) != BE_OK) return rc;
+    // YT = VL Phi^T  (block upper), into Wt
+    {
+        EpiStore e;
+        e.out = w.Wt; e.sub = nullptr; e.ld = ld; e.Tp = Tp; e.T = T; e.pad_diag = 0.0; e.mirror = 0;
+        if ((rc = launch_gemm(ctx, gemm_args(w.VL, w.M2, Tp, B, SHAPE_UPPER, KLO_TA, KHI_TB), e)) != BE_OK) return rc;
+    }
+    // g = sum Kbar_u .* dK/dtheta with Kbar_u = VL YT^T
+    const int ctas = nblk * nblk * 2;
+    BE_CUDA(cudaMemsetAsync(w.partial, 0, sizeof(double) * 2 * (size_t)B * ctas, ctx->stream));
+    {
+        EpiKbarGrad e;
+        e.X = X; e.variance = variance; e.lengthscale = lengthscale; e.partial = w.partial; e.T = T; e.R = R;
+        e.ctas_per_problem = ctas; e.g0 = 0.0; e.g1 = 0.0;
+        if ((rc = launch_gemm(ctx, gemm_args(w.VL, w.Wt, Tp, B, SHAPE_FULL, KLO_MAX, KHI_END), e)) != BE_OK) return rc;
+    }
+    k_vgp_adam<<<grid1d(B, 128), 128, 0, ctx->stream>>>(w.partial, ctas, B, lr, 0.9, 0.999, 1e-7, w.u, w.am, w.av, w.step,
+                                                       variance, lengthscale);
+    BE_LAUNCHED();
+    return BE_OK;
+}
 
 }  // namespace
 
@@ -620,6 +739,163 @@ int be_barycentre_1d_finish(be_ctx* ctx, const double* partial, int C, int N, do
     k_barycentre_finish<<<grid1d((size_t)C * N, 128), 128, 0, ctx->stream>>>(partial, C, N, tolerance, init_var,
                                                                              max_iters, mu, sigma, iters);
     BE_LAUNCHED();
+    return BE_OK;
+}
+
+size_t be_vgp_fit_workspace_bytes(int B, int T, int R) {
+    (void)R;
+    size_t Tp = pad_dim(T);
+    size_t mat = align_up(padded_matrix_doubles(B, T) * 8, 256);
+    size_t vec = align_up((size_t)B * T * 8, 256);
+    size_t ctas = (size_t)num_blocks((int)Tp) * num_blocks((int)Tp) * 2;
+    return 9 * mat + 2 * align_up(dinv_doubles(B, T) * 8, 256) + align_up(pbuf_doubles(B, T) * 8, 256) + 4 * vec +
+           3 * align_up((size_t)B * 2 * 8, 256) + align_up((size_t)B * ctas * 2 * 8, 256) +
+           2 * align_up((size_t)B * 4, 256) + 4096;
+}
+
+int be_vgp_fit(be_ctx* ctx, const double* X, const double* y_mean, const double* y_var, int B, int T, int R,
+               int n_iters, double gamma, double lr, int train_hypers, double jitter, double* variance,
+               double* lengthscale, double* mu, double* var_diag, double* cov, double* scale_tri, double* mvn_stats,
+               int* info_fit, int* info_dist, void* workspace, size_t workspace_bytes) {
+    if (!ctx) return -1;
+    if (!X) return -2;
+    if (!y_mean) return -3;
+    if (!y_var) return -4;
+    if (B <= 0) return -5;
+    if (T <= 0) return -6;
+    if (R <= 0 || matern_smem(R) > 200 * 1024) return -7;
+    if (n_iters < 0) return -8;
+    if (!(gamma > 0.0 && gamma <= 1.0)) return -9;
+    if (!(jitter >= 0.0)) return -12;
+    if (!variance) return -13;
+    if (!lengthscale) return -14;
+    if (!mu) return -15;
+    if (!var_diag) return -16;
+    if (!cov) return -17;
+    if (!mvn_stats) return -19;
+    if (!info_fit) return -20;
+    if (!info_dist) return -21;
+    if (!workspace || workspace_bytes < be_vgp_fit_workspace_bytes(B, T, R)) return BE_ERR_WORKSPACE;
+    const int Tp = pad_dim(T), ld = Tp, nblk = num_blocks(Tp);
+    const size_t nm = padded_matrix_doubles(B, T);
+    Carver cv(workspace, workspace_bytes);
+    VgpBuffers w;
+    w.Mk = cv.take<double>(nm); w.Ut = cv.take<double>(nm); w.Wt = cv.take<double>(nm); w.P = cv.take<double>(nm);
+    w.M2 = cv.take<double>(nm); w.VP = cv.take<double>(nm); w.VL = cv.take<double>(nm); w.S = cv.take<double>(nm);
+    w.Zt = cv.take<double>(nm);
+    w.DinvL = cv.take<double>(dinv_doubles(B, T)); w.DinvP = cv.take<double>(dinv_doubles(B, T));
+    w.Pbuf = cv.take<double>(pbuf_doubles(B, T));
+    w.n1 = cv.take<double>((size_t)B * T); w.qmu = cv.take<double>((size_t)B * T); w.r = cv.take<double>((size_t)B * T);
+    w.zeros = cv.take<double>((size_t)B * T);
+    w.u = cv.take<double>((size_t)B * 2); w.am = cv.take<double>((size_t)B * 2); w.av = cv.take<double>((size_t)B * 2);
+    w.partial = cv.take<double>((size_t)B * nblk * nblk * 2 * 2);
+    w.step = cv.take<int>(B); w.info_tmp = cv.take<int>(B);
+    if (!w.info_tmp) return BE_ERR_WORKSPACE;
+
+    cudaStream_t user_stream = ctx->stream;
+    BE_CUDA(cudaMemsetAsync(info_fit, 0, sizeof(int) * B, user_stream));
+    BE_CUDA(cudaMemsetAsync(info_dist, 0, sizeof(int) * B, user_stream));
+    BE_CUDA(cudaMemsetAsync(w.info_tmp, 0, sizeof(int) * B, user_stream));
+    BE_CUDA(cudaMemsetAsync(w.n1, 0, sizeof(double) * B * T, user_stream));
+    BE_CUDA(cudaMemsetAsync(w.qmu, 0, sizeof(double) * B * T, user_stream));
+    BE_CUDA(cudaMemsetAsync(w.zeros, 0, sizeof(double) * B * T, user_stream));
+    BE_CUDA(cudaMemsetAsync(w.am, 0, sizeof(double) * B * 2, user_stream));
+    BE_CUDA(cudaMemsetAsync(w.av, 0, sizeof(double) * B * 2, user_stream));
+    BE_CUDA(cudaMemsetAsync(w.step, 0, sizeof(int) * B, user_stream));
+    k_set_identity<<<ctx->sm_count * 8, 256, 0, user_stream>>>(w.P, ld, Tp, B);  // q_sqrt = I
+    BE_LAUNCHED();
+    k_set_identity<<<ctx->sm_count * 8, 256, 0, user_stream>>>(w.S, ld, Tp, B);
+    BE_LAUNCHED();
+    k_vgp_unconstrain<<<grid1d(B, 128), 128, 0, user_stream>>>(variance, lengthscale, B, w.u);
+    BE_LAUNCHED();
+
+    // The training loop: one iteration is captured into a CUDA graph on a private stream and replayed
+    // n_iters times -- ~60 small launches per iteration would otherwise be launch-latency bound.
+    if (n_iters > 0) {
+        cudaStream_t cap;
+        cudaEvent_t fork, join;
+        BE_CUDA(cudaStreamCreateWithFlags(&cap, cudaStreamNonBlocking));
+        BE_CUDA(cudaEventCreateWithFlags(&fork, cudaEventDisableTiming));
+        BE_CUDA(cudaEventCreateWithFlags(&join, cudaEventDisableTiming));
+        BE_CUDA(cudaEventRecord(fork, user_stream));
+        BE_CUDA(cudaStreamWaitEvent(cap, fork, 0));
+        const bool prof = ctx->profiling;
+        const long long launches0 = ctx->launches;
+        ctx->profiling = false;
+        ctx->stream = cap;
+        cudaGraph_t graph = nullptr;
+        cudaGraphExec_t exec = nullptr;
+        cudaError_t ce = cudaStreamBeginCapture(cap, cudaStreamCaptureModeThreadLocal);
+        int rc = BE_OK;
+        if (ce == cudaSuccess) {
+            rc = vgp_iteration(ctx, w, X, y_mean, y_var, variance, lengthscale, jitter, gamma, lr, train_hypers, B, T, R,
+                               info_fit);
+            ce = cudaStreamEndCapture(cap, &graph);
+        }
+        const long long per_iter = ctx->launches - launches0;
+        if (ce == cudaSuccess && rc == BE_OK) ce = cudaGraphInstantiate(&exec, graph, 0);
+        if (ce == cudaSuccess && rc == BE_OK) {
+            for (int it = 0; it < n_iters && ce == cudaSuccess; ++it) ce = cudaGraphLaunch(exec, cap);
+            ctx->launches = launches0 + per_iter * n_iters;
+        }
+        if (exec) cudaGraphExecDestroy(exec);
+        if (graph) cudaGraphDestroy(graph);
+        ctx->stream = user_stream;
+        ctx->profiling = prof;
+        cudaError_t ce2 = cudaEventRecord(join, cap);
+        if (ce2 == cudaSuccess) ce2 = cudaStreamWaitEvent(user_stream, join, 0);
+        cudaEventDestroy(fork);
+        cudaEventDestroy(join);
+        // the private stream can be destroyed once its work is ordered before user_stream's next op
+        cudaStreamDestroy(cap);
+        if (rc != BE_OK) return rc;
+        if (ce != cudaSuccess) return cuda_fail(ctx, ce, "vgp graph");
+        if (ce2 != cudaSuccess) return cuda_fail(ctx, ce2, "vgp join");
+    }
+
+    // predict_f(X, full_cov=True) at the final hyper-parameters (models.py:217) + diag(y_var) (:220)
+    const int ntl = nblk * (nblk + 1) / 2;
+    const int nt32 = (Tp + 31) / 32;
+    int rc;
+    k_matern32<1><<<(unsigned)((size_t)ntl * B), 256, matern_smem(R), ctx->stream>>>(X, B, T, R, variance, lengthscale,
+                                                                                   w.zeros, w.zeros, jitter, w.Mk, Tp,
+                                                                                   ld, ntl);
+    BE_LAUNCHED();
+    if ((rc = potrf_padded(ctx, w.Mk, Tp, T, B, w.DinvL, w.Pbuf, w.VL, info_fit)) != BE_OK) return rc;
+    if ((rc = trtri_padded(ctx, w.VL, w.Mk, Tp, B, w.DinvL, w.Pbuf)) != BE_OK) return rc;
+    k_matern32<2><<<(unsigned)((size_t)nblk * nblk * B), 256, matern_smem(R), ctx->stream>>>(
+        X, B, T, R, variance, lengthscale, nullptr, nullptr, 0.0, w.Ut, Tp, ld, nblk * nblk);  // Ut := K (no jitter)
+    BE_LAUNCHED();
+    k_transpose<<<(unsigned)((size_t)nt32 * nt32 * B), 256, 0, ctx->stream>>>(w.VL, ld, Tp, T, 2, w.Wt, nullptr, nullptr,
+                                                                             B);  // Wt := Lm^-1 (lower)
+    BE_LAUNCHED();
+    {   // AT = K Lm^-T  (= A^T, A = Lm^-1 K)
+        EpiStore e;
+        e.out = w.Zt; e.sub = nullptr; e.ld = ld; e.Tp = Tp; e.T = T; e.pad_diag = 0.0; e.mirror = 0;
+        if ((rc = launch_gemm(ctx, gemm_args(w.Ut, w.Wt, Tp, B, SHAPE_FULL, KLO_ZERO, KHI_TB), e)) != BE_OK) return rc;
+    }
+    k_rowdot<<<grid1d((size_t)B * T, 8), 256, 0, ctx->stream>>>(w.Zt, ld, Tp, T, 0, 0, w.qmu, nullptr, nullptr, 0.0, mu, B);
+    BE_LAUNCHED();
+    {   // M2 = AT S - AT
+        EpiStore e;
+        e.out = w.M2; e.sub = w.Zt; e.ld = ld; e.Tp = Tp; e.T = T; e.pad_diag = 0.0; e.mirror = 0;
+        if ((rc = launch_gemm(ctx, gemm_args(w.Zt, w.S, Tp, B, SHAPE_FULL, KLO_ZERO, KHI_END), e)) != BE_OK) return rc;
+    }
+    {   // cov = K + (AT (S - I)) AT^T + D
+        EpiCov e;
+        e.K = w.Ut; e.y_var = y_var; e.cov = cov; e.var_diag = var_diag; e.ld = ld; e.Tp = Tp; e.T = T;
+        if ((rc = launch_gemm(ctx, gemm_args(w.M2, w.Zt, Tp, B, SHAPE_LOWER, KLO_ZERO, KHI_END), e)) != BE_OK) return rc;
+    }
+    // Distribution(mu, cov, MultivariateNormalFullCovariance): data.py:38-39
+    k_pad_from_dense<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(cov, mu, B, T, Tp, Tp, w.P, 1);
+    BE_LAUNCHED();
+    if ((rc = potrf_padded(ctx, w.P, Tp, T, B, w.DinvP, w.Pbuf, nullptr, info_dist)) != BE_OK) return rc;
+    k_mvn_stats<<<B, 256, 0, ctx->stream>>>(w.P, ld, Tp, T, mvn_stats);
+    BE_LAUNCHED();
+    if (scale_tri) {
+        k_copy_out_tri<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(w.P, ld, Tp, T, scale_tri, B);
+        BE_LAUNCHED();
+    }
     return BE_OK;
 }
 

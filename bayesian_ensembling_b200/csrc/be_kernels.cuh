@@ -50,6 +50,7 @@ __global__ void k_gpdtw1d_inputs(const double* __restrict__ reals, int B, int R,
 // Matern-3/2 gram (gpflow Matern32 on X/l with the |x|^2+|y|^2-2xy expansion, r2 clamped at
 // 1e-36).  One CTA per 128 x 128 tile.  MODE 0: dense symmetric K [B,T,T].
 // MODE 1: padded lower tiles of M = K + diag(y_var + jitter), padding identity, row T = y_mean.
+// MODE 2: padded [Tp,ld] K, all tiles, no noise, zero padding (predict_f's Kmn, models.py:217).
 // --------------------------------------------------------------------------------------
 template <int MODE>
 __global__ void __launch_bounds__(256) k_matern32(const double* __restrict__ X, int B, int T, int R,
@@ -69,7 +70,7 @@ __global__ void __launch_bounds__(256) k_matern32(const double* __restrict__ X, 
     if (MODE == 1) {
         tri_decode(tile, ti, tj);
     } else {
-        int nt = (T + NB - 1) / NB;
+        int nt = ((MODE == 2 ? Tp : T) + NB - 1) / NB;
         ti = tile / nt;
         tj = tile % nt;
     }
@@ -93,7 +94,7 @@ __global__ void __launch_bounds__(256) k_matern32(const double* __restrict__ X, 
         sj[r] = s;
     }
     __syncthreads();
-    const int lim = MODE == 1 ? Tp : T;
+    const int lim = MODE == 0 ? T : Tp;
     for (int e = threadIdx.x; e < NB * NB; e += blockDim.x) {
         int i = e >> 7, j = e & 127;
         int gi = ti * NB + i, gj = tj * NB + j;
@@ -109,9 +110,9 @@ __global__ void __launch_bounds__(256) k_matern32(const double* __restrict__ X, 
         } else if (MODE == 1 && gi == T && gj < T) {
             val = y_mean[(size_t)b * T + gj];
         } else {
-            val = gi == gj ? 1.0 : 0.0;
+            val = (MODE == 1 && gi == gj) ? 1.0 : 0.0;
         }
-        if (MODE == 1)
+        if (MODE != 0)
             out[(size_t)b * Tp * ld + (size_t)gi * ld + gj] = val;
         else
             out[(size_t)b * T * T + (size_t)gi * T + gj] = val;
@@ -216,7 +217,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, GEMM_CTAS_PER_SM)
     const double* Db = Dinv + ((size_t)b * nblk + cb) * NB * NB + (size_t)half * BN * NB;
     TileAcc acc;
     double* Cb = Mb + (size_t)ti * NB * ld + cb * NB + half * BN;
-    gemm_nt_mainloop(Sb, NB, a_rows, Db, NB, b_rows, kw, smem2, acc);
+    // Dinv is lower triangular: output columns [half*64, half*64+64) only contract k < (half+1)*64
+    const int klen = min(kw, (half + 1) * BN);
+    gemm_nt_mainloop(Sb, NB, a_rows, Db, NB, b_rows, klen, smem2, acc);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
     for (int mi = 0; mi < 8; ++mi) {

@@ -230,6 +230,7 @@ __global__ void __launch_bounds__(256, 1) k_diag_block(double* __restrict__ Mat,
     for (int e = tid; e < 128 * 128; e += 256) {
         int r = e >> 7, c = e & 127;
         if (r < n && c <= r && c < nr) Mb[(size_t)(r0 + r) * ld + r0 + c] = S[r * DG_LD + c];
+        if (r < nr && c > r && c < n) Mb[(size_t)(r0 + r) * ld + r0 + c] = 0.0;  // clean strict upper part
     }
     __syncthreads();
     // ---- inverse of blockdiag(L11, I): rows >= nr become identity rows first

@@ -1,0 +1,361 @@
+// Kernels of the VGP training loop GPDTW1D.fit runs (ensembles/models.py:185-220): whitened
+// variational GP, heteroskedastic Gaussian likelihood, natural-gradient steps on q and Adam
+// steps on the two Matern-3/2 hyper-parameters, then predict_f(full_cov=True).
+//
+// Everything O(T^3) goes through the same FP64 DMMA tile engine as the fixed-theta path: one
+// generic batched "NT" tile kernel (k_gemm_nt) whose tile set, contraction range and epilogue
+// are template / argument choices, plus the blocked potrf / trtri of be_api.cu.  State is kept
+// in NATURAL parameters across iterations (P = S^-1 = -2 theta_2 and n1 = theta_1), which is
+// the fixed point form of gpflow's natgrad step for this conjugate model ("L2").
+#pragma once
+#include "be_kernels.cuh"
+
+namespace be {
+
+enum { SHAPE_FULL = 0, SHAPE_LOWER = 1, SHAPE_UPPER = 2 };  // block pairs (tA, tB): all / tA>=tB / tA<=tB
+enum { KLO_ZERO = 0, KLO_TA = 1, KLO_MAX = 2 };             // first contracted column: 0 / tA*128 / max(tA,tB)*128
+enum { KHI_END = 0, KHI_TB = 1, KHI_TA = 2 };               // one past the last: Tp / (tB+1)*128 / (tA+1)*128
+
+struct GemmArgs {
+    const double* A;
+    const double* Bm;
+    int lda, ldb;
+    size_t strideA, strideB;  // per-problem strides (doubles)
+    int Tp, nblk, B;
+    int shape, klo, khi;
+};
+
+__host__ __device__ inline int gemm_tiles(int nblk, int shape) {
+    return shape == SHAPE_FULL ? nblk * nblk : nblk * (nblk + 1) / 2;
+}
+
+// C-tile(tA, tB)[i, j] = sum_{k in [k0, k1)} A[tA*128 + i, k] * Bm[tB*128 + j, k]; the epilogue
+// object decides what to do with every pair of adjacent columns.
+template <class Epi>
+__global__ void __launch_bounds__(GEMM_THREADS, GEMM_CTAS_PER_SM) k_gemm_nt(GemmArgs g, Epi epi) {
+    extern __shared__ __align__(16) double2 smem2[];
+    int tile = blockIdx.x / (2 * g.B), rem = blockIdx.x % (2 * g.B);
+    const int half = rem / g.B, b = rem % g.B;
+    int tA, tB;
+    if (g.shape == SHAPE_FULL) {
+        tA = tile / g.nblk;
+        tB = tile % g.nblk;
+    } else if (g.shape == SHAPE_LOWER) {
+        tri_decode(tile, tA, tB);
+    } else {
+        tri_decode(tile, tB, tA);
+    }
+    const int a_rows = blk_rows(g.Tp, tA), b_rows = min(BN, blk_rows(g.Tp, tB) - half * BN);
+    if (b_rows <= 0) return;
+    int k0 = g.klo == KLO_ZERO ? 0 : (g.klo == KLO_TA ? tA : max(tA, tB)) * NB;
+    int k1 = g.khi == KHI_END ? g.Tp : min(g.Tp, ((g.khi == KHI_TB ? tB : tA) + 1) * NB);
+    TileAcc acc;
+    const int klen = max(0, k1 - k0);
+    gemm_nt_mainloop(g.A + (size_t)b * g.strideA + (size_t)tA * NB * g.lda + k0, g.lda, a_rows,
+                     g.Bm + (size_t)b * g.strideB + (size_t)(tB * NB + half * BN) * g.ldb + k0, g.ldb, b_rows, klen, smem2,
+                     acc);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int mi = 0; mi < 8; ++mi) {
+        int r = acc_row(warp, lane, mi);
+        if (r >= a_rows) continue;
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni) {
+            int c = acc_col(warp, lane, ni);
+            if (c >= b_rows) continue;
+            epi(b, tA * NB + r, tB * NB + half * BN + c, acc.v[mi][ni][0], acc.v[mi][ni][1]);
+        }
+    }
+    epi.finish(b, tile * 2 + half, reinterpret_cast<double*>(smem2));
+}
+
+struct EpiBase {
+    __device__ void finish(int, int, double*) {}
+};
+
+// out[gr, gc] = value on the real T x T part, `pad_diag` on the padded diagonal, 0 elsewhere.
+// mirror: also write the transposed entry (symmetric results computed on lower tiles only).
+// sub: subtract Sub[gr, gc] first (W = AT * S - AT).
+struct EpiStore : EpiBase {
+    double* out;
+    const double* sub;
+    int ld, Tp, T;
+    double pad_diag;
+    int mirror;
+    __device__ void operator()(int b, int gr, int gc, double v0, double v1) {
+        double* ob = out + (size_t)b * Tp * ld;
+        double v[2] = {v0, v1};
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            int c = gc + e;
+            double val;
+            if (gr < T && c < T) {
+                val = v[e];
+                if (sub) val -= sub[(size_t)b * Tp * ld + (size_t)gr * ld + c];
+            } else {
+                val = gr == c ? pad_diag : 0.0;
+            }
+            ob[(size_t)gr * ld + c] = val;
+            if (mirror) ob[(size_t)c * ld + gr] = val;
+        }
+    }
+};
+
+// natural-gradient step on theta_2 (models.py:209):  P <- (1-gamma) P + gamma (I + L^T D^-1 L),
+// lower tiles; also copied to `work`, the buffer the next factorisation destroys.
+struct EpiNatP : EpiBase {
+    double* P;
+    double* work;
+    int ld, Tp, T;
+    double gamma;
+    __device__ void operator()(int b, int gr, int gc, double v0, double v1) {
+        size_t off = (size_t)b * Tp * ld + (size_t)gr * ld + gc;
+        double v[2] = {v0, v1}, o[2];
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            int c = gc + e;
+            double eye = gr == c ? 1.0 : 0.0;
+            if (gr < T && c < T) {
+                o[e] = (1.0 - gamma) * P[off + e] + gamma * (eye + v[e]);
+            } else {
+                o[e] = eye;
+            }
+        }
+        *reinterpret_cast<double2*>(P + off) = make_double2(o[0], o[1]);
+        *reinterpret_cast<double2*>(work + off) = make_double2(o[0], o[1]);
+    }
+};
+
+// LbarT[b_, i] = q_mu[b_] r[i] - (S L^T)[b_, i] / s[i]        (d ELBO / d L, transposed)
+struct EpiLbarT : EpiBase {
+    double* out;
+    const double* q_mu;
+    const double* r;
+    const double* y_var;
+    int ld, Tp, T;
+    __device__ void operator()(int b, int gr, int gc, double v0, double v1) {
+        double v[2] = {v0, v1}, o[2];
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            int c = gc + e;
+            o[e] = (gr < T && c < T) ? q_mu[(size_t)b * T + gr] * r[(size_t)b * T + c] - v[e] / y_var[(size_t)b * T + c] : 0.0;
+        }
+        *reinterpret_cast<double2*>(out + (size_t)b * Tp * ld + (size_t)gr * ld + gc) = make_double2(o[0], o[1]);
+    }
+};
+
+// Phi = tril(L^T Lbar) with the diagonal halved (Cholesky reverse-mode, Murray 2016)
+struct EpiPhi : EpiBase {
+    double* out;
+    int ld, Tp, T;
+    __device__ void operator()(int b, int gr, int gc, double v0, double v1) {
+        double v[2] = {v0, v1}, o[2];
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            int c = gc + e;
+            o[e] = (gr < T && c < T && c <= gr) ? (c == gr ? 0.5 * v[e] : v[e]) : 0.0;
+        }
+        *reinterpret_cast<double2*>(out + (size_t)b * Tp * ld + (size_t)gr * ld + gc) = make_double2(o[0], o[1]);
+    }
+};
+
+// g_theta = sum_{a,b} Kbar_u[a,b] dK[a,b]/dtheta for theta = (variance, lengthscale); per-CTA
+// partial sums go to partial[b][cta][2] and are added in a fixed order by k_vgp_adam.
+struct EpiKbarGrad {
+    const double* X;
+    const double* variance;
+    const double* lengthscale;
+    double* partial;
+    int T, R, ctas_per_problem;
+    double g0, g1;
+    __device__ void operator()(int b, int gr, int gc, double v0, double v1) {
+        if (gr >= T) return;
+        const double ls = lengthscale[b], var = variance[b];
+        const double* xa = X + ((size_t)b * T + gr) * R;
+        double v[2] = {v0, v1};
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            int c = gc + e;
+            if (c >= T) continue;
+            const double* xb = X + ((size_t)b * T + c) * R;
+            double dot = 0.0, sa = 0.0, sb = 0.0;
+            for (int k = 0; k < R; ++k) {
+                double pa = xa[k] / ls, pb = xb[k] / ls;
+                dot += pa * pb;
+                sa += pa * pa;
+                sb += pb * pb;
+            }
+            double r2 = (-2.0 * dot + sa) + sb;
+            double rr = sqrt(fmax(r2, 1e-36));
+            double ex = exp(-SQRT3 * rr);
+            g0 += v[e] * (1.0 + SQRT3 * rr) * ex;
+            if (r2 > 1e-36) g1 += v[e] * (3.0 * var * rr * rr * ex / ls);
+        }
+    }
+    __device__ void finish(int b, int cta, double* red) {
+        __syncthreads();
+        double a0 = g0, a1 = g1;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            a0 += __shfl_xor_sync(0xffffffffu, a0, o);
+            a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+        }
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        if (lane == 0) {
+            red[2 * warp] = a0;
+            red[2 * warp + 1] = a1;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double s0 = 0, s1 = 0;
+            for (int w = 0; w < GEMM_THREADS / 32; ++w) {
+                s0 += red[2 * w];
+                s1 += red[2 * w + 1];
+            }
+            partial[((size_t)b * ctas_per_problem + cta) * 2] = s0;
+            partial[((size_t)b * ctas_per_problem + cta) * 2 + 1] = s1;
+        }
+    }
+};
+
+// cov = K + AT (S - I) AT^T + D   (predict_f full_cov + models.py:220), lower tiles, mirrored
+struct EpiCov : EpiBase {
+    const double* K;  // padded [Tp, ld], both triangles, no jitter
+    const double* y_var;
+    double* cov;  // dense [B, T, T]
+    double* var_diag;
+    int ld, Tp, T;
+    __device__ void operator()(int b, int gr, int gc, double v0, double v1) {
+        if (gr >= T) return;
+        double v[2] = {v0, v1};
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            int c = gc + e;
+            if (c >= T || c > gr) continue;
+            double val = K[(size_t)b * Tp * ld + (size_t)gr * ld + c] + v[e];
+            if (c == gr) {
+                val += y_var[(size_t)b * T + gr];
+                var_diag[(size_t)b * T + gr] = val;
+            }
+            cov[(size_t)b * T * T + (size_t)gr * T + c] = val;
+            cov[(size_t)b * T * T + (size_t)c * T + gr] = val;
+        }
+    }
+};
+
+// out[a][i] = in[i][a] restricted to one triangle of `in` (tri = 1: lower, a <= i; tri = 2: upper,
+// a >= i; 0: everything), optionally scaled by colscale[i] (0 on padding).  32 x 32 smem tiles.
+__global__ void __launch_bounds__(256) k_transpose(const double* __restrict__ in, int ld, int Tp, int T, int tri,
+                                                   double* __restrict__ out, double* __restrict__ out_scaled,
+                                                   const double* __restrict__ y_var, int B) {
+    __shared__ double tile[32][33];
+    const int nt = (Tp + 31) / 32;
+    int t = blockIdx.x % (nt * nt), b = blockIdx.x / (nt * nt);
+    const int ti = t / nt, ta = t % nt;  // input rows block ti, input cols block ta
+    const double* ib = in + (size_t)b * Tp * ld;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int rr = ty; rr < 32; rr += 8) {
+        int i = ti * 32 + rr, a = ta * 32 + tx;
+        double v = 0.0;
+        if (i < Tp && a < Tp && (tri == 0 || (tri == 1 ? a <= i : a >= i))) v = ib[(size_t)i * ld + a];
+        tile[rr][tx] = v;
+    }
+    __syncthreads();
+    for (int rr = ty; rr < 32; rr += 8) {
+        int a = ta * 32 + rr, i = ti * 32 + tx;
+        if (a < Tp && i < Tp) {
+            double v = tile[tx][rr];
+            out[(size_t)b * Tp * ld + (size_t)a * ld + i] = v;
+            if (out_scaled) out_scaled[(size_t)b * Tp * ld + (size_t)a * ld + i] = i < T ? v / y_var[(size_t)b * T + i] : 0.0;
+        }
+    }
+}
+
+// One warp per row: s = sum_k M[i][k] x[k] over the triangle given by tri (0 full, 1 k <= i, 2 k >= i).
+//   op 0: out[i] = s
+//   op 1: out[i] = (1-gamma) out[i] + gamma s, with x[k] := y[k] / y_var[k]   (theta_1 step)
+//   op 2: out[i] = (y[i] - s) / y_var[i]                                      (residual r)
+__global__ void __launch_bounds__(256) k_rowdot(const double* __restrict__ M, int ld, int Tp, int T, int tri, int op,
+                                                const double* __restrict__ x, const double* __restrict__ y,
+                                                const double* __restrict__ y_var, double gamma,
+                                                double* __restrict__ out, int B) {
+    int wg = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (wg >= B * T) return;
+    int b = wg / T, i = wg % T;
+    const double* row = M + (size_t)b * Tp * ld + (size_t)i * ld;
+    int k0 = tri == 2 ? i : 0, k1 = tri == 1 ? i + 1 : T;
+    double s = 0.0;
+    for (int k = k0 + lane; k < k1; k += 32) {
+        double xv = op == 1 ? y[(size_t)b * T + k] / y_var[(size_t)b * T + k] : x[(size_t)b * T + k];
+        s = fma(row[k], xv, s);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) {
+        size_t gi = (size_t)b * T + i;
+        if (op == 0) out[gi] = s;
+        else if (op == 1) out[gi] = (1.0 - gamma) * out[gi] + gamma * s;
+        else out[gi] = (y[gi] - s) / y_var[gi];
+    }
+}
+
+__device__ __forceinline__ double softplus_d(double u) { return u > 0.0 ? u + log1p(exp(-u)) : log1p(exp(u)); }
+
+// u [B,2] unconstrained (variance, lengthscale) -> constrained values (gpflow's softplus bijector)
+__global__ void k_vgp_constrain(const double* __restrict__ u, int B, double* __restrict__ variance,
+                                double* __restrict__ lengthscale) {
+    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    variance[b] = softplus_d(u[2 * b]);
+    lengthscale[b] = softplus_d(u[2 * b + 1]);
+}
+
+// tf.optimizers.Adam (TF 2.8 OptimizerV2) step on the two unconstrained parameters (models.py:192,210):
+// g_u = -(dELBO/dtheta) * dsoftplus/du,  dsoftplus/du = 1 - exp(-theta);  then the new constrained values.
+__global__ void k_vgp_adam(const double* __restrict__ partial, int ctas_per_problem, int B, double lr, double b1,
+                           double b2, double eps, double* __restrict__ u, double* __restrict__ m,
+                           double* __restrict__ v, int* __restrict__ step, double* __restrict__ variance,
+                           double* __restrict__ lengthscale) {
+    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    double g[2] = {0.0, 0.0};
+    for (int c = 0; c < ctas_per_problem; ++c) {
+        g[0] += partial[((size_t)b * ctas_per_problem + c) * 2];
+        g[1] += partial[((size_t)b * ctas_per_problem + c) * 2 + 1];
+    }
+    const double theta[2] = {variance[b], lengthscale[b]};
+    const int t = step[b] + 1;
+    step[b] = t;
+    const double lr_t = lr * sqrt(1.0 - pow(b2, (double)t)) / (1.0 - pow(b1, (double)t));
+#pragma unroll
+    for (int p = 0; p < 2; ++p) {
+        double gu = -g[p] * (-expm1(-theta[p]));
+        double mm = b1 * m[2 * b + p] + (1.0 - b1) * gu;
+        double vv = b2 * v[2 * b + p] + (1.0 - b2) * gu * gu;
+        m[2 * b + p] = mm;
+        v[2 * b + p] = vv;
+        u[2 * b + p] -= lr_t * mm / (sqrt(vv) + eps);
+    }
+    variance[b] = softplus_d(u[2 * b]);
+    lengthscale[b] = softplus_d(u[2 * b + 1]);
+}
+
+// constrained (variance, lengthscale) -> unconstrained u = softplus^-1(theta) = theta + log(1 - exp(-theta))
+__global__ void k_vgp_unconstrain(const double* __restrict__ variance, const double* __restrict__ lengthscale, int B,
+                                  double* __restrict__ u) {
+    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    u[2 * b] = variance[b] + log(-expm1(-variance[b]));
+    u[2 * b + 1] = lengthscale[b] + log(-expm1(-lengthscale[b]));
+}
+
+// padded identity (q_sqrt = I  =>  P = S = I)
+__global__ void k_set_identity(double* __restrict__ M, int ld, int Tp, int B) {
+    size_t n = (size_t)B * Tp * ld;
+    for (size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x; gid < n; gid += (size_t)gridDim.x * blockDim.x) {
+        size_t rem = gid % ((size_t)Tp * ld);
+        M[gid] = (rem / ld == rem % ld) ? 1.0 : 0.0;
+    }
+}
+
+}  // namespace be

@@ -54,7 +54,7 @@ class GPDTW1D:
                 ls = torch.full((B,), float(self.hyperparameters[1]), dtype=torch.float64, device=be.device)
                 post = be.gp_posterior(X, y_mean, y_var, var, ls, DEFAULT_JITTER)
             else:
-                post = be.vgp_fit(X, y_mean, y_var, n_optim_nits)  # models.py:185-220
+                post, _var, _ls = be.vgp_fit(X, y_mean, y_var, n_optim_nits)  # models.py:185-220
             for k, i in enumerate(idxs):
                 pm = models[i]
                 blank_array = ones_like(pm.model_data[0].drop_vars("realisation")) * np.nan

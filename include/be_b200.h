@@ -97,6 +97,23 @@ int be_gp_posterior(be_ctx* ctx, const double* X, const double* y_mean, const do
                     double* mvn_stats, int* info_fit, int* info_dist,
                     void* workspace, size_t workspace_bytes);
 
+/* ---- a1 L2: the training loop GPDTW1D.fit actually runs, models.py:185-220 ----------------
+ * Whitened VGP, Matern-3/2 on X, heteroskedastic Gaussian likelihood (a2, models.py:142-149;
+ * its variational expectation enters through the closed-form natural-gradient target and the
+ * analytic ELBO gradient).  n_iters times: NaturalGradient(gamma) step on (q_mu, q_sqrt)
+ * (models.py:209), then -- if train_hypers -- one Adam(lr) step on the two softplus-constrained
+ * kernel parameters (models.py:210; TF defaults beta1 .9, beta2 .999, eps 1e-7).  From GPflow's
+ * initial state q_mu = 0, q_sqrt = I; variance / lengthscale [B] hold the initial values on entry
+ * (GPflow: 1, 1) and the trained values on return.  Then predict_f(X, full_cov=True) (:217) and
+ * cov += diag(y_var) (:220).  One iteration is captured in a CUDA graph and replayed.
+ * Outputs as be_gp_posterior; cov [B,T,T] is required here. */
+size_t be_vgp_fit_workspace_bytes(int B, int T, int R);
+int be_vgp_fit(be_ctx* ctx, const double* X, const double* y_mean, const double* y_var, int B, int T, int R,
+               int n_iters, double gamma, double lr, int train_hypers, double jitter,
+               double* variance, double* lengthscale,
+               double* mu, double* var_diag, double* cov, double* scale_tri, double* mvn_stats,
+               int* info_fit, int* info_dist, void* workspace, size_t workspace_bytes);
+
 /* ---- a3: Distribution(mu, cov, MultivariateNormalFullCovariance), data.py:38-39 ---------
  * from an arbitrary covariance: scale_tri, diag and the log-prob statistics. */
 size_t be_mvn_from_cov_workspace_bytes(int B, int T);

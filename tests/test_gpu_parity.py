@@ -355,3 +355,62 @@ def test_reference_api_end_to_end(backend):
     assert rel_err(ll, rp.mvn_log_prob(o["mu"][0], o["scale_tri"][0], obs[0][:, None])) < 1e-9
     ll1 = mc[0].distribution._dist.log_prob(obs[0])
     assert abs(ll1 - rp.mvn_log_prob(o["mu"][0], o["scale_tri"][0], obs[0])) <= 1e-9 * abs(ll1)
+
+
+# ------------------------------------------------------------------------------------ a1 L2: the training loop
+L2_TOL = 1e-7  # measured: see DESIGN.md "L2 parity"; the loop amplifies rounding through Adam
+
+
+@pytest.mark.parametrize("T,R,M,n_it,train", [(24, 3, 3, 2, True), (24, 3, 2, 25, True), (86, 5, 2, 40, True),
+                                              (130, 4, 2, 10, True), (165, 10, 2, 12, True), (40, 3, 2, 30, False),
+                                              (24, 3, 2, 0, True), (86, 5, 2, 400, True), (251, 3, 1, 60, True)])
+def test_vgp_fit_vs_oracle(backend, T, R, M, n_it, train):
+    """GPDTW1D.fit below the DBA step (models.py:179-220): natgrad(0.5) + Adam(0.01) from GPflow's
+    initial state, then predict_f(full_cov=True) + diag(y_var)."""
+    reals, _ = _cell(M, R, T, 2, seed=1000 + T + n_it)
+    X, ym, yv = backend.gpdtw1d_inputs(_t(backend, reals))
+    post, var, ls = backend.vgp_fit(X, ym, yv, n_it, train_hypers=train)
+    assert int(post.info_fit.abs().sum()) == 0 and int(post.info_dist.abs().sum()) == 0
+    worst = 0.0
+    for m in range(M):
+        mu_o, cov_o, st = rp.gpdtw1d_fit(reals[m], n_optim_nits=n_it, train_hypers=train, return_state=True)
+        assert abs(float(var[m]) / st["variance"] - 1) <= L2_TOL and abs(float(ls[m]) / st["lengthscale"] - 1) <= L2_TOL
+        e_mu = rel_err(post.mu[m].cpu().numpy(), mu_o)
+        e_cov = rel_err(post.cov[m].cpu().numpy(), cov_o)
+        e_var = float(np.abs(post.var_diag[m].cpu().numpy() / np.diag(cov_o) - 1).max())
+        e_tri = rel_err(post.scale_tri[m].cpu().numpy(), np.linalg.cholesky(cov_o))
+        worst = max(worst, e_mu, e_cov, e_var, e_tri)
+        assert max(e_mu, e_cov, e_var, e_tri) <= L2_TOL, (e_mu, e_cov, e_var, e_tri)
+    print(f"vgp_fit T={T} n_it={n_it}: worst rel err {worst:.2e}")
+
+
+def test_vgp_fit_converges_to_closed_form(backend):
+    """With frozen hyper-parameters the loop converges geometrically to the closed-form
+    posterior be_gp_posterior computes."""
+    reals, _ = _cell(2, 4, 60, 2, seed=5)
+    X, ym, yv = backend.gpdtw1d_inputs(_t(backend, reals))
+    post, var, ls = backend.vgp_fit(X, ym, yv, 60, train_hypers=False, init_variance=0.5, init_lengthscale=6.0)
+    ref = backend.gp_posterior(X, ym, yv, [0.5, 0.5], [6.0, 6.0])
+    assert rel_err(post.mu.cpu().numpy(), ref.mu.cpu().numpy()) < 1e-6
+    assert rel_err(post.cov.cpu().numpy(), ref.cov.cpu().numpy()) < 1e-6
+
+
+def test_reference_api_default_fit_runs_training_loop(backend):
+    """tests/test_weights.py:90 verbatim: fit(GPDTW1D(), compile_objective=True, n_optim_nits=2)."""
+    import bayesian_ensembling_b200 as es
+    from bayesian_ensembling_b200.labelled import DataArray
+
+    M, R, T, Ro = 2, 3, 24, 2
+    reals, obs = _cell(M, R, T, Ro, seed=31, monthly=True)
+    pms = [es.ProcessModel(DataArray(reals[m], ("realisation", "time")), f"model{m}") for m in range(M)]
+    mc = es.ModelCollection(pms)
+    mc.fit(model=es.GPDTW1D(), compile_objective=True, n_optim_nits=2, progress_bar=False)
+    for m in range(M):
+        mu_o, cov_o = rp.gpdtw1d_fit(reals[m], n_optim_nits=2)
+        assert rel_err(mc[m].distribution.mean.values, mu_o) <= L2_TOL
+        assert rel_err(mc[m].distribution._dist.covariance(), cov_o) <= L2_TOL
+    obs_pm = es.ProcessModel(DataArray(obs, ("realisation", "time")), "obs")
+    w = es.LogLikelihoodWeight()(mc, obs_pm)
+    assert w.shape == (M, T)
+    ok = ~np.isnan(w.values).any(axis=0)
+    assert np.allclose(w.values[:, ok].sum(axis=0), 1.0, atol=1e-6)

@@ -100,16 +100,17 @@ def fit_weight_barycentre(realisations, observations, variance, lengthscale, *, 
 def fit_weight_barycentre_member_sharded(realisations_local, observations, variance_local, lengthscale_local, *,
                                          group=None, jitter=DEFAULT_JITTER, standardisation_constant=1.0,
                                          time_mean_weights=False, tolerance=1e-6, init_var=1.0,
-                                         all_reduce=None) -> CellBatchResult:
+                                         all_reduce=None, ops=None) -> CellBatchResult:
     """Member-sharded form for few-cell configs: every rank holds ``M_local`` members of ALL C
     cells.  The only exchange is one all-reduce (sum, fp64) of the packed partial sums
     ``[3,C,T] = (sum w~, sum w~ mu, sum w~ sigma)`` -- NCCL over NVLink when launched under
     torchrun; ``all_reduce`` can be injected (tests use gloo on CPU tensors).  With
     ``time_mean_weights`` the normaliser must be known before the time mean, so there are two
-    small all-reduces."""
+    small all-reduces.  ``ops`` is the operator object (default: the CUDA
+    ``Backend``); the CPU test-suite injects a stand-in to exercise this host logic over gloo."""
     import torch.distributed as dist
 
-    be = Backend.get()
+    be = Backend.get() if ops is None else ops
     r = be._in(realisations_local)
     o = be._in(observations)
     C, Ml, R, T = r.shape

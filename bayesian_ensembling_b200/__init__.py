@@ -5,7 +5,8 @@ from .data import Distribution, ModelCollection, ProcessModel  # noqa: F401
 from .ensemble_scheme import Barycentre  # noqa: F401
 from .labelled import DataArray  # noqa: F401
 from .models import GPDTW1D  # noqa: F401
-from .wasserstein import gaussian_barycentre  # noqa: F401
+from .wasserstein import (gaussian_barycentre, gaussian_barycentre_fullcov, gaussian_w2_distance_distrax,  # noqa: F401
+                          sqrtm, wasserstien_distance)
 from .weights import LogLikelihoodWeight, UniformWeight  # noqa: F401
 
 __version__ = "0.1.0"

@@ -58,6 +58,13 @@ SIGNATURES = {
     "be_barycentre_1d": (_I, [_P, _P, _P, _P, _I, _I, _I, _D, _D, _I, _P, _P, _P]),
     "be_barycentre_1d_partial": (_I, [_P, _P, _P, _P, _I, _I, _I, _P]),
     "be_barycentre_1d_finish": (_I, [_P, _P, _I, _I, _D, _D, _I, _P, _P, _P]),
+    "be_sqrtm_psd_workspace_bytes": (_Z, [_I, _I]),
+    "be_sqrtm_psd": (_I, [_P, _P, _I, _I, _D, _I, _P, _P, _P, _P, _P, _Z]),
+    "be_w2_distance_workspace_bytes": (_Z, [_I, _I]),
+    "be_w2_distance": (_I, [_P, _P, _P, _P, _P, _I, _I, _D, _I, _P, _P, _P, _Z]),
+    "be_w2_distance_diag": (_I, [_P, _P, _P, _P, _P, _I, _I, _P]),
+    "be_barycentre_fullcov_workspace_bytes": (_Z, [_I, _I, _I]),
+    "be_barycentre_fullcov": (_I, [_P, _P, _P, _P, _I, _I, _I, _D, _D, _I, _D, _I, _P, _P, _P, _P, _P, _Z]),
 }
 
 BE_OK = 0

@@ -6,6 +6,7 @@ checks).  Every numerical operation is a call into ``libbe_b200.so``.
 from __future__ import annotations
 
 import ctypes
+import os
 from dataclasses import dataclass
 
 import torch
@@ -13,6 +14,7 @@ import torch
 from . import _lib
 
 DEFAULT_JITTER = 1e-6  # gpflow.config.default_jitter()
+_POISON = bool(os.environ.get("BE_B200_POISON_WORKSPACE"))
 
 
 def _ptr(t):
@@ -71,6 +73,8 @@ class Backend:
         if self._workspace is None or self._workspace.numel() < nbytes:
             self._workspace = None
             self._workspace = torch.empty(int(nbytes), dtype=torch.uint8, device=self.device)
+        if _POISON:  # test hook: every byte 0xFF = NaN doubles, so a read of unwritten workspace shows up
+            self._workspace.fill_(255)
         return self._workspace
 
     def _in(self, t, shape=None, name="tensor"):
@@ -325,3 +329,75 @@ class Backend:
                                               int(max_iters), _ptr(mu), _ptr(sigma), _ptr(iters))
         _lib.check(self.ctx, rc, "be_barycentre_1d_finish")
         return mu, sigma, iters
+
+    # ------------------------------------------------------------------ a7 / a8 / a9
+    SQRTM_TOL = 1e-10
+    SQRTM_MAX_ITERS = 40
+
+    def sqrtm_psd(self, A, want_inverse=False, tol=None, max_iters=None):
+        """[B,T,T] symmetric positive definite -> principal square root (wasserstein.py:10-13).
+        Returns (sqrt [B,T,T], inv_sqrt or None, iterations, info [B] int32)."""
+        A = self._in(A)
+        B, T, _ = A.shape
+        out = self._new(B, T, T)
+        inv = self._new(B, T, T) if want_inverse else None
+        info = self._new(B, dtype=torch.int32)
+        iters = ctypes.c_int(0)
+        nbytes = int(self.lib.be_sqrtm_psd_workspace_bytes(B, T))
+        ws = self._ws(nbytes)
+        self._sync_stream()
+        rc = self.lib.be_sqrtm_psd(self.ctx, _ptr(A), B, T, float(tol or self.SQRTM_TOL),
+                                   int(max_iters or self.SQRTM_MAX_ITERS), _ptr(out), _ptr(inv),
+                                   ctypes.cast(ctypes.byref(iters), ctypes.c_void_p), _ptr(info), _ptr(ws), nbytes)
+        _lib.check(self.ctx, rc, "be_sqrtm_psd")
+        return out, inv, int(iters.value), info
+
+    def w2_distance(self, mu1, sigma1, mu2, sigma2):
+        """P pairs of full-covariance Gaussians -> w2 [P] (wasserstein.py:21-47, quirk Q-W2)."""
+        sigma1 = self._in(sigma1)
+        P, T, _ = sigma1.shape
+        sigma2 = self._in(sigma2, (P, T, T), "sigma2")
+        mu1 = self._in(mu1, (P, T), "mu1")
+        mu2 = self._in(mu2, (P, T), "mu2")
+        w2 = self._new(P)
+        info = self._new(P, dtype=torch.int32)
+        nbytes = int(self.lib.be_w2_distance_workspace_bytes(P, T))
+        ws = self._ws(nbytes)
+        self._sync_stream()
+        rc = self.lib.be_w2_distance(self.ctx, _ptr(mu1), _ptr(sigma1), _ptr(mu2), _ptr(sigma2), P, T,
+                                     self.SQRTM_TOL, self.SQRTM_MAX_ITERS, _ptr(w2), _ptr(info), _ptr(ws), nbytes)
+        _lib.check(self.ctx, rc, "be_w2_distance")
+        return w2, info
+
+    def w2_distance_diag(self, mu1, var1, mu2, var2):
+        """full_cov=False branch (wasserstein.py:36-39): variances on a diagonal."""
+        mu1 = self._in(mu1)
+        P, T = mu1.shape
+        var1 = self._in(var1, (P, T), "var1")
+        mu2 = self._in(mu2, (P, T), "mu2")
+        var2 = self._in(var2, (P, T), "var2")
+        w2 = self._new(P)
+        self._sync_stream()
+        rc = self.lib.be_w2_distance_diag(self.ctx, _ptr(mu1), _ptr(var1), _ptr(mu2), _ptr(var2), P, T, _ptr(w2))
+        _lib.check(self.ctx, rc, "be_w2_distance_diag")
+        return w2
+
+    def barycentre_fullcov(self, mus, sigmas, weights, tolerance=1e-6, init_var=1.0, max_iters=200):
+        """mus [C,M,T], sigmas [C,M,T,T], weights [C,M] -> mu [C,T], S [C,T,T], iters [C] (host),
+        info [C*M] (BASELINE config 5; the definition is in DESIGN.md 3.4)."""
+        sigmas = self._in(sigmas)
+        C, M, T, _ = sigmas.shape
+        mus = self._in(mus, (C, M, T), "mus")
+        weights = self._in(weights, (C, M), "weights")
+        mu, S = self._new(C, T), self._new(C, T, T)
+        info = self._new(C * M, dtype=torch.int32)
+        iters = (ctypes.c_int * C)()
+        nbytes = int(self.lib.be_barycentre_fullcov_workspace_bytes(C, M, T))
+        ws = self._ws(nbytes)
+        self._sync_stream()
+        rc = self.lib.be_barycentre_fullcov(self.ctx, _ptr(mus), _ptr(sigmas), _ptr(weights), C, M, T,
+                                            float(tolerance), float(init_var), int(max_iters), self.SQRTM_TOL,
+                                            self.SQRTM_MAX_ITERS, _ptr(mu), _ptr(S),
+                                            ctypes.cast(iters, ctypes.c_void_p), _ptr(info), _ptr(ws), nbytes)
+        _lib.check(self.ctx, rc, "be_barycentre_fullcov")
+        return mu, S, list(iters), info

@@ -8,18 +8,19 @@
 #include "../../include/be_b200.h"
 #include "be_kernels.cuh"
 #include "vgp_kernels.cuh"
+#include "sqrtm_kernels.cuh"
 
 using namespace be;
 
 // kernel families of the profiler (be_ctx_profile_*): one per kernel of be_kernels.cuh
 enum Family {
     F_INPUTS = 0, F_GRAM, F_DIAG, F_PANEL, F_SYRK, F_TRTRI, F_LAUUM, F_MEAN, F_STATS, F_COPY, F_WEIGHTS, F_BARY,
-    F_GEMM, F_VGP_MISC, F_COUNT
+    F_GEMM, F_VGP_MISC, F_SQRTM_MISC, F_COUNT
 };
 static const char* const kFamilyName[F_COUNT] = {
     "k_gpdtw1d_inputs", "k_matern32", "k_diag_block", "k_panel_scale", "k_chol_update", "k_trtri_accum",
     "k_lauum_cov", "k_posterior_mean", "k_mvn_stats", "copy/pad", "k_loglik_weights", "k_barycentre",
-    "k_gemm_nt", "vgp elementwise"};
+    "k_gemm_nt", "vgp elementwise", "sqrtm elementwise"};
 
 struct ProfRecord {
     int family;
@@ -127,6 +128,9 @@ int ensure_kernel_attrs(be_ctx* ctx) {
     BE_CUDA(cudaFuncSetAttribute(k_gemm_nt<EpiPhi>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
     BE_CUDA(cudaFuncSetAttribute(k_gemm_nt<EpiKbarGrad>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
     BE_CUDA(cudaFuncSetAttribute(k_gemm_nt<EpiCov>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
+    BE_CUDA(cudaFuncSetAttribute(k_gemm_nt<EpiDB>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
+    BE_CUDA(cudaFuncSetAttribute(k_gemm_nt<EpiSym>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
+    BE_CUDA(cudaFuncSetAttribute(k_gemm_nt<EpiPlain>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
     g_attr_done = true;
     return BE_OK;
 }
@@ -214,6 +218,7 @@ inline GemmArgs gemm_args(const double* A, const double* Bm, int Tp, int B, int 
     g.Bm = Bm;
     g.lda = g.ldb = Tp;
     g.strideA = g.strideB = (size_t)Tp * Tp;
+    g.divA = g.divB = 1;
     g.Tp = Tp;
     g.nblk = num_blocks(Tp);
     g.B = B;
@@ -900,3 +905,5 @@ int be_vgp_fit(be_ctx* ctx, const double* X, const double* y_mean, const double*
 }
 
 }  // extern "C"
+
+#include "be_w2_api.cuh"

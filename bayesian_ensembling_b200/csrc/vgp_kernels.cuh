@@ -21,6 +21,7 @@ struct GemmArgs {
     const double* Bm;
     int lda, ldb;
     size_t strideA, strideB;  // per-problem strides (doubles)
+    int divA, divB;           // problem b reads operand slot b / div (one S^1/2 shared by the M members of a cell)
     int Tp, nblk, B;
     int shape, klo, khi;
 };
@@ -51,8 +52,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, GEMM_CTAS_PER_SM) k_gemm_nt(Gemm
     int k1 = g.khi == KHI_END ? g.Tp : min(g.Tp, ((g.khi == KHI_TB ? tB : tA) + 1) * NB);
     TileAcc acc;
     const int klen = max(0, k1 - k0);
-    gemm_nt_mainloop(g.A + (size_t)b * g.strideA + (size_t)tA * NB * g.lda + k0, g.lda, a_rows,
-                     g.Bm + (size_t)b * g.strideB + (size_t)(tB * NB + half * BN) * g.ldb + k0, g.ldb, b_rows, klen, smem2,
+    gemm_nt_mainloop(g.A + (size_t)(b / g.divA) * g.strideA + (size_t)tA * NB * g.lda + k0, g.lda, a_rows,
+                     g.Bm + (size_t)(b / g.divB) * g.strideB + (size_t)(tB * NB + half * BN) * g.ldb + k0, g.ldb, b_rows, klen, smem2,
                      acc);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll

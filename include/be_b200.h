@@ -169,6 +169,48 @@ int be_barycentre_1d_finish(be_ctx* ctx, const double* partial, int C, int N,
                             double tolerance, double init_var, int max_iters,
                             double* mu, double* sigma, int* iters);
 
+/* ---- a7: sqrtm, ensembles/wasserstein.py:10-13 --------------------------------------------
+ * The reference computes U diag(sqrt(s)) V^H from jnp.linalg.svd; for SYMMETRIC POSITIVE DEFINITE
+ * input -- all the path ever passes (covariances and S^1/2 Sigma S^1/2 products) -- that is the
+ * principal square root, computed here by the scaled Denman-Beavers iteration on the FP64
+ * tensor cores.  A [B,T,T] symmetric (both triangles read) -> sqrt_out [B,T,T];
+ * inv_sqrt_out [B,T,T] (may be NULL) = A^-1/2.  Iterates until the relative Frobenius change of
+ * the iterate is < tol (1e-10 recommended) or max_iters; *iters_host (HOST int, may be NULL)
+ * receives the iteration count.  info [B] (device): k > 0 = an iterate was not positive definite
+ * at leading minor k (input not SPD).  Synchronises the ctx stream once per iteration. */
+size_t be_sqrtm_psd_workspace_bytes(int B, int T);
+int be_sqrtm_psd(be_ctx* ctx, const double* A, int B, int T, double tol, int max_iters,
+                 double* sqrt_out, double* inv_sqrt_out, int* iters_host, int* info,
+                 void* workspace, size_t workspace_bytes);
+
+/* ---- a8: gaussian_w2_distance_distrax, ensembles/wasserstein.py:21-47 ----------------------
+ * w2[p] = |mu1 - mu2|_2 + tr(S1 + S2 - 2 sqrtm(sqrtm(S1) S2 sqrtm(S1)))   -- the location term
+ * is NOT squared (quirk Q-W2, :40,45).  mu* [P,T], sigma* [P,T,T], w2 [P], info [P].
+ * be_w2_distance_diag is the full_cov=False branch (:36-39): var* [P,T] are the variances the
+ * reference puts on a diagonal, for which sqrtm is elementwise. */
+size_t be_w2_distance_workspace_bytes(int P, int T);
+int be_w2_distance(be_ctx* ctx, const double* mu1, const double* sigma1, const double* mu2,
+                   const double* sigma2, int P, int T, double sqrtm_tol, int sqrtm_max_iters,
+                   double* w2, int* info, void* workspace, size_t workspace_bytes);
+int be_w2_distance_diag(be_ctx* ctx, const double* mu1, const double* var1, const double* mu2,
+                        const double* var2, int P, int T, double* w2);
+
+/* ---- a9: full-covariance Gaussian W2 barycentre (BASELINE config 5) -------------------------
+ * The reference has no such code; this is the matrix generalisation of wasserstein.py:61-100
+ * with wasserstein.py:10-13 as the square root, as DEFINED by oracle/reference_path.py
+ * (fullcov_barycentre):  S0 = init_var I;  S <- sum_m w_m (S^1/2 Sigma_m S^1/2)^1/2;  signed stop
+ * rule tr(S_new - S)/T < tolerance (reduces exactly to wasserstein.py:88 at T = 1);
+ * mu = sum_m w_m mu_m (:98).  mus [C,M,T], sigmas [C,M,T,T], weights [C,M] -> mu [C,T],
+ * S_out [C,T,T]; iters_host [C] (HOST, may be NULL) iterations taken, > max_iters = not
+ * converged (the reference only warns); info [C*M] (device) as be_sqrtm_psd.
+ * Synchronises the ctx stream inside. */
+size_t be_barycentre_fullcov_workspace_bytes(int C, int M, int T);
+int be_barycentre_fullcov(be_ctx* ctx, const double* mus, const double* sigmas, const double* weights,
+                          int C, int M, int T, double tolerance, double init_var, int max_iters,
+                          double sqrtm_tol, int sqrtm_max_iters,
+                          double* mu, double* S_out, int* iters_host, int* info,
+                          void* workspace, size_t workspace_bytes);
+
 #ifdef __cplusplus
 }
 #endif

@@ -414,3 +414,131 @@ def test_reference_api_default_fit_runs_training_loop(backend):
     assert w.shape == (M, T)
     ok = ~np.isnan(w.values).any(axis=0)
     assert np.allclose(w.values[:, ok].sum(axis=0), 1.0, atol=1e-6)
+
+
+# ------------------------------------------------------------------------------------ a7 / a8 / a9
+def _posterior_covs(M, R, T, seed):
+    reals, _ = _cell(M, R, T, 2, seed=seed)
+    mus, covs = [], []
+    for m in range(M):
+        X, y, s = rp.gpdtw1d_inputs(reals[m])
+        mu, cov = rp.gp_posterior_closed_form(X, y, s, 0.5, 6.0)
+        mus.append(mu)
+        covs.append(cov)
+    return np.asarray(mus), np.asarray(covs)
+
+
+@pytest.mark.parametrize("T", [1, 2, 17, 86, 128, 165, 251, 300])
+def test_sqrtm_vs_svd_oracle(backend, T):
+    """wasserstein.py:10-13 on posterior covariances (what the path feeds it) and on a random SPD matrix."""
+    _, covs = _posterior_covs(2, 4, T, seed=T)
+    rng = np.random.default_rng(T)
+    G = rng.standard_normal((T, T + 3))
+    A = np.concatenate([covs, (G @ G.T / T + 1e-3 * np.eye(T))[None]])
+    out, inv, iters, info = backend.sqrtm_psd(_t(backend, A), want_inverse=True)
+    assert int(info.abs().sum()) == 0 and 1 <= iters <= 25
+    worst = 0.0
+    for b in range(A.shape[0]):
+        want = rp.sqrtm_svd(A[b])
+        got = out[b].cpu().numpy()
+        worst = max(worst, rel_err(got, want))
+        assert rel_err(got @ got, A[b]) < 1e-11
+        assert np.abs(got @ inv[b].cpu().numpy() - np.eye(T)).max() < 1e-9
+        assert np.array_equal(got, got.T)
+    print(f"sqrtm T={T}: {iters} iterations, worst rel err {worst:.2e}")
+    assert worst < 1e-9  # tolerance of the north star for barycentre moments is 1e-6
+
+
+def test_sqrtm_reports_non_spd(backend):
+    A = np.eye(5)
+    A[3, 3] = -1.0
+    _, _, _, info = backend.sqrtm_psd(_t(backend, A[None]))
+    assert int(info[0]) == 4
+
+
+@pytest.mark.parametrize("T", [3, 86, 165])
+def test_w2_distance_vs_oracle(backend, T):
+    mus, covs = _posterior_covs(4, 5, T, seed=100 + T)
+    pairs = [(0, 1), (1, 2), (2, 3), (3, 0), (1, 1)]
+    i, j = [p[0] for p in pairs], [p[1] for p in pairs]
+    w2, info = backend.w2_distance(_t(backend, mus[i]), _t(backend, covs[i]), _t(backend, mus[j]), _t(backend, covs[j]))
+    assert int(info.abs().sum()) == 0
+    want = np.array([rp.gaussian_w2_distance(mus[a], covs[a], mus[b], covs[b]) for a, b in pairs])
+    assert np.abs(w2.cpu().numpy() - want).max() <= 1e-9 * max(1.0, np.abs(want).max())
+    # full_cov=False branch: variances on a diagonal
+    var = np.asarray([np.diag(c) for c in covs])
+    w2d = backend.w2_distance_diag(_t(backend, mus[i]), _t(backend, var[i]), _t(backend, mus[j]), _t(backend, var[j]))
+    wantd = np.array([rp.gaussian_w2_distance(mus[a], np.diag(var[a]), mus[b], np.diag(var[b])) for a, b in pairs])
+    assert np.abs(w2d.cpu().numpy() - wantd).max() <= 1e-10 * max(1.0, np.abs(wantd).max())
+
+
+def test_w2_python_api(backend):
+    from bayesian_ensembling_b200 import dists, gaussian_w2_distance_distrax, sqrtm, wasserstien_distance
+
+    mus, covs = _posterior_covs(2, 5, 40, seed=7)
+    a = dists.MultivariateNormalFullCovariance(mus[0], covs[0])
+    b = dists.MultivariateNormalFullCovariance(mus[1], covs[1])
+    assert abs(gaussian_w2_distance_distrax(a, b) - rp.gaussian_w2_distance(mus[0], covs[0], mus[1], covs[1])) < 1e-9
+    va, vb = np.diag(covs[0]), np.diag(covs[1])
+    assert abs(gaussian_w2_distance_distrax(a, b, full_cov=False)
+               - rp.gaussian_w2_distance(mus[0], np.diag(va), mus[1], np.diag(vb))) < 1e-10
+    assert rel_err(sqrtm(covs[0]), rp.sqrtm_svd(covs[0])) < 1e-9
+    z = np.zeros(40)
+    assert abs(wasserstien_distance(covs[0], covs[1]) - rp.gaussian_w2_distance(z, covs[0], z, covs[1])) < 1e-9
+    with pytest.raises(ValueError):
+        sqrtm(-np.eye(3))
+
+
+@pytest.mark.parametrize("T,M,scale", [(1, 3, 1.0), (1, 3, 2000.0), (24, 3, 1.0), (86, 4, 1.0), (40, 3, 2000.0), (130, 2, 500.0)])
+def test_fullcov_barycentre_vs_oracle(backend, T, M, scale):
+    """a9 against the oracle's definition; scale > 1 pushes tr(S) above init_var so that the fixed
+    point iterates (with degC-anomaly covariances it exits at iteration 0, like the 1-D rule)."""
+    mus, covs = _posterior_covs(M, 4, T, seed=300 + T)
+    covs = covs * scale
+    rng = np.random.default_rng(T)
+    w = rng.uniform(0.2, 1.0, M)
+    w /= w.sum()
+    mu, S, iters, info = backend.barycentre_fullcov(_t(backend, mus[None]), _t(backend, covs[None]), _t(backend, w[None]))
+    mo, So, ito = rp.fullcov_barycentre(mus, covs, w)
+    assert int(info.abs().sum()) == 0
+    assert iters[0] == ito, (iters, ito)
+    if scale > 1.0:
+        assert ito > 0
+    assert rel_err(mu[0].cpu().numpy(), mo) < 1e-12
+    assert rel_err(S[0].cpu().numpy(), So) < TOL_WEIGHTS
+    print(f"fullcov barycentre T={T} M={M}: {ito} iterations, rel err {rel_err(S[0].cpu().numpy(), So):.2e}")
+
+
+def test_fullcov_barycentre_reduces_to_1d_kernel(backend):
+    """T = 1: the matrix fixed point and its stop rule ARE gaussian_barycentre (wasserstein.py:61-100)."""
+    rng = np.random.default_rng(5)
+    for scale in (0.05, 30.0):
+        M = 5
+        mus = rng.normal(size=(M, 1))
+        var = rng.uniform(0.5, 2.0, size=(M, 1, 1)) * scale
+        w = rng.uniform(0.1, 1.0, M)
+        w /= w.sum()
+        mu, S, iters, _ = backend.barycentre_fullcov(_t(backend, mus[None]), _t(backend, var[None]), _t(backend, w[None]))
+        bm, bs, bi = backend.barycentre_1d(_t(backend, mus.reshape(1, M, 1)), _t(backend, var.reshape(1, M, 1)),
+                                           _t(backend, w.reshape(1, M, 1)))
+        assert iters[0] == int(bi.item())
+        assert abs(float(S.item()) - float(bs.item()) ** 2) < 1e-13 * max(1.0, float(S.item()))
+        assert abs(float(mu.item()) - float(bm.item())) < 1e-14
+
+
+def test_fullcov_barycentre_cells_batched(backend):
+    """Several cells in one call == one call per cell (cells converge at different iterations)."""
+    C, M, T = 3, 3, 30
+    mus, covs = _posterior_covs(C * M, 4, T, seed=11)
+    mus, covs = mus.reshape(C, M, T), covs.reshape(C, M, T, T).copy()
+    covs[1] *= 50.0
+    covs[2] *= 400.0
+    w = np.full((C, M), 1.0 / M)
+    mu, S, iters, _ = backend.barycentre_fullcov(_t(backend, mus), _t(backend, covs), _t(backend, w))
+    assert len(set(iters)) > 1
+    for c in range(C):
+        mu1, S1, it1, _ = backend.barycentre_fullcov(_t(backend, mus[c:c + 1]), _t(backend, covs[c:c + 1]),
+                                                     _t(backend, w[c:c + 1]))
+        assert it1[0] == iters[c]
+        assert rel_err(S[c].cpu().numpy(), S1[0].cpu().numpy()) < 1e-12
+        assert rel_err(mu[c].cpu().numpy(), mu1[0].cpu().numpy()) < 1e-14

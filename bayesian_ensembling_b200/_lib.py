@@ -12,7 +12,7 @@ import subprocess
 import sys
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libbe_b200.so")
+LIB_PATH = os.environ.get("BE_B200_LIB") or os.path.join(_HERE, "libbe_b200.so")  # override: A/B experiments only
 CSRC = os.path.join(_HERE, "csrc")
 INCLUDE = os.path.join(os.path.dirname(_HERE), "include")
 

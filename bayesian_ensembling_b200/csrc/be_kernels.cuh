@@ -156,8 +156,8 @@ __global__ void k_pad_from_dense(const double* __restrict__ A, const double* __r
 __global__ void __launch_bounds__(GEMM_THREADS, GEMM_CTAS_PER_SM)
     k_chol_update(double* __restrict__ Mat, double* __restrict__ Pbuf, int ld, int Tp, int kb, int B) {
     extern __shared__ __align__(16) double2 smem2[];
-    int tile = blockIdx.x / (2 * B), rem = blockIdx.x % (2 * B);
-    const int half = rem / B, b = rem % B;  // 128 x 64 half-tiles: columns half*64 .. half*64+63 of block kb
+    int tile, half, b;  // 128 x 64 half-tiles: columns half*64 .. half*64+63 of block kb
+    cta_decode(B, tile, half, b);
     const int ti = kb + tile;
     double* Mb = Mat + (size_t)b * Tp * ld;
     const int a_rows = blk_rows(Tp, ti), b_rows = min(BN, blk_rows(Tp, kb) - half * BN);
@@ -206,8 +206,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, GEMM_CTAS_PER_SM)
     k_panel_scale(const double* __restrict__ Pbuf, double* __restrict__ Mat, int ld, int Tp, int row_blk0, int cb,
                   const double* __restrict__ Dinv, int nblk, double sign, int B) {
     extern __shared__ __align__(16) double2 smem2[];
-    int tile = blockIdx.x / (2 * B), rem = blockIdx.x % (2 * B);
-    const int half = rem / B, b = rem % B;
+    int tile, half, b;
+    cta_decode(B, tile, half, b);
     int ti = row_blk0 + tile;
     double* Mb = Mat + (size_t)b * Tp * ld;
     const double* Sb = Pbuf + ((size_t)b * Tp + (size_t)ti * NB) * NB;
@@ -244,8 +244,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, GEMM_CTAS_PER_SM)
     k_trtri_accum(const double* __restrict__ V, const double* __restrict__ Cm, double* __restrict__ Pbuf, int ld,
                   int Tp, int i, int B) {
     extern __shared__ __align__(16) double2 smem2[];
-    int j = blockIdx.x / (2 * B), rem = blockIdx.x % (2 * B);
-    const int half = rem / B, b = rem % B;
+    int j, half, b;
+    cta_decode(B, j, half, b);
     const double* Vb = V + (size_t)b * Tp * ld;
     const double* Cb = Cm + (size_t)b * Tp * ld;
     const int b_rows = min(BN, blk_rows(Tp, i) - half * BN);
@@ -277,8 +277,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, GEMM_CTAS_PER_SM)
                 const double* __restrict__ mu, double* __restrict__ Work, double* __restrict__ var_diag,
                 double* __restrict__ cov_dense, int B) {
     extern __shared__ __align__(16) double2 smem2[];
-    int tile = blockIdx.x / (2 * B), rem = blockIdx.x % (2 * B);
-    const int half = rem / B, b = rem % B;
+    int tile, half, b;
+    cta_decode(B, tile, half, b);
     int ti, tj;
     tri_decode(tile, ti, tj);
     const double* Vb = V + (size_t)b * Tp * ld;

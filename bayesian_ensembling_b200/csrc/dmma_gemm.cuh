@@ -142,6 +142,30 @@ __device__ __forceinline__ void gemm_nt_mainloop(const double* __restrict__ A, i
     __syncthreads();  // every global read of A/B has landed: in-place epilogues are safe
 }
 
+// CTA rasterisation of the tile kernels: grid = tiles * 2 * B, TILE-major (the same tile of all B
+// problems side by side, so every CTA of a wave has the same K length and the wave drains together).
+// No operand is shared between co-resident CTAs in this order, which shows up as DRAM traffic well
+// above the algorithmic bytes (k_lauum_cov: 133 GB per launch against 10.4 GB, profiles/r01f_traffic.csv)
+// -- but DRAM then runs at ~2.8 TB/s, 43% of the measured peak, and is not the limiter: the
+// problem-major order (-DBE_RASTER_PROBLEM_MAJOR), which lets the CTAs of one problem share operand
+// rows through L2, measured 2% SLOWER on the cfg2 bench (30.08 vs 30.72 cells/s, same box, r01f).
+#ifdef BE_RASTER_PROBLEM_MAJOR
+__device__ __forceinline__ void cta_decode(int B, int& tile, int& half, int& b) {
+    const int per = gridDim.x / B;
+    b = blockIdx.x / per;
+    const int r = blockIdx.x % per;
+    tile = r >> 1;
+    half = r & 1;
+}
+#else
+__device__ __forceinline__ void cta_decode(int B, int& tile, int& half, int& b) {
+    tile = blockIdx.x / (2 * B);
+    const int rem = blockIdx.x % (2 * B);
+    half = rem / B;
+    b = rem % B;
+}
+#endif
+
 // lower-triangular pair index -> (ti >= tj)
 __device__ __forceinline__ void tri_decode(int idx, int& ti, int& tj) {
     int t = (int)((sqrt(8.0 * (double)idx + 1.0) - 1.0) * 0.5);

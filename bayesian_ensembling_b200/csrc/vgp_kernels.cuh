@@ -35,8 +35,8 @@ __host__ __device__ inline int gemm_tiles(int nblk, int shape) {
 template <class Epi>
 __global__ void __launch_bounds__(GEMM_THREADS, GEMM_CTAS_PER_SM) k_gemm_nt(GemmArgs g, Epi epi) {
     extern __shared__ __align__(16) double2 smem2[];
-    int tile = blockIdx.x / (2 * g.B), rem = blockIdx.x % (2 * g.B);
-    const int half = rem / g.B, b = rem % g.B;
+    int tile, half, b;
+    cta_decode(g.B, tile, half, b);
     int tA, tB;
     if (g.shape == SHAPE_FULL) {
         tA = tile / g.nblk;

@@ -102,11 +102,10 @@ def fit_weight_barycentre_member_sharded(realisations_local, observations, varia
                                          time_mean_weights=False, tolerance=1e-6, init_var=1.0,
                                          all_reduce=None, ops=None) -> CellBatchResult:
     """Member-sharded form for few-cell configs: every rank holds ``M_local`` members of ALL C
-    cells.  The only exchange is one all-reduce (sum, fp64) of the packed partial sums
-    ``[3,C,T] = (sum w~, sum w~ mu, sum w~ sigma)`` -- NCCL over NVLink when launched under
-    torchrun; ``all_reduce`` can be injected (tests use gloo on CPU tensors).  With
-    ``time_mean_weights`` the normaliser must be known before the time mean, so there are two
-    small all-reduces.  ``ops`` is the operator object (default: the CUDA
+    cells.  Two small all-reduces (sum, fp64) join them -- first the normaliser ``sum_m w~ [C,T]``,
+    then the packed ``[3,C,T] = (1, sum w mu, sum w sigma)`` of the NORMALISED weights -- NCCL over
+    NVLink when launched under torchrun; ``all_reduce`` can be injected (tests use gloo on CPU
+    tensors).  The time-mean of the weights (utils.py:111,133) sits between the two.  ``ops`` is the operator object (default: the CUDA
     ``Backend``); the CPU test-suite injects a stand-in to exercise this host logic over gloo."""
     import torch.distributed as dist
 
@@ -125,17 +124,17 @@ def fit_weight_barycentre_member_sharded(realisations_local, observations, varia
     post = be.gp_posterior(X, ym, yv, var, ls, jitter, want_cov=False, want_scale_tri=False)
     _, lls_exp, _ = be.loglik_weights_mvn(post.mvn_stats, o, Ml, standardisation_constant, want_lls=True)
     mu3, var3 = post.mu.view(C, Ml, T), post.var_diag.view(C, Ml, T)
-    partial = be.barycentre_1d_partial(mu3, var3, lls_exp)
-    if not time_mean_weights:
-        partial = all_reduce(partial)
-        w = be.weights_normalise(lls_exp, partial[0])
-    else:
-        total = all_reduce(partial[0].clone())
-        w = be.weights_normalise(lls_exp, total)
-        w_bar = be.weights_time_mean(w)
-        partial = be.barycentre_1d_partial(mu3, var3, w_bar)
-        partial = all_reduce(partial)
-        partial[0].fill_(1.0)  # utils.py:119: time-mean weights are used un-renormalised
+    # 1st exchange: the normaliser sum_m w~ (weights.py:122-123).  The weights are then formed exactly as the
+    # reference forms them, w = w~ / total, BEFORE they multiply anything: with Q-EXP's un-shifted exp the
+    # w~ are routinely denormal (1e-310), and sum(w~ mu) / sum(w~) would lose the bits that w~ / total keeps
+    # (measured 3e-6 relative on the barycentre mean at T=12 when one packed all-reduce of un-normalised
+    # partial sums was used).
+    total = all_reduce(be.barycentre_1d_partial(mu3, var3, lls_exp)[0].clone())
+    w = be.weights_normalise(lls_exp, total)
+    w_used = be.weights_time_mean(w) if time_mean_weights else w  # utils.py:111,133
+    # 2nd exchange: (sum_m w mu, sum_m w sigma) over the local members, packed in one buffer
+    partial = all_reduce(be.barycentre_1d_partial(mu3, var3, w_used))
+    partial[0].fill_(1.0)  # the weights are already normalised (time-mean weights are used as they are, utils.py:119)
     bmu, bsd, bit = be.barycentre_1d_finish(partial, tolerance, init_var, 200)
     return CellBatchResult(weights=w, bary_mu=bmu, bary_std=bsd, bary_iters=bit, mu=mu3, var_diag=var3,
                            info_fit=post.info_fit.view(C, Ml), info_dist=post.info_dist.view(C, Ml))

@@ -49,7 +49,8 @@ def workload_config(cfg, cells_per_step, n_gpus):
         "fit_level": "L1 fixed kernel hyper-parameters (variance 0.5, lengthscale 6.0): posterior + "
                      "distribution Cholesky + LogLikelihoodWeight + Barycentre",
         "sharding": "cells across ranks, no collective" if n_gpus > 1 else "single GPU",
-        "l2": "inputs+workspace per step >> 126 MB L2 (each member's work matrices are 2 x 73 MB)",
+        "l2": f"no flush needed: work matrices per step = {cells_per_step * cfg.members * 2 * (cfg.steps + 2) ** 2 * 8 / 1e6:.0f} MB "
+              f"(2 padded T x T fp64 matrices per member) vs 126 MB L2",
     }
 
 
@@ -301,6 +302,28 @@ def run_ours(args, cfg):
     tensor_flops = sum(p["flops"] for n, p in prof.items() if n in TENSOR_FAMILIES)
     total_launches = sum_over_ranks(float(launches))
 
+    # ---- L2: the natgrad + Adam training loop GPDTW1D.fit actually runs (models.py:208-215) ---------
+    l2 = None
+    if args.l2_iters > 0:
+        Bm = cfg.members
+        X, ym, yv = be.gpdtw1d_inputs(r_dev[0])
+        be.vgp_fit(X, ym, yv, 1, want_scale_tri=False)  # warm-up (graph instantiation, workspace)
+        torch.cuda.synchronize()
+        t_it = []
+        for n_it in (1, 1 + args.l2_iters):
+            f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            f0.record()
+            be.vgp_fit(X, ym, yv, n_it, want_scale_tri=False)
+            f1.record()
+            torch.cuda.synchronize()
+            t_it.append(f0.elapsed_time(f1))
+        ms_iter = (t_it[1] - t_it[0]) / args.l2_iters
+        l2 = {"ms_per_iteration_per_cell": ms_iter, "iterations_timed": args.l2_iters, "members": Bm,
+              "fixed_cost_ms_per_cell": t_it[0] - ms_iter,
+              "cells_per_sec_at_2000_iterations": 1e3 / (t_it[0] - ms_iter + 2000 * ms_iter),
+              "note": "be_vgp_fit on one cell (24 members batched): natural-gradient step + Adam step per iteration, "
+                      "CUDA-graph replay; 2000 iterations is what experiments/full_experiment_script.py:87-113 uses"}
+
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads, blas = _blas_threads()
@@ -332,6 +355,7 @@ def run_ours(args, cfg):
                                   "note": "all factorisation kernels (Cholesky x2, triangular inverse, lauum) together, "
                                           "algorithmic flops = 4/3 T^3 per member"},
             "stages": stages,
+            "l2_training_loop": l2,
             "cpu_baseline": cpu_baseline,
         }
         print(json.dumps(line), flush=True)
@@ -349,6 +373,7 @@ def main():
     ap.add_argument("--cells-per-step", type=int, default=6)
     ap.add_argument("--cpu-members", type=int, default=2, help="members of one cell the CPU arm times per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--l2-iters", type=int, default=3, help="training-loop iterations timed for the l2_training_loop line (0: skip)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     from bayesian_ensembling_b200 import synthetic

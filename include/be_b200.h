@@ -161,8 +161,10 @@ int be_barycentre_1d(be_ctx* ctx, const double* means, const double* variances,
                      double tolerance, double init_var, int max_iters,
                      double* mu, double* sigma, int* iters);
 /* member-sharded form (multi-GPU): partial sums over the local members
- *   partial [3,C,N] = (sum_m w~, sum_m w~ mu, sum_m w~ sqrt(var)) from UN-normalised w~;
- * all-reduce partial over ranks (NCCL), then be_barycentre_1d_finish divides and iterates. */
+ *   partial [3,C,N] = (sum_m w, sum_m w mu, sum_m w sqrt(var)) for whatever weights are passed:
+ * un-normalised w~ to obtain the normaliser (slot 0, all-reduced first, then be_weights_normalise),
+ * then the normalised weights for slots 1-2; all-reduce over ranks (NCCL);
+ * be_barycentre_1d_finish divides slots 1-2 by slot 0 and iterates. */
 int be_barycentre_1d_partial(be_ctx* ctx, const double* means, const double* variances,
                              const double* lls_exp, int C, int M_local, int N, double* partial);
 int be_barycentre_1d_finish(be_ctx* ctx, const double* partial, int C, int N,

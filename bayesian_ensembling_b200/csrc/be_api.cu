@@ -135,7 +135,7 @@ int ensure_kernel_attrs(be_ctx* ctx) {
     return BE_OK;
 }
 
-inline size_t matern_smem(int R) { return ((size_t)2 * NB * (R | 1) + 2 * NB) * sizeof(double); }
+inline size_t matern_smem(int R) { return ((size_t)2 * NB * R + 2 * NB) * sizeof(double); }
 
 // Blocked right-looking Cholesky of B padded matrices, in place (lower).  Never pivots on
 // columns >= T; rows >= T ride along (file header of be_kernels.cuh).  Fills Dinv with the

@@ -52,18 +52,65 @@ __global__ void k_gpdtw1d_inputs(const double* __restrict__ reals, int B, int R,
 // MODE 1: padded lower tiles of M = K + diag(y_var + jitter), padding identity, row T = y_mean.
 // MODE 2: padded [Tp,ld] K, all tiles, no noise, zero padding (predict_f's Kmn, models.py:217).
 // --------------------------------------------------------------------------------------
+// sqrt(q) for a NORMAL positive q (callers clamp at 1e-36): MUFU seed, one Newton step on 1/sqrt and
+// one on the root -- correctly rounded in all but a vanishing share of cases, no special-case calls.
+__device__ __forceinline__ double sqrt_pos(double q) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(q));
+    double e = fma(-q * y, y, 1.0);
+    y = fma(0.5 * y, e, y);
+    double r = q * y;
+    return fma(fma(-r, r, q), 0.5 * y, r);
+}
+
+// exp(-x) for x >= 0: n = rint(-x log2 e) by the 1.5 * 2^52 trick, Cody-Waite reduction with a
+// two-part ln 2, degree-13 Taylor polynomial on |r| <= ln2 / 2 (truncation 4e-18), exponent patched
+// in as an integer.  Valid for 0 <= x <= 700 and branch-free, so that the compiler interleaves the
+// chains of neighbouring entries; callers send x > 700 and NaN to the library routine.  <= 1 ulp from
+// the library exp (tests/test_gpu_parity.py::test_matern32_gram holds 1e-12 vs NumPy).
+__device__ __forceinline__ double exp_neg(double x) {
+    const double MAGIC = 6755399441055744.0;
+    double t = fma(x, -1.4426950408889634, MAGIC);
+    int n = __double2loint(t);
+    double nf = t - MAGIC;
+    double r = fma(nf, -6.93147180369123816490e-01, -x);
+    r = fma(nf, -1.90821492927058770002e-10, r);
+    double p = 1.6059043836821613e-10;           // 1/13!
+    p = fma(p, r, 2.08767569878681e-09);         // 1/12!
+    p = fma(p, r, 2.505210838544172e-08);        // 1/11!
+    p = fma(p, r, 2.755731922398589e-07);        // 1/10!
+    p = fma(p, r, 2.7557319223985893e-06);       // 1/9!
+    p = fma(p, r, 2.48015873015873e-05);         // 1/8!
+    p = fma(p, r, 1.984126984126984e-04);        // 1/7!
+    p = fma(p, r, 1.388888888888889e-03);        // 1/6!
+    p = fma(p, r, 8.333333333333333e-03);        // 1/5!
+    p = fma(p, r, 4.1666666666666664e-02);       // 1/4!
+    p = fma(p, r, 1.6666666666666666e-01);       // 1/3!
+    p = fma(p, r, 0.5);
+    p = fma(p, r, 1.0);
+    p = fma(p, r, 1.0);
+    return p * __hiloint2double((1023 + n) << 20, 0);
+}
+
+// Thread t = (ty, tx) = (t / 16, t % 16) owns rows ty*8 .. ty*8+7 and the column pairs
+// (2 tx, 2 tx + 1) + 32 c, c = 0..3, of the tile: the scaled inputs sit k-major in shared memory
+// ([k][row]) so that every operand fetch is a conflict-free LDS.128 (broadcast for the rows) and
+// every store is a 16-byte one with 16 lanes covering 256 contiguous bytes of a row.  What remains
+// per entry is the FP64 sqrt and exp, which is what bounds this kernel (FP64 pipe, not HBM).
+#ifndef BE_MATERN_CTAS
+#define BE_MATERN_CTAS 4
+#endif
 template <int MODE>
-__global__ void __launch_bounds__(256) k_matern32(const double* __restrict__ X, int B, int T, int R,
-                                                  const double* __restrict__ variance,
-                                                  const double* __restrict__ lengthscale,
-                                                  const double* __restrict__ y_mean, const double* __restrict__ y_var,
-                                                  double jitter, double* __restrict__ out, int Tp, int ld,
-                                                  int ntiles) {
-    extern __shared__ double sm[];
-    const int Rp = R | 1;
-    double* xi = sm;
-    double* xj = xi + NB * Rp;
-    double* si = xj + NB * Rp;
+__global__ void __launch_bounds__(256, BE_MATERN_CTAS) k_matern32(const double* __restrict__ X, int B, int T, int R,
+                                                     const double* __restrict__ variance,
+                                                     const double* __restrict__ lengthscale,
+                                                     const double* __restrict__ y_mean, const double* __restrict__ y_var,
+                                                     double jitter, double* __restrict__ out, int Tp, int ld,
+                                                     int ntiles) {
+    extern __shared__ __align__(16) double sm[];
+    double* xi = sm;              // [R][128]  rows of the tile, k-major
+    double* xj = xi + NB * R;     // [R][128]  columns of the tile
+    double* si = xj + NB * R;     // |x_i / l|^2
     double* sj = si + NB;
     int tile = blockIdx.x / B, b = blockIdx.x % B;
     int ti, tj;
@@ -79,43 +126,96 @@ __global__ void __launch_bounds__(256) k_matern32(const double* __restrict__ X, 
     for (int e = threadIdx.x; e < NB * R; e += blockDim.x) {
         int r = e / R, k = e % R;
         int gi = ti * NB + r, gj = tj * NB + r;
-        xi[r * Rp + k] = gi < T ? Xb[(size_t)gi * R + k] / ls : 0.0;
-        xj[r * Rp + k] = gj < T ? Xb[(size_t)gj * R + k] / ls : 0.0;
+        xi[k * NB + r] = gi < T ? Xb[(size_t)gi * R + k] / ls : 0.0;
+        xj[k * NB + r] = gj < T ? Xb[(size_t)gj * R + k] / ls : 0.0;
     }
     __syncthreads();
-    if (threadIdx.x < NB) {
+    {
+        const double* src = threadIdx.x < NB ? xi : xj;
+        const int r = threadIdx.x & (NB - 1);
         double s = 0.0;
-        for (int k = 0; k < R; ++k) s += xi[threadIdx.x * Rp + k] * xi[threadIdx.x * Rp + k];
-        si[threadIdx.x] = s;
-    } else {
-        int r = threadIdx.x - NB;
-        double s = 0.0;
-        for (int k = 0; k < R; ++k) s += xj[r * Rp + k] * xj[r * Rp + k];
-        sj[r] = s;
+        for (int k = 0; k < R; ++k) s += src[k * NB + r] * src[k * NB + r];
+        (threadIdx.x < NB ? si : sj)[r] = s;
     }
     __syncthreads();
+    const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
     const int lim = MODE == 0 ? T : Tp;
-    for (int e = threadIdx.x; e < NB * NB; e += blockDim.x) {
-        int i = e >> 7, j = e & 127;
-        int gi = ti * NB + i, gj = tj * NB + j;
-        if (gi >= lim || gj >= lim) continue;
-        double val;
-        if (gi < T && gj < T) {
-            double dot = 0.0;
-            for (int k = 0; k < R; ++k) dot += xi[i * Rp + k] * xj[j * Rp + k];
-            double r2 = (-2.0 * dot + si[i]) + sj[j];
-            double r = sqrt(fmax(r2, 1e-36));
-            val = var * (1.0 + SQRT3 * r) * exp(-SQRT3 * r);
-            if (MODE == 1 && gi == gj) val += y_var[(size_t)b * T + gi] + jitter;
-        } else if (MODE == 1 && gi == T && gj < T) {
-            val = y_mean[(size_t)b * T + gj];
-        } else {
-            val = (MODE == 1 && gi == gj) ? 1.0 : 0.0;
+    // fast path: every entry of the tile is a real (i, j) pair and (MODE 1) no diagonal entry is in it
+    const bool interior = (ti + 1) * NB <= T && (tj + 1) * NB <= T && !(MODE == 1 && ti == tj);
+    double* ob = MODE != 0 ? out + (size_t)b * Tp * ld : out + (size_t)b * T * T;
+    const int ldo = MODE != 0 ? ld : T;
+    // 2 x 2 entries at a time (two rows, one column pair): few registers, so four CTAs (32 warps) stay
+    // resident per SM and hide the long dependent chains of the FP64 sqrt and exp.
+#pragma unroll 1
+    for (int ip = 0; ip < 4; ++ip) {
+        const int lr = ty * 8 + 2 * ip;  // local rows lr, lr + 1
+        const int gi0 = ti * NB + lr;
+        const double2 si2 = *reinterpret_cast<const double2*>(si + lr);
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+            const int lc = 2 * tx + 32 * c;  // local columns lc, lc + 1
+            const int gj = tj * NB + lc;
+            double acc[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+            for (int k = 0; k < R; ++k) {
+                const double2 a2 = *reinterpret_cast<const double2*>(xi + k * NB + lr);
+                const double2 b2 = *reinterpret_cast<const double2*>(xj + k * NB + lc);
+                acc[0][0] = fma(a2.x, b2.x, acc[0][0]);
+                acc[0][1] = fma(a2.x, b2.y, acc[0][1]);
+                acc[1][0] = fma(a2.y, b2.x, acc[1][0]);
+                acc[1][1] = fma(a2.y, b2.y, acc[1][1]);
+            }
+            const double2 sj2 = *reinterpret_cast<const double2*>(sj + lc);
+            double v[2][2];
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    double r2 = (-2.0 * acc[i][e] + (i ? si2.y : si2.x)) + (e ? sj2.y : sj2.x);
+                    const double x = SQRT3 * sqrt_pos(fmax(r2, 1e-36));
+                    v[i][e] = x;
+                }
+            const bool fast = v[0][0] <= 700.0 && v[0][1] <= 700.0 && v[1][0] <= 700.0 && v[1][1] <= 700.0;
+            if (fast) {  // one straight-line block: the four polynomial chains interleave
+                const double e00 = exp_neg(v[0][0]), e01 = exp_neg(v[0][1]), e10 = exp_neg(v[1][0]), e11 = exp_neg(v[1][1]);
+                v[0][0] = var * (1.0 + v[0][0]) * e00;
+                v[0][1] = var * (1.0 + v[0][1]) * e01;
+                v[1][0] = var * (1.0 + v[1][0]) * e10;
+                v[1][1] = var * (1.0 + v[1][1]) * e11;
+            } else {
+#pragma unroll
+                for (int i = 0; i < 2; ++i)
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) v[i][e] = var * (1.0 + v[i][e]) * exp(-v[i][e]);
+            }
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const int gi = gi0 + i;
+                if (interior) {
+                    if (MODE != 0) {
+                        *reinterpret_cast<double2*>(ob + (size_t)gi * ldo + gj) = make_double2(v[i][0], v[i][1]);
+                    } else {
+                        ob[(size_t)gi * ldo + gj] = v[i][0];
+                        ob[(size_t)gi * ldo + gj + 1] = v[i][1];
+                    }
+                    continue;
+                }
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int gc = gj + e;
+                    if (gi >= lim || gc >= lim) continue;
+                    double val;
+                    if (gi < T && gc < T) {
+                        val = v[i][e];
+                        if (MODE == 1 && gi == gc) val += y_var[(size_t)b * T + gi] + jitter;
+                    } else if (MODE == 1 && gi == T && gc < T) {
+                        val = y_mean[(size_t)b * T + gc];
+                    } else {
+                        val = (MODE == 1 && gi == gc) ? 1.0 : 0.0;
+                    }
+                    ob[(size_t)gi * ldo + gc] = val;
+                }
+            }
         }
-        if (MODE != 0)
-            out[(size_t)b * Tp * ld + (size_t)gi * ld + gj] = val;
-        else
-            out[(size_t)b * T * T + (size_t)gi * T + gj] = val;
     }
 }
 
@@ -449,7 +549,12 @@ __global__ void k_mvn_constvec_logprob(const double* __restrict__ stats, const d
 }
 
 // one thread per (cell, time): mean over obs realisations (weights.py:103-104), exp(c .) (:107),
-// normalise over models (:122-123).  Sequential sums in the reference's order.
+// normalise over models (:122-123).  The constant-vector log-density is quadratic in the observation,
+// so its mean over the Ro realisations needs only mean(o) and mean(o^2):
+//   mean_r ll = -1/2 (|a|^2 mean(o^2) - 2 a.b mean(o) + |b|^2) - T/2 log 2pi - sum log diag L
+// (same terms as summing the Ro log-densities, one rounding pattern apart: ~1e-13 on the weights).
+// That takes the kernel from M*Ro to M density evaluations per point and makes it HBM-bound
+// (bench.py hbm_stages); the per-realisation values stay available from k_mvn_constvec_logprob.
 __global__ void k_loglik_weights_mvn(const double* __restrict__ stats, const double* __restrict__ obs, int C, int M,
                                      int Ro, int T, double cst, double* __restrict__ w, double* __restrict__ lls_exp,
                                      double* __restrict__ lls_mean) {
@@ -457,12 +562,21 @@ __global__ void k_loglik_weights_mvn(const double* __restrict__ stats, const dou
     if (gid >= (size_t)C * T) return;
     int c = (int)(gid / T), i = (int)(gid % T);
     const double* ob = obs + (size_t)c * Ro * T + i;
+    double m1 = 0.0, m2 = 0.0;
+    for (int r = 0; r < Ro; ++r) {
+        double o = ob[(size_t)r * T];
+        m1 += o;
+        m2 = fma(o, o, m2);
+    }
+    m1 /= Ro;
+    m2 /= Ro;
+    const double base = -0.5 * (double)T * LOG_2PI;
     double total = 0.0;
     for (int m = 0; m < M; ++m) {
-        const double* st = stats + ((size_t)c * M + m) * 4;
-        double s = 0.0;
-        for (int r = 0; r < Ro; ++r) s += constvec_ll(st, ob[(size_t)r * T], T);
-        double mean = s / Ro;
+        const double2* sp = reinterpret_cast<const double2*>(stats + ((size_t)c * M + m) * 4);
+        const double2 s01 = __ldg(sp), s23 = __ldg(sp + 1);
+        double maha = (m2 * s01.x - 2.0 * m1 * s01.y) + s23.x;
+        double mean = (-0.5 * maha + base) - s23.y;
         double e = exp(cst * mean);
         size_t o = ((size_t)c * M + m) * T + i;
         if (lls_mean) lls_mean[o] = mean;

@@ -74,6 +74,11 @@ struct TileAcc {
     double v[8][4][2];  // [m-block][n-block][pair]; warp tile 64 x 32
 };
 
+// Tried and dropped (r01g): interleaving the 8-row / 8-column blocks between the warps and skipping,
+// under a per-warp 32-bit mask, the DMMAs of blocks past a ragged edge or strictly above the diagonal
+// of a diagonal tile (~5% of the issued DMMAs at T=3012).  With both the masked and the plain loop
+// inlined in one kernel ptxas hit the 255-register cap and spilled, and k_chol_update got 6% SLOWER
+// (88.9 vs 83.5 ms per cfg2 step); the plain loop stays.
 // Thread's coordinates inside the 128 x 128 tile for accumulator (mi, ni, e).
 __device__ __forceinline__ int acc_row(int warp, int lane, int mi) { return (warp >> 1) * 64 + mi * 8 + (lane >> 2); }
 __device__ __forceinline__ int acc_col(int warp, int lane, int ni) { return (warp & 1) * 32 + ni * 8 + 2 * (lane & 3); }

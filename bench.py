@@ -161,6 +161,52 @@ def run_reference(args, cfg):
 
 
 # ------------------------------------------------------------------------------------------------
+# memory-bound stages measured alone
+# ------------------------------------------------------------------------------------------------
+def measure_hbm_stages(be, cfg, n_points, hbm_peak, reps=5):
+    """LogLikelihoodWeight, weight time-mean and Barycentre kernels on C x T = n_points points with M
+    members (cfg3/cfg4-shaped: many cells), finite weights, buffers >> 126 MB L2.  Algorithmic bytes
+    per point are DESIGN.md section 4's figures; time = best of ``reps`` CUDA-event timings."""
+    import torch
+
+    M, Ro, T = cfg.members, cfg.obs_realisations, 1980
+    C = max(1, n_points // T)
+    N = C * T
+    g = torch.Generator(device=be.device).manual_seed(1)
+    rnd = lambda *s: torch.rand(*s, dtype=torch.float64, device=be.device, generator=g)  # noqa: E731
+    # constant-vector log-prob statistics (|a|^2, a.b, |b|^2, sum log diag L) giving ll in about [-6, 0]
+    a2 = 0.5 + rnd(C * M)
+    stats = torch.stack([a2, a2 * (0.9 + 0.2 * rnd(C * M)), a2 * (1.0 + 0.2 * rnd(C * M)),
+                         -0.5 * T * 1.8378770664093453 + rnd(C * M)], dim=1).contiguous()
+    obs = 0.8 + 0.4 * rnd(C, Ro, T)
+    means, variances = rnd(C, M, T), 0.01 + 0.05 * rnd(C, M, T)
+
+    def timed(fn):
+        best = float("inf")
+        for _ in range(reps + 1):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            out = fn()
+            e1.record()
+            torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        return best, out
+
+    res = {}
+    ms, w = timed(lambda: be.loglik_weights_mvn(stats, obs, M))
+    assert bool(torch.isfinite(w).all())
+    res["k_loglik_weights"] = (ms, N * 8.0 * (Ro + M) + C * M * 32.0)
+    ms, wb = timed(lambda: be.weights_time_mean(w))
+    res["k_weights_time_mean"] = (ms, N * M * 16.0)
+    ms, out = timed(lambda: be.barycentre_1d(means, variances, w))
+    assert int(out[2].max()) == 0  # degC-anomaly scale: the signed stop rule exits at iteration 0
+    res["k_barycentre"] = (ms, N * (24.0 * M + 16.0 + 4.0))
+    return {"points": N, "cells": C, "time_steps": T, "members": M, "peak_gbs": hbm_peak,
+            "kernels": {k: {"ms": ms, "algorithmic_bytes": b, "gbs": b / ms / 1e6, "frac_of_hbm_peak": b / ms / 1e6 / hbm_peak}
+                        for k, (ms, b) in res.items()}}
+
+
+# ------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------
 TENSOR_FAMILIES = {"k_chol_update", "k_trtri_accum", "k_lauum_cov", "k_panel_scale", "k_diag_block"}
@@ -324,6 +370,12 @@ def run_ours(args, cfg):
               "note": "be_vgp_fit on one cell (24 members batched): natural-gradient step + Adam step per iteration, "
                       "CUDA-graph replay; 2000 iterations is what experiments/full_experiment_script.py:87-113 uses"}
 
+    # ---- memory-bound stages on their own, at a size >> L2 and with FINITE weights ----------------
+    # (inside the cfg2 step they see 6 x 3012 points -- launch-latency sized -- and, at T=3012, NaN weights)
+    hbm_stages = None
+    if args.hbm_points > 0 and rank == 0:
+        hbm_stages = measure_hbm_stages(be, cfg, args.hbm_points, hbm_peak)
+
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads, blas = _blas_threads()
@@ -356,6 +408,7 @@ def run_ours(args, cfg):
                                           "algorithmic flops = 4/3 T^3 per member"},
             "stages": stages,
             "l2_training_loop": l2,
+            "hbm_stages": hbm_stages,
             "cpu_baseline": cpu_baseline,
         }
         print(json.dumps(line), flush=True)
@@ -373,6 +426,8 @@ def main():
     ap.add_argument("--cells-per-step", type=int, default=6)
     ap.add_argument("--cpu-members", type=int, default=2, help="members of one cell the CPU arm times per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--hbm-points", type=int, default=4_000_000,
+                    help="(cell, time) points of the stand-alone memory-bound stage measurements (0: skip)")
     ap.add_argument("--l2-iters", type=int, default=3, help="training-loop iterations timed for the l2_training_loop line (0: skip)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)

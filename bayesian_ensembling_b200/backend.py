@@ -401,3 +401,41 @@ class Backend:
                                             ctypes.cast(iters, ctypes.c_void_p), _ptr(info), _ptr(ws), nbytes)
         _lib.check(self.ctx, rc, "be_barycentre_fullcov")
         return mu, S, list(iters), info
+
+    # ------------------------------------------------------------------ SURVEY 8f "next": CRPS / similarity weights
+    def crps_weights(self, loc, scale, obs, want_crps=False):
+        """loc/scale [C,M,N], obs [C,Ro,N] -> weights [C,M,N] (+ crps_mean) (weights.py:444-515)"""
+        loc = self._in(loc)
+        C, M, N = loc.shape
+        scale = self._in(scale, (C, M, N), "scale")
+        obs = self._in(obs)
+        Ro = obs.shape[1]
+        w = self._new(C, M, N)
+        cm = self._new(C, M, N) if want_crps else None
+        self._sync_stream()
+        rc = self.lib.be_crps_weights(self.ctx, _ptr(loc), _ptr(scale), _ptr(obs), C, M, Ro, N, _ptr(w), _ptr(cm))
+        _lib.check(self.ctx, rc, "be_crps_weights")
+        return (w, cm) if want_crps else w
+
+    def w2_collapse(self, w2):
+        """w2 [C,M,M,N] -> weights [C,M,N]: nanmean over the second model, normalised over models"""
+        w2 = self._in(w2)
+        C, M, M2, N = w2.shape
+        assert M == M2
+        w = self._new(C, M, N)
+        self._sync_stream()
+        rc = self.lib.be_w2_collapse(self.ctx, _ptr(w2), C, M, N, _ptr(w))
+        _lib.check(self.ctx, rc, "be_w2_collapse")
+        return w
+
+    def similarity_weights_pointwise(self, mean, var, want_w2=False):
+        """mean/var [C,M,N] -> weights [C,M,N] (+ w2 [C,M,M,N]) (weights.py:302-325,331)"""
+        mean = self._in(mean)
+        C, M, N = mean.shape
+        var = self._in(var, (C, M, N), "var")
+        w = self._new(C, M, N)
+        w2 = self._new(C, M, M, N) if want_w2 else None
+        self._sync_stream()
+        rc = self.lib.be_similarity_weights_pointwise(self.ctx, _ptr(mean), _ptr(var), C, M, N, _ptr(w), _ptr(w2))
+        _lib.check(self.ctx, rc, "be_similarity_weights_pointwise")
+        return (w, w2) if want_w2 else w

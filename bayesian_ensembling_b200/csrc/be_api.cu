@@ -9,6 +9,7 @@
 #include "be_kernels.cuh"
 #include "vgp_kernels.cuh"
 #include "sqrtm_kernels.cuh"
+#include "weights_next_kernels.cuh"
 
 using namespace be;
 

@@ -68,12 +68,12 @@ __device__ __forceinline__ double sqrt_pos(double q) {
 // in as an integer.  Valid for 0 <= x <= 700 and branch-free, so that the compiler interleaves the
 // chains of neighbouring entries; callers send x > 700 and NaN to the library routine.  <= 1 ulp from
 // the library exp (tests/test_gpu_parity.py::test_matern32_gram holds 1e-12 vs NumPy).
-__device__ __forceinline__ double exp_neg(double x) {
+__device__ __forceinline__ double exp_core(double y) {  // exp(y), |y| <= 700
     const double MAGIC = 6755399441055744.0;
-    double t = fma(x, -1.4426950408889634, MAGIC);
+    double t = fma(y, 1.4426950408889634, MAGIC);
     int n = __double2loint(t);
     double nf = t - MAGIC;
-    double r = fma(nf, -6.93147180369123816490e-01, -x);
+    double r = fma(nf, -6.93147180369123816490e-01, y);
     r = fma(nf, -1.90821492927058770002e-10, r);
     double p = 1.6059043836821613e-10;           // 1/13!
     p = fma(p, r, 2.08767569878681e-09);         // 1/12!
@@ -91,6 +91,7 @@ __device__ __forceinline__ double exp_neg(double x) {
     p = fma(p, r, 1.0);
     return p * __hiloint2double((1023 + n) << 20, 0);
 }
+__device__ __forceinline__ double exp_neg(double x) { return exp_core(-x); }
 
 // Thread t = (ty, tx) = (t / 16, t % 16) owns rows ty*8 .. ty*8+7 and the column pairs
 // (2 tx, 2 tx + 1) + 32 c, c = 0..3, of the tile: the scaled inputs sit k-major in shared memory
@@ -553,8 +554,11 @@ __global__ void k_mvn_constvec_logprob(const double* __restrict__ stats, const d
 // so its mean over the Ro realisations needs only mean(o) and mean(o^2):
 //   mean_r ll = -1/2 (|a|^2 mean(o^2) - 2 a.b mean(o) + |b|^2) - T/2 log 2pi - sum log diag L
 // (same terms as summing the Ro log-densities, one rounding pattern apart: ~1e-13 on the weights).
-// That takes the kernel from M*Ro to M density evaluations per point and makes it HBM-bound
-// (bench.py hbm_stages); the per-realisation values stay available from k_mvn_constvec_logprob.
+// That takes the kernel from M*Ro to M density evaluations per point (15% -> 42% of the HBM peak at 4M
+// points, bench.py hbm_stages); the per-realisation values stay available from k_mvn_constvec_logprob.
+// (Variants that interleave four fast-exp chains, or keep the un-normalised weights in registers instead of
+// re-reading them, measured SLOWER at 4M points -- 0.44 / 0.52 ms against 0.40 ms: the kernel is latency-bound
+// at the occupancy those variants allow, not ALU- or traffic-bound.)
 __global__ void k_loglik_weights_mvn(const double* __restrict__ stats, const double* __restrict__ obs, int C, int M,
                                      int Ro, int T, double cst, double* __restrict__ w, double* __restrict__ lls_exp,
                                      double* __restrict__ lls_mean) {

@@ -318,4 +318,47 @@ int be_barycentre_fullcov(be_ctx* ctx, const double* mus, const double* sigmas, 
     return BE_OK;
 }
 
+/* ---- SURVEY 8f "next": CRPSWeight and ModelSimilarityWeight ------------------------------------ */
+int be_crps_weights(be_ctx* ctx, const double* loc, const double* scale, const double* obs, int C, int M, int Ro,
+                    int N, double* weights, double* crps_mean) {
+    if (!ctx) return -1;
+    if (!loc) return -2;
+    if (!scale) return -3;
+    if (!obs) return -4;
+    if (C <= 0) return -5;
+    if (M <= 0) return -6;
+    if (Ro <= 0) return -7;
+    if (N <= 0) return -8;
+    if (!weights) return -9;
+    k_crps_weights<<<grid1d((size_t)C * N, 128), 128, 0, ctx->stream>>>(loc, scale, obs, C, M, Ro, N, weights, crps_mean);
+    BE_LAUNCHED();
+    return BE_OK;
+}
+
+int be_w2_collapse(be_ctx* ctx, const double* w2, int C, int M, int N, double* weights) {
+    if (!ctx) return -1;
+    if (!w2) return -2;
+    if (C <= 0) return -3;
+    if (M <= 0) return -4;
+    if (N <= 0) return -5;
+    if (!weights) return -6;
+    k_w2_collapse<<<grid1d((size_t)C * N, 128), 128, 0, ctx->stream>>>(w2, C, M, N, weights);
+    BE_LAUNCHED();
+    return BE_OK;
+}
+
+int be_similarity_weights_pointwise(be_ctx* ctx, const double* mean, const double* var, int C, int M, int N,
+                                    double* weights, double* w2_out) {
+    if (!ctx) return -1;
+    if (!mean) return -2;
+    if (!var) return -3;
+    if (C <= 0) return -4;
+    if (M <= 0) return -5;
+    if (N <= 0) return -6;
+    if (!weights) return -7;
+    k_similarity_pointwise<<<grid1d((size_t)C * N, 128), 128, 0, ctx->stream>>>(mean, var, C, M, N, weights, w2_out);
+    BE_LAUNCHED();
+    return BE_OK;
+}
+
 }  // extern "C"

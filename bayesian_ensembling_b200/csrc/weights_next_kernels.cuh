@@ -1,0 +1,109 @@
+// SURVEY 8f "next" rows: CRPSWeight (ensembles/weights.py:444-515) and ModelSimilarityWeight
+// (weights.py:214-333).  Per-point kernels over [C, M, N] arrays, HBM-bound.
+#pragma once
+#include "be_kernels.cuh"
+
+namespace be {
+
+constexpr double INV_SQRT_PI = 0.5641895835477563;
+constexpr double INV_SQRT_2PI = 0.3989422804014327;
+
+// properscoring.crps_gaussian: sig (z (2 Phi(z) - 1) + 2 phi(z) - 1/sqrt(pi)),  z = (x - mu) / sig
+__device__ __forceinline__ double crps_gaussian_d(double x, double mu, double sig) {
+    double z = (x - mu) / sig;
+    double pdf = exp(-0.5 * z * z) * INV_SQRT_2PI;
+    double cdf = normcdf(z);
+    return sig * (z * (2.0 * cdf - 1.0) + 2.0 * pdf - INV_SQRT_PI);
+}
+
+// one thread per (cell, point): weights.py:469-471 (mean over obs realisations), :507 (inverse),
+// :510-511 (normalise over models).  scale = the distribution's stddev() -- for the dx.Normal the
+// reference builds at :497 that is the member's VARIANCE (quirk Q-SCALE); the caller passes it.
+__global__ void k_crps_weights(const double* __restrict__ loc, const double* __restrict__ scale,
+                               const double* __restrict__ obs, int C, int M, int Ro, int N, double* __restrict__ w,
+                               double* __restrict__ crps_mean) {
+    size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= (size_t)C * N) return;
+    int c = (int)(gid / N), i = (int)(gid % N);
+    const double* ob = obs + (size_t)c * Ro * N + i;
+    double total = 0.0;
+    for (int m = 0; m < M; ++m) {
+        size_t o = ((size_t)c * M + m) * N + i;
+        double l = loc[o], sc = scale[o];
+        double s = 0.0;
+        for (int r = 0; r < Ro; ++r) s += crps_gaussian_d(ob[(size_t)r * N], l, sc);
+        double mean = s / Ro;
+        if (crps_mean) crps_mean[o] = mean;
+        double inv = 1.0 / mean;
+        w[o] = inv;
+        total += inv;
+    }
+    for (int m = 0; m < M; ++m) {
+        size_t o = ((size_t)c * M + m) * N + i;
+        w[o] = w[o] / total;
+    }
+}
+
+// nanmean over j of d[c, i, j, n], then normalise over i (weights.py:259,296,321 and :331).
+// One thread per (cell, n); the M x M distances of a point are read once.
+__global__ void k_w2_collapse(const double* __restrict__ d, int C, int M, int N, double* __restrict__ w) {
+    size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= (size_t)C * N) return;
+    int c = (int)(gid / N), n = (int)(gid % N);
+    const double* dc = d + (size_t)c * M * M * N + n;
+    double total = 0.0;
+    for (int i = 0; i < M; ++i) {
+        double s = 0.0, cnt = 0.0;
+        for (int j = 0; j < M; ++j) {
+            double v = dc[((size_t)i * M + j) * N];
+            if (!isnan(v)) {
+                s += v;
+                cnt += 1.0;
+            }
+        }
+        double m = s / cnt;
+        w[((size_t)c * M + i) * N + n] = m;
+        total += m;
+    }
+    for (int i = 0; i < M; ++i) {
+        size_t o = ((size_t)c * M + i) * N + n;
+        w[o] = w[o] / total;
+    }
+}
+
+// mode="temporal" (weights.py:302-325): per point n and pair (i, j) the 1-dimensional
+// full_cov=False W2 of wasserstein.py:36-45,  |m_i - m_j| + (v_i + v_j - 2 sqrt(sqrt(v_i) v_j sqrt(v_i))),
+// v = the distributions' variance() (the caller passes it: variance**2 for the reference's
+// dx.Normal(mean, variance)); nanmean over j; normalise over i.  Optionally writes the distances.
+__global__ void k_similarity_pointwise(const double* __restrict__ mean, const double* __restrict__ var, int C, int M,
+                                       int N, double* __restrict__ w, double* __restrict__ w2_out) {
+    size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= (size_t)C * N) return;
+    int c = (int)(gid / N), n = (int)(gid % N);
+    const double* mc = mean + (size_t)c * M * N + n;
+    const double* vc = var + (size_t)c * M * N + n;
+    double total = 0.0;
+    for (int i = 0; i < M; ++i) {
+        const double mi = mc[(size_t)i * N], vi = vc[(size_t)i * N];
+        const double ri = sqrt(vi);
+        double s = 0.0, cnt = 0.0;
+        for (int j = 0; j < M; ++j) {
+            const double mj = mc[(size_t)j * N], vj = vc[(size_t)j * N];
+            double dist = fabs(mi - mj) + ((vi + vj) - 2.0 * sqrt(ri * vj * ri));
+            if (w2_out) w2_out[(((size_t)c * M + i) * M + j) * N + n] = dist;
+            if (!isnan(dist)) {
+                s += dist;
+                cnt += 1.0;
+            }
+        }
+        double m = s / cnt;
+        w[((size_t)c * M + i) * N + n] = m;
+        total += m;
+    }
+    for (int i = 0; i < M; ++i) {
+        size_t o = ((size_t)c * M + i) * N + n;
+        w[o] = w[o] / total;
+    }
+}
+
+}  // namespace be

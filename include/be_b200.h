@@ -213,6 +213,25 @@ int be_barycentre_fullcov(be_ctx* ctx, const double* mus, const double* sigmas, 
                           double* mu, double* S_out, int* iters_host, int* info,
                           void* workspace, size_t workspace_bytes);
 
+/* ---- SURVEY 8f "next" rows 2-3 (callers either side of the path) --------------------------
+ * CRPSWeight._compute, ensembles/weights.py:444-515: crps_mean[c,m,n] = mean over obs realisations of
+ * properscoring.crps_gaussian(obs, loc, scale) (:469-471); weights = (1/crps) normalised over
+ * models (:507-511).  loc, scale [C,M,N] -- scale is the distribution's stddev(), which for the
+ * dx.Normal(mean, variance) built at :497 is the member's VARIANCE (quirk Q-SCALE); obs [C,Ro,N];
+ * weights [C,M,N]; crps_mean [C,M,N] may be NULL. */
+int be_crps_weights(be_ctx* ctx, const double* loc, const double* scale, const double* obs,
+                    int C, int M, int Ro, int N, double* weights, double* crps_mean);
+/* ModelSimilarityWeight._compute, ensembles/weights.py:214-333.
+ * be_w2_collapse: w2 [C,M,M,N] pairwise distances (from be_w2_distance / be_w2_distance_diag)
+ *   -> nanmean over the second model (:259,296,321), normalised over models (:331): weights [C,M,N]
+ *   (mode "single": N = 1; mode "spatial": N = lat * lon).
+ * be_similarity_weights_pointwise: mode "temporal" (:302-325) in one pass -- per point the
+ *   1-dimensional full_cov=False W2 of wasserstein.py:36-45 between every pair of members;
+ *   mean, var [C,M,N] (var = the distributions' variance()); w2_out [C,M,M,N] may be NULL. */
+int be_w2_collapse(be_ctx* ctx, const double* w2, int C, int M, int N, double* weights);
+int be_similarity_weights_pointwise(be_ctx* ctx, const double* mean, const double* var,
+                                    int C, int M, int N, double* weights, double* w2_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -463,6 +463,79 @@ def fullcov_barycentre(mus, sigmas, weights, tolerance=1e-6, init_var=1.0, max_i
 
 
 # --------------------------------------------------------------------------------------
+# SURVEY 8f "next" rows 2 and 3: ModelSimilarityWeight and CRPSWeight
+# --------------------------------------------------------------------------------------
+def model_similarity_weights_single(mus, sigmas):
+    """``ModelSimilarityWeight._compute(mode="single")`` for full-covariance members,
+    ensembles/weights.py:240-265,331: all M^2 pairwise W2 "distances" (a8, including the
+    un-squared location term), ``nanmean`` over the second model, normalise by the sum over models.
+    Returns ``(weights [M], w2 [M,M])``."""
+    M = len(mus)
+    w2 = np.full((M, M), np.nan)
+    for i in range(M):
+        for j in range(M):
+            w2[i, j] = gaussian_w2_distance(mus[i], sigmas[i], mus[j], sigmas[j])
+    v = np.nanmean(w2, axis=1)
+    return v / v.sum(), w2
+
+
+def w2_distance_diag(mu1, var1, mu2, var2):
+    """``gaussian_w2_distance_distrax(..., full_cov=False)`` (wasserstein.py:36-45) on vectors:
+    the covariances are ``diag(variance)``."""
+    mu1, mu2 = np.atleast_1d(mu1), np.atleast_1d(mu2)
+    return gaussian_w2_distance(mu1, np.diag(np.atleast_1d(var1)), mu2, np.diag(np.atleast_1d(var2)))
+
+
+def model_similarity_weights_temporal(means, variances):
+    """``mode="temporal"``, ensembles/weights.py:302-325,331: per time step t and pair (i, j),
+    ``dx.Normal(mean_i[t], variance_i[t])`` -- the variance goes in as a SCALE (quirk Q-SCALE),
+    so the distribution's variance is ``variance**2`` -- and the 1-dimensional
+    ``full_cov=False`` W2; ``nanmean`` over j; normalise over models.  Inputs ``[M,T]``."""
+    means, variances = np.asarray(means, dtype=np.float64), np.asarray(variances, dtype=np.float64)
+    M, T = means.shape
+    w2 = np.full((M, M, T), np.nan)
+    v = variances * variances  # dx.Normal(loc, scale).variance() with scale = variance
+    for i in range(M):
+        for j in range(M):
+            for t in range(T):
+                w2[i, j, t] = w2_distance_diag(means[i, t], v[i, t], means[j, t], v[j, t])
+    m = np.nanmean(w2, axis=1)
+    return m / m.sum(axis=0), w2
+
+
+def crps_gaussian(x, mu, sig):
+    """``properscoring.crps_gaussian`` (properscoring 0.1, requirements.txt:127; un-vendored):
+    ``sig * (z (2 Phi(z) - 1) + 2 phi(z) - 1/sqrt(pi))``, ``z = (x - mu) / sig``."""
+    from scipy import special
+
+    z = (np.asarray(x, dtype=np.float64) - mu) / sig
+    pdf = np.exp(-0.5 * z * z) / math.sqrt(2.0 * math.pi)
+    cdf = special.ndtr(z)
+    return sig * (z * (2.0 * cdf - 1.0) + 2.0 * pdf - 1.0 / math.sqrt(math.pi))
+
+
+def crps_weights(locs, variances, obs):
+    """``CRPSWeight._compute``, ensembles/weights.py:469-515: per model and point
+    ``dx.Normal(model_mean[i], model_var[i])`` (:497; the variance is the SCALE, Q-SCALE), mean over
+    the observation realisations of ``crps_gaussian(obs, mu, sigma)`` (:469-471), inverse (:507),
+    normalise over models (:510-511).  ``locs, variances [M,N]``, ``obs [Ro,N]``.
+    Returns ``(weights [M,N], crps [M,N])``."""
+    locs, variances, obs = (np.asarray(a, dtype=np.float64) for a in (locs, variances, obs))
+    crps = np.asarray([np.mean([crps_gaussian(o, l, s) for o in obs], axis=0) for l, s in zip(locs, variances)])
+    with np.errstate(over="ignore", invalid="ignore", divide="ignore"):
+        inv = 1.0 / crps
+        return inv / inv.sum(axis=0), crps
+
+
+def inverse_square_weights(model_means, obs_mean):
+    """``InverseSquareWeight._compute``, ensembles/weights.py:158-169: ``(mean_r model - mean_r obs)^-2``
+    normalised over models.  ``model_means [M,N]``, ``obs_mean [N]``."""
+    with np.errstate(over="ignore", invalid="ignore", divide="ignore"):
+        w = (np.asarray(model_means) - np.asarray(obs_mean)[None]) ** -2.0
+        return w / w.sum(axis=0)
+
+
+# --------------------------------------------------------------------------------------
 # the whole path for one grid cell (what bench.py's cpu_baseline times)
 # --------------------------------------------------------------------------------------
 def cell_pipeline_L1(realisations, obs, variance, lengthscale, y_means=None, jitter=DEFAULT_JITTER,

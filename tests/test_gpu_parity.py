@@ -542,3 +542,79 @@ def test_fullcov_barycentre_cells_batched(backend):
         assert it1[0] == iters[c]
         assert rel_err(S[c].cpu().numpy(), S1[0].cpu().numpy()) < 1e-12
         assert rel_err(mu[c].cpu().numpy(), mu1[0].cpu().numpy()) < 1e-14
+
+
+# ------------------------------------------------------------------------------------ SURVEY 8f "next": CRPS / similarity weights
+def test_crps_weights_vs_oracle(backend):
+    rng = np.random.default_rng(3)
+    C, M, Ro, N = 2, 5, 3, 57
+    loc = rng.normal(size=(C, M, N))
+    var = rng.uniform(0.01, 0.5, size=(C, M, N))  # passed as the SCALE (quirk Q-SCALE)
+    obs = rng.normal(size=(C, Ro, N))
+    w, cm = backend.crps_weights(_t(backend, loc), _t(backend, var), _t(backend, obs), want_crps=True)
+    for c in range(C):
+        wo, co = rp.crps_weights(loc[c], var[c], obs[c])
+        assert rel_err(cm[c].cpu().numpy(), co) < 1e-13
+        assert rel_err(w[c].cpu().numpy(), wo) < 1e-12
+        assert np.abs(w[c].cpu().numpy().sum(axis=0) - 1.0).max() < 1e-12
+
+
+def test_similarity_weights_vs_oracle(backend):
+    mus, covs = _posterior_covs(4, 5, 30, seed=17)
+    M = 4
+    # mode "single": M*M full-covariance W2 distances, nanmean, normalise
+    ii, jj = np.divmod(np.arange(M * M), M)
+    w2, info = backend.w2_distance(_t(backend, mus[ii]), _t(backend, covs[ii]), _t(backend, mus[jj]), _t(backend, covs[jj]))
+    w = backend.w2_collapse(w2.reshape(1, M, M, 1))[0, :, 0].cpu().numpy()
+    wo, w2o = rp.model_similarity_weights_single(mus, covs)
+    assert np.abs(w2.cpu().numpy().reshape(M, M) - w2o).max() < 1e-9
+    assert rel_err(w, wo) < 1e-9
+    # mode "temporal": 1-D W2 per time step with variance**2 (dx.Normal(mean, variance))
+    var = np.asarray([np.diag(c) for c in covs])
+    wt, w2t = backend.similarity_weights_pointwise(_t(backend, mus[None]), _t(backend, (var * var)[None]), want_w2=True)
+    wto, w2to = rp.model_similarity_weights_temporal(mus, var)
+    assert np.abs(w2t[0].cpu().numpy() - w2to).max() < 1e-13
+    assert rel_err(wt[0].cpu().numpy(), wto) < 1e-12
+    # NaN distances are skipped by the nanmean
+    d = np.arange(1.0, 1.0 + M * M * 3).reshape(1, M, M, 3)
+    d[0, 1, 2, 0] = np.nan
+    got = backend.w2_collapse(_t(backend, d))[0].cpu().numpy()
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        m = np.nanmean(d[0], axis=1)
+    assert rel_err(got, m / m.sum(axis=0)) < 1e-14
+
+
+def test_reference_weight_classes_shapes_and_sums(backend):
+    """The reference's own weight test (tests/test_weights.py:71-101): every weight class returns a
+    labelled array of shape (M,) + obs.mean('realisation').shape that sums to 1 over models."""
+    import bayesian_ensembling_b200 as es
+    from bayesian_ensembling_b200.labelled import DataArray
+
+    M, R, T, Ro = 5, 3, 24, 2
+    reals, obs = _cell(M, R, T, Ro, seed=31, monthly=True)
+    time = np.arange(T)
+    pms = [es.ProcessModel(DataArray(reals[m], ("realisation", "time"),
+                                     {"realisation": np.arange(R), "time": time}), f"model{m}") for m in range(M)]
+    obs_pm = es.ProcessModel(DataArray(obs, ("realisation", "time"), {"realisation": np.arange(Ro), "time": time}), "obs")
+    mc = es.ModelCollection(pms)
+    mc.fit(es.GPDTW1D(), compile_objective=True, n_optim_nits=2, progress_bar=False)
+    mus = np.stack([m.distribution._dist.mean() for m in mc])
+    covs = np.stack([m.distribution._dist.covariance() for m in mc])
+    var = np.stack([m.distribution._dist.variance() for m in mc])
+    for cls, kwargs in ((es.InverseSquareWeight, {}), (es.UniformWeight, {}), (es.CRPSWeight, {}),
+                        (es.ModelSimilarityWeight, {"mode": "temporal"})):
+        w = cls()(mc, obs_pm, **kwargs)
+        assert w.shape == (M, T), cls
+        assert np.abs(np.nansum(w.values, axis=0) - 1.0).max() < 1e-6, cls
+    wc = es.CRPSWeight()(mc, obs_pm).values
+    assert rel_err(wc, rp.crps_weights(mus, var, obs)[0]) < 1e-10
+    ws = es.ModelSimilarityWeight()(mc, mode="temporal").values
+    assert rel_err(ws, rp.model_similarity_weights_temporal(mus, var)[0]) < 1e-10
+    w1 = es.ModelSimilarityWeight()(mc, mode="single")
+    assert w1.shape == (M, 1) and w1.dims == ("model", "time")
+    assert rel_err(w1.values[:, 0], rp.model_similarity_weights_single(mus, covs)[0]) < 1e-8
+    wi = es.InverseSquareWeight()(mc, obs_pm).values
+    assert rel_err(wi, rp.inverse_square_weights(reals.mean(axis=1), obs.mean(axis=0))) < 1e-12
+    with pytest.raises(ValueError):
+        es.ModelSimilarityWeight()(mc, mode="nope")

@@ -183,3 +183,36 @@ def test_fullcov_barycentre_commuting_case():
     want = (0.5 * np.sqrt(d1) + 0.5 * np.sqrt(d2)) ** 2
     assert np.allclose(np.diag(S), want, rtol=1e-4)
     assert np.abs(S - np.diag(np.diag(S))).max() < 1e-12
+
+
+def test_crps_gaussian_known_answers():
+    """properscoring.crps_gaussian closed form: CRPS of N(0,1) at its mean is (sqrt2 - 1)/sqrt(pi);
+    against the defining integral int (F(y) - 1{y >= x})^2 dy elsewhere."""
+    import math
+
+    from scipy import integrate, special
+
+    assert abs(rp.crps_gaussian(0.0, 0.0, 1.0) - (math.sqrt(2.0) - 1.0) / math.sqrt(math.pi)) < 1e-15
+    for x, mu, s in ((0.7, 0.2, 1.3), (-2.0, 1.0, 0.4)):
+        f = lambda y: (special.ndtr((y - mu) / s) - (y >= x)) ** 2  # noqa: E731
+        want = integrate.quad(f, -40, x)[0] + integrate.quad(f, x, 40)[0]
+        assert abs(rp.crps_gaussian(x, mu, s) - want) < 1e-9
+
+
+def test_next_row_weights_normalise_over_models():
+    rng = np.random.default_rng(11)
+    M, T, Ro = 4, 9, 3
+    means, var, obs = rng.normal(size=(M, T)), rng.uniform(0.1, 1.0, (M, T)), rng.normal(size=(Ro, T))
+    for w in (rp.crps_weights(means, var, obs)[0], rp.model_similarity_weights_temporal(means, var)[0],
+              rp.inverse_square_weights(means, obs.mean(axis=0))):
+        assert w.shape == (M, T) and np.abs(w.sum(axis=0) - 1.0).max() < 1e-12
+    # temporal similarity: identical members are at distance 0 of each other, so a duplicated member pair
+    # gets a smaller raw mean distance than the odd one out
+    means2 = np.stack([means[0], means[0], means[1]])
+    var2 = np.stack([var[0], var[0], var[1]])
+    w, w2 = rp.model_similarity_weights_temporal(means2, var2)
+    assert np.abs(w2[0, 1]).max() < 1e-15 and (w[2] > w[0]).all()
+    # single mode reduces to the pairwise a8 distances
+    S = [np.diag(v) for v in var]
+    ws, d = rp.model_similarity_weights_single(list(means), S)
+    assert abs(ws.sum() - 1.0) < 1e-12 and np.abs(np.diag(d)).max() < 1e-12

@@ -326,7 +326,9 @@ def run_ours(args, cfg):
         p = prof[top]
         traffic = None
         try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(top)
+            # measured once with ncu (dram__bytes_read.sum + dram__bytes_write.sum, averaged per launch of this
+            # kernel over one step of this workload): tools/gpu_traffic.sh -> profiles/traffic.json
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))["bytes_per_launch"].get(top)
         except Exception:
             pass
         if top in TENSOR_FAMILIES:

@@ -158,6 +158,13 @@ class ModelCollection:
             dist = model.fit(process_model, **kwargs)
             process_model.distribution = dist
 
+    def save(self, path: str):
+        """ensembles/data.py:397-404, as a library-independent ``.npz`` instead of a pickle of
+        xarray / distrax objects; reload with ``utils.load_model_collection(path)``."""
+        from .checkpoint import save_model_collection
+
+        save_model_collection(self, path)
+
     @property
     def time(self):
         return self.models[0].time

@@ -618,3 +618,75 @@ def test_reference_weight_classes_shapes_and_sums(backend):
     assert rel_err(wi, rp.inverse_square_weights(reals.mean(axis=1), obs.mean(axis=0))) < 1e-12
     with pytest.raises(ValueError):
         es.ModelSimilarityWeight()(mc, mode="nope")
+
+
+# ------------------------------------------------------------------------------------ checkpoints
+def test_model_collection_npz_round_trip(backend, tmp_path):
+    import bayesian_ensembling_b200 as es
+    from bayesian_ensembling_b200 import utils
+    from bayesian_ensembling_b200.labelled import DataArray
+
+    M, R, T = 3, 3, 30
+    reals, obs = _cell(M, R, T, 2, seed=41)
+    time = 1850 + np.arange(T)
+    pms = [es.ProcessModel(DataArray(reals[m], ("realisation", "time"), {"realisation": np.arange(R), "time": time}),
+                           f"model{m}") for m in range(M)]
+    mc = es.ModelCollection(pms)
+    mc.fit(es.GPDTW1D(hyperparameters=(0.5, 6.0)), progress_bar=False)
+    path = str(tmp_path / "mc.npz")
+    mc.save(path)
+    mc2 = utils.load_model_collection(path)
+    assert mc2.model_names == mc.model_names
+    for a, b in zip(mc, mc2):
+        assert np.array_equal(a.model_data.values, b.model_data.values)
+        assert np.array_equal(a.time.values, b.time.values)
+        assert np.array_equal(a.distribution._dist.mean(), b.distribution._dist.mean())
+        assert np.array_equal(a.distribution._dist.covariance(), b.distribution._dist.covariance())
+        assert rel_err(b.distribution._dist.scale_tri, a.distribution._dist.scale_tri) < 1e-13
+    obs_pm = es.ProcessModel(DataArray(obs, ("realisation", "time"), {"realisation": np.arange(2), "time": time}), "obs")
+    w1, w2 = es.LogLikelihoodWeight()(mc, obs_pm), es.LogLikelihoodWeight()(mc2, obs_pm)
+    _nan_equal_close(w2.values, w1.values, 1e-10, "weights after reload")
+
+
+def test_golden_members_through_checkpoint_loader(backend, golden_members, tmp_path):
+    """The reference's fitted members (tests/golden) written in the reference's pickle LAYOUT and read
+    back by load_reference_pickle: posteriors are rebuilt on the device (data.py:38-39 -> be_mvn_from_cov)."""
+    import pickle
+    import sys
+    import types
+
+    from bayesian_ensembling_b200 import utils
+
+    # a throw-away module tree that pickles with the same shape as the reference's objects
+    mod = types.ModuleType("fake_ensembles_data")
+    for name in ("ModelCollection", "ProcessModel", "Distribution", "DataArray", "Variable", "MVN"):
+        setattr(mod, name, type(name, (), {"__module__": "fake_ensembles_data"}))
+    sys.modules["fake_ensembles_data"] = mod
+    try:
+        members = golden_members[:2]
+        pms = []
+        for g in members:
+            var = mod.Variable()
+            var.__dict__.update(_dims=("realisation", "time"), _data=g.realisations)
+            da = mod.DataArray()
+            da.__dict__.update(_name="tas", _variable=var)
+            inner = mod.MVN()
+            inner.__dict__.update(_loc=g.mu, _covariance_matrix=g.cov, _scale_tri=g.scale_tri)
+            dist = mod.Distribution()
+            dist.__dict__.update(mu=g.mu, covariance=g.cov, _dist=inner)
+            pm = mod.ProcessModel()
+            pm.__dict__.update(model_data=da, model_name=g.name, idx=0, _distribution=dist)
+            pms.append(pm)
+        mc = mod.ModelCollection()
+        mc.__dict__.update(models=pms, idx=0)
+        path = str(tmp_path / "ref_layout.pkl")
+        with open(path, "wb") as f:
+            pickle.dump(mc, f, protocol=4)
+    finally:
+        del sys.modules["fake_ensembles_data"]
+    loaded = utils.load_reference_pickle(path)
+    for pm, g in zip(loaded, members):
+        assert pm.model_name == g.name
+        assert np.array_equal(pm.model_data.values, g.realisations)
+        assert rel_err(pm.distribution._dist.scale_tri, g.scale_tri) < 1e-12  # pinned by the reference's own factor
+        assert np.array_equal(pm.distribution._dist.mean(), g.mu)

@@ -115,10 +115,22 @@ def _blas_threads():
         return os.cpu_count() or 1, "?"
 
 
+def _use_all_host_threads():
+    """torchrun exports OMP_NUM_THREADS=1 to every rank; the CPU arm is meant to use all host cores."""
+    try:
+        from threadpoolctl import threadpool_limits
+
+        threadpool_limits(limits=os.cpu_count() or 1, user_api="blas")
+    except Exception:
+        pass
+
+
 def cpu_sample_seconds(cfg, members, repeats=1):
     """Oracle fit -> weight -> barycentre on ``members`` members of cell 0 (bounded sample)."""
     from bayesian_ensembling_b200 import synthetic
     from oracle import reference_path as rp
+
+    _use_all_host_threads()
 
     reals, obs = synthetic.make_cells(cfg, n_cells=1)
     best = float("inf")
@@ -133,6 +145,7 @@ def run_reference(args, cfg):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    _use_all_host_threads()
     threads, blas = _blas_threads()
     m = args.cpu_members
     for _ in range(args.warmup):
@@ -225,6 +238,7 @@ def run_ours(args, cfg):
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
     torch.cuda.set_device(local)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     be = Backend.get()
     dev = be.device
@@ -380,6 +394,7 @@ def run_ours(args, cfg):
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        _use_all_host_threads()
         threads, blas = _blas_threads()
         m = args.cpu_members
         dt = cpu_sample_seconds(cfg, m)

@@ -690,3 +690,25 @@ def test_golden_members_through_checkpoint_loader(backend, golden_members, tmp_p
         assert np.array_equal(pm.model_data.values, g.realisations)
         assert rel_err(pm.distribution._dist.scale_tri, g.scale_tri) < 1e-12  # pinned by the reference's own factor
         assert np.array_equal(pm.distribution._dist.mean(), g.mu)
+
+
+def test_cfg5_properties_at_size(backend):
+    """BASELINE config 5 shape at T=515 (the oracle's SVD-based fixed point takes minutes at 3012; the
+    full size is run by tools/run_cfg5.py -> profiles/): with degC-anomaly covariances the signed stop
+    rule exits at iteration 0, where S = sum_m w_m sqrtm(Sigma_m) exactly; S is symmetric positive
+    definite; one member is checked against the SVD oracle."""
+    import torch
+
+    M, T = 4, 515
+    mus, covs = _posterior_covs(M, 5, T, seed=55)
+    w = np.array([0.1, 0.2, 0.3, 0.4])
+    mu, S, iters, info = backend.barycentre_fullcov(_t(backend, mus[None]), _t(backend, covs[None]), _t(backend, w[None]))
+    assert iters[0] == 0 and int(info.abs().sum()) == 0
+    roots, _, _, _ = backend.sqrtm_psd(_t(backend, covs))
+    want = (roots * _t(backend, w)[:, None, None]).sum(0)
+    assert ((S[0] - want).abs().max() / want.abs().max()).item() < 1e-14
+    assert torch.equal(S[0], S[0].T)
+    _, pd = backend.potrf(S)
+    assert int(pd.item()) == 0
+    assert rel_err(roots[0].cpu().numpy(), rp.sqrtm_svd(covs[0])) < 1e-9
+    assert rel_err(mu[0].cpu().numpy(), (w[:, None] * mus).sum(0)) < 1e-13

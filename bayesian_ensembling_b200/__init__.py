@@ -2,6 +2,7 @@
 
 Mirrors the reference's public names (ensembles/__init__.py:1-6) for the path in scope."""
 from .data import Distribution, ModelCollection, ProcessModel  # noqa: F401
+from .dtw import dtw_barycenter_averaging_subgradient, performDBA  # noqa: F401
 from .ensemble_scheme import Barycentre  # noqa: F401
 from .labelled import DataArray  # noqa: F401
 from .models import GPDTW1D  # noqa: F401

@@ -67,6 +67,10 @@ SIGNATURES = {
     "be_crps_weights": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _P, _P]),
     "be_w2_collapse": (_I, [_P, _P, _I, _I, _I, _P]),
     "be_similarity_weights_pointwise": (_I, [_P, _P, _P, _I, _I, _I, _P, _P]),
+    "be_dtw_dba_workspace_bytes": (_Z, [_I, _I, _I]),
+    "be_dtw_barycenter_averaging_subgradient": (_I, [_P, _P, _I, _I, _I, _I, _D, _D, _D, _P, _P, _P, _P, _P, _Z]),
+    "be_perform_dba": (_I, [_P, _P, _I, _I, _I, _I, _P, _P, _P, _Z]),
+    "be_dtw_squared": (_I, [_P, _P, _P, _I, _I, _P]),
     "be_barycentre_fullcov": (_I, [_P, _P, _P, _P, _I, _I, _I, _D, _D, _I, _D, _I, _P, _P, _P, _P, _P, _Z]),
 }
 

@@ -402,6 +402,54 @@ class Backend:
         _lib.check(self.ctx, rc, "be_barycentre_fullcov")
         return mu, S, list(iters), info
 
+    # ------------------------------------------------------------------ SURVEY 8f "next" row 1: DTW barycentre averaging
+    def dtw_barycenter_averaging_subgradient(self, reals, max_iter=30, initial_step_size=0.05, final_step_size=0.005,
+                                             tol=1e-5, init_barycenter=None, want_info=False):
+        """reals [B,R,T] -> barycentre [B,T] (tslearn semantics; models.py:176-178 passes max_iter=50, tol=1e-3)"""
+        reals = self._in(reals)
+        B, R, T = reals.shape
+        init = None if init_barycenter is None else self._in(init_barycenter, (B, T), "init_barycenter")
+        bary = self._new(B, T)
+        n_iter = self._new(B, dtype=torch.int32)
+        cost = self._new(B)
+        nbytes = int(self.lib.be_dtw_dba_workspace_bytes(B, R, T))
+        if nbytes == 0:
+            raise ValueError(f"dtw_barycenter_averaging_subgradient: unsupported shape B={B} R={R} T={T} (T <= 4096)")
+        ws = self._ws(nbytes)
+        self._sync_stream()
+        rc = self.lib.be_dtw_barycenter_averaging_subgradient(
+            self.ctx, _ptr(reals), B, R, T, int(max_iter), float(initial_step_size), float(final_step_size),
+            float(tol), _ptr(init), _ptr(bary), _ptr(n_iter), _ptr(cost), _ptr(ws), nbytes)
+        _lib.check(self.ctx, rc, "be_dtw_barycenter_averaging_subgradient")
+        return (bary, n_iter, cost) if want_info else bary
+
+    def perform_dba(self, reals, n_iterations=10, want_medoid=False):
+        """reals [B,R,T] -> centre [B,T] (ensembles/dtwa.py:6-20)"""
+        reals = self._in(reals)
+        B, R, T = reals.shape
+        center = self._new(B, T)
+        medoid = self._new(B, dtype=torch.int32)
+        nbytes = int(self.lib.be_dtw_dba_workspace_bytes(B, R, T))
+        if nbytes == 0:
+            raise ValueError(f"perform_dba: unsupported shape B={B} R={R} T={T} (T <= 4096)")
+        ws = self._ws(nbytes)
+        self._sync_stream()
+        rc = self.lib.be_perform_dba(self.ctx, _ptr(reals), B, R, T, int(n_iterations), _ptr(center), _ptr(medoid),
+                                     _ptr(ws), nbytes)
+        _lib.check(self.ctx, rc, "be_perform_dba")
+        return (center, medoid) if want_medoid else center
+
+    def dtw_squared(self, a, x):
+        """a, x [P,T] -> squared DTW distance of each pair [P] (ensembles/dtwa.py:48-75)"""
+        a = self._in(a)
+        P, T = a.shape
+        x = self._in(x, (P, T), "x")
+        out = self._new(P)
+        self._sync_stream()
+        rc = self.lib.be_dtw_squared(self.ctx, _ptr(a), _ptr(x), P, T, _ptr(out))
+        _lib.check(self.ctx, rc, "be_dtw_squared")
+        return out
+
     # ------------------------------------------------------------------ SURVEY 8f "next": CRPS / similarity weights
     def crps_weights(self, loc, scale, obs, want_crps=False):
         """loc/scale [C,M,N], obs [C,Ro,N] -> weights [C,M,N] (+ crps_mean) (weights.py:444-515)"""

@@ -10,18 +10,19 @@
 #include "vgp_kernels.cuh"
 #include "sqrtm_kernels.cuh"
 #include "weights_next_kernels.cuh"
+#include "dtw_kernels.cuh"
 
 using namespace be;
 
 // kernel families of the profiler (be_ctx_profile_*): one per kernel of be_kernels.cuh
 enum Family {
     F_INPUTS = 0, F_GRAM, F_DIAG, F_PANEL, F_SYRK, F_TRTRI, F_LAUUM, F_MEAN, F_STATS, F_COPY, F_WEIGHTS, F_BARY,
-    F_GEMM, F_VGP_MISC, F_SQRTM_MISC, F_COUNT
+    F_GEMM, F_VGP_MISC, F_SQRTM_MISC, F_DTW_DP, F_DTW_BACK, F_DBA_UPDATE, F_COUNT
 };
 static const char* const kFamilyName[F_COUNT] = {
     "k_gpdtw1d_inputs", "k_matern32", "k_diag_block", "k_panel_scale", "k_chol_update", "k_trtri_accum",
     "k_lauum_cov", "k_posterior_mean", "k_mvn_stats", "copy/pad", "k_loglik_weights", "k_barycentre",
-    "k_gemm_nt", "vgp elementwise", "sqrtm elementwise"};
+    "k_gemm_nt", "vgp elementwise", "sqrtm elementwise", "k_dtw_dp", "k_dtw_backtrack", "k_dba_update"};
 
 struct ProfRecord {
     int family;
@@ -908,3 +909,4 @@ int be_vgp_fit(be_ctx* ctx, const double* X, const double* y_mean, const double*
 }  // extern "C"
 
 #include "be_w2_api.cuh"
+#include "be_dtw_api.cuh"

@@ -1,0 +1,283 @@
+// DTW barycentre averaging on the device (the step that produces y_mean,
+// ensembles/models.py:176-178 via tslearn, and the reference's own ensembles/dtwa.py).
+//
+// The DTW table cost[i,j] = (a_i - x_j)^2 + min(cost[i-1,j-1], cost[i-1,j], cost[i,j-1]) is filled as a
+// systolic wavefront: thread t owns the W columns [tW, tW+W) and works on row i = s - t at step s,
+// so the only communication is "my last column of this row" to thread t+1 (a warp shuffle; one
+// shared-memory slot per warp boundary and one barrier per step when a pair needs more than a
+// warp).  Rows of the previous step live in registers.  Each thread records its W 2-bit argmin
+// codes per step in ONE word, laid out step-major ([step][thread]) so that a step's stores are
+// coalesced; the backtrack kernel maps (i, j) -> word (i + j/W, j/W).
+//
+// Every product and sum is an explicit round-to-nearest intrinsic (no FMA contraction): the
+// path is a discrete function of the table, so the table must round exactly as the CPU oracle
+// (oracle/dba.c, -ffp-contract=off) and the NumPy/numba code it restates.
+#pragma once
+#include <stdint.h>
+
+namespace be {
+
+constexpr int DTW_TIE_TSLEARN = 0;  // argmin([diag, top, left]), first minimum wins (tslearn _return_path)
+constexpr int DTW_TIE_DTWA = 1;     // ensembles/dtwa.py:113-129
+
+template <int W> struct DtwWord { typedef uint32_t type; };
+template <> struct DtwWord<1> { typedef uint8_t type; };
+template <> struct DtwWord<2> { typedef uint8_t type; };
+template <> struct DtwWord<4> { typedef uint8_t type; };
+template <> struct DtwWord<8> { typedef uint16_t type; };
+
+__host__ __device__ inline int dtw_threads_used(int T, int W) { return (T + W - 1) / W; }
+__host__ __device__ inline int dtw_steps(int T, int W) { return T + dtw_threads_used(T, W) - 1; }
+
+// One pair = (row sequence a = A[pair / R], column sequence x = X[(pair / x_group) * R + pair % R]).
+// NWARPS == 1: one warp per pair, 4 pairs per 128-thread CTA, shuffles only.
+// NWARPS  > 1: one CTA of NWARPS warps per pair.
+template <int W, int NWARPS, int TIE, bool DIRS>
+__global__ void __launch_bounds__(NWARPS == 1 ? 128 : NWARPS * 32)
+k_dtw_dp(const double* __restrict__ A, const double* __restrict__ X, int T, int R, int x_group, int n_pairs,
+         const int* __restrict__ active, typename DtwWord<W>::type* __restrict__ dirs, size_t dirs_stride,
+         double* __restrict__ sqcost) {
+    typedef typename DtwWord<W>::type word_t;
+    constexpr int NT = NWARPS * 32;
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    int pair, t;
+    if (NWARPS == 1) {
+        pair = blockIdx.x * 4 + warp;
+        t = lane;
+        if (pair >= n_pairs) return;
+    } else {
+        pair = blockIdx.x;
+        t = threadIdx.x;
+    }
+    if (active && !active[pair / R]) return;  // uniform over the threads that share barriers
+    const double* a = A + (size_t)(pair / R) * T;
+    const double* x = X + ((size_t)(pair / x_group) * R + pair % R) * T;
+    const int nthr = dtw_threads_used(T, W);
+    const int steps = T + nthr - 1;
+    const int j0 = t * W;
+    const double INF = __longlong_as_double(0x7ff0000000000000LL);
+    double xj[W], up[W];
+#pragma unroll
+    for (int k = 0; k < W; ++k) {
+        xj[k] = (j0 + k < T) ? x[j0 + k] : 0.0;
+        up[k] = INF;
+    }
+    double diag_in = (t == 0) ? 0.0 : INF;  // cost[-1,-1] = 0 (tslearn's border; dtwa.py:53 cost[0,0] = delta[0,0])
+    double out = INF;
+    double a_cur = (t == 0) ? a[0] : 0.0;
+    word_t* drow = DIRS ? dirs + (size_t)pair * dirs_stride + t : nullptr;
+    __shared__ double edge[2][NWARPS > 1 ? NWARPS : 1];
+    for (int s = 0; s < steps; ++s) {
+        double in = __shfl_up_sync(0xffffffffu, out, 1);
+        if (NWARPS > 1) {
+            if (lane == 0 && warp > 0) in = edge[(s & 1) ^ 1][warp - 1];
+        }
+        if (t == 0) in = INF;
+        const int i = s - t;
+        if (i >= 0 && i < T && t < nthr) {
+            const double ai = a_cur;
+            double left = in, diag = diag_in;
+            unsigned codes = 0;
+#pragma unroll
+            for (int k = 0; k < W; ++k) {
+                const double diff = __dsub_rn(ai, xj[k]);
+                const double d = __dmul_rn(diff, diff);
+                const double top = up[k];
+                double m;
+                unsigned code;
+                if (TIE == DTW_TIE_TSLEARN) {
+                    m = diag; code = 0;
+                    if (top < m) { m = top; code = 1; }
+                    if (left < m) { m = left; code = 2; }
+                } else {
+                    if (diag <= left) {
+                        if (diag <= top) { m = diag; code = 0; } else { m = top; code = 1; }
+                    } else {
+                        if (left <= top) { m = left; code = 2; } else { m = top; code = 1; }
+                    }
+                }
+                const double cur = __dadd_rn(m, d);
+                diag = top;
+                up[k] = cur;
+                left = cur;
+                codes |= code << (2 * k);
+            }
+            out = left;
+            diag_in = in;
+            if (DIRS) drow[(size_t)s * NT] = (word_t)codes;
+            if (i == T - 1 && t == nthr - 1) {
+                const int kl = (T - 1) - j0;
+                double fin = 0.0;
+#pragma unroll
+                for (int k = 0; k < W; ++k)
+                    if (k == kl) fin = up[k];
+                sqcost[pair] = fin;
+            }
+        }
+        const int in1 = i + 1;
+        a_cur = (in1 >= 0 && in1 < T) ? __ldg(a + in1) : 0.0;
+        if (NWARPS > 1) {
+            if (lane == 31) edge[s & 1][warp] = out;
+            __syncthreads();
+        }
+    }
+}
+
+// Walks the optimal path of one pair back from (T-1, T-1) (tslearn _return_path; dtwa.py:131-139).
+// One warp per pair: the lanes fetch the direction words of 32 rows x 2 column strips around the
+// current cell in one coalesced-ish gather, then the warp walks inside that window with shuffles.
+// v[pair, i] = number of path cells in row i, wx[pair, i] = sum of x_j over them in walk order
+// (j decreasing) -- the summation order oracle/dba.c defines.
+template <int W, int NWARPS>
+__global__ void __launch_bounds__(128)
+k_dtw_backtrack(const double* __restrict__ X, int T, int R, int n_pairs, const int* __restrict__ active,
+                const typename DtwWord<W>::type* __restrict__ dirs, size_t dirs_stride, double* __restrict__ v,
+                double* __restrict__ wx) {
+    typedef typename DtwWord<W>::type word_t;
+    constexpr int NT = NWARPS * 32;
+    const int lane = threadIdx.x & 31;
+    const int pair = blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (pair >= n_pairs) return;
+    if (active && !active[pair / R]) return;
+    const double* x = X + (size_t)pair * T;
+    const word_t* d = dirs + (size_t)pair * dirs_stride;
+    double* vo = v + (size_t)pair * T;
+    double* wo = wx + (size_t)pair * T;
+    int i = T - 1, j = T - 1;
+    double acc = 0.0, cnt = 0.0;
+    for (;;) {
+        const int i0 = i, t0 = j / W;
+        const int row = i0 - lane;
+        unsigned wA = 0, wB = 0;
+        if (row >= 0) {
+            wA = d[(size_t)(row + t0) * NT + t0];
+            if (t0 > 0) wB = d[(size_t)(row + t0 - 1) * NT + (t0 - 1)];
+        }
+        bool done = false;
+        for (;;) {
+            cnt += 1.0;
+            acc = __dadd_rn(acc, x[j]);
+            if (i == 0 && j == 0) { done = true; break; }
+            const int t = j / W;
+            const unsigned word = __shfl_sync(0xffffffffu, (t == t0) ? wA : wB, i0 - i);
+            const unsigned code = (word >> (2 * (j - t * W))) & 3u;
+            const int ni = i - (code != 2u), nj = j - (code != 1u);
+            if (ni != i) {
+                if (lane == 0) { vo[i] = cnt; wo[i] = acc; }
+                cnt = 0.0;
+                acc = 0.0;
+            }
+            i = ni;
+            j = nj;
+            if (i0 - i >= 32 || j / W < t0 - 1) break;
+        }
+        if (done) {
+            if (lane == 0) { vo[0] = cnt; wo[0] = acc; }
+            break;
+        }
+    }
+}
+
+// tslearn _subgradient_update_barycenter + the loop tail of dtw_barycenter_averaging_subgradient:
+//   delta = sum_k (v_k * c - wx_k)  (k increasing, "+= v_k c" then "-= wx_k");  c -= (2 eta / R) delta;
+//   cost = sum_k sqrt(sq_k)^2 / R;  |cost_prev - cost| < tol -> stop;  cost_prev < cost -> keep cost_prev
+//   (tslearn only warns);  else cost_prev = cost.
+// One CTA per problem. state[b]: active flag; n_active: device counter the host polls.
+__global__ void k_dba_subgradient_update(double* __restrict__ bary, const double* __restrict__ v,
+                                         const double* __restrict__ wx, const double* __restrict__ sqcost, int T, int R,
+                                         double step, double tol, int* __restrict__ active,
+                                         double* __restrict__ cost_prev, double* __restrict__ cost_last,
+                                         int* __restrict__ n_iter, int* __restrict__ n_active) {
+    const int b = blockIdx.x;
+    if (!active[b]) return;
+    double* c = bary + (size_t)b * T;
+    const double* vb = v + (size_t)b * R * T;
+    const double* wb = wx + (size_t)b * R * T;
+    for (int i = threadIdx.x; i < T; i += blockDim.x) {
+        const double ci = c[i];
+        double delta = 0.0;
+        for (int k = 0; k < R; ++k) {
+            delta = __dadd_rn(delta, __dmul_rn(vb[(size_t)k * T + i], ci));
+            delta = __dsub_rn(delta, wb[(size_t)k * T + i]);
+        }
+        c[i] = __dsub_rn(ci, __dmul_rn(step, delta));
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double cost = 0.0;
+        for (int k = 0; k < R; ++k) {
+            const double dist = sqrt(sqcost[(size_t)b * R + k]);
+            cost = __dadd_rn(cost, __dmul_rn(dist, dist));
+        }
+        cost = cost / (double)R;
+        n_iter[b] += 1;
+        cost_last[b] = cost;
+        const double prev = cost_prev[b];
+        if (fabs(prev - cost) < tol) {
+            active[b] = 0;
+            atomicSub(n_active, 1);
+        } else if (prev < cost) {
+        } else {
+            cost_prev[b] = cost;
+        }
+    }
+}
+
+// ensembles/dtwa.py:23-37: ss[c] = sum_k squared_DTW(series_c, series_k) (sequential from 0), first
+// strict minimum wins; centre := series[medoid] (dtwa.py:15).  sq [B, R, R].  One CTA per problem.
+__global__ void k_dba_medoid(const double* __restrict__ X, const double* __restrict__ sq, int T, int R,
+                             double* __restrict__ center, int* __restrict__ medoid) {
+    const int b = blockIdx.x;
+    __shared__ int best_c;
+    if (threadIdx.x == 0) {
+        int m = -1;
+        double best = 1e20;
+        for (int c = 0; c < R; ++c) {
+            double ss = 0.0;
+            for (int k = 0; k < R; ++k) ss = __dadd_rn(ss, sq[((size_t)b * R + c) * R + k]);
+            if (m == -1 || ss < best) { best = ss; m = c; }
+        }
+        best_c = m;
+        if (medoid) medoid[b] = m;
+    }
+    __syncthreads();
+    const double* src = X + ((size_t)b * R + best_c) * T;
+    for (int i = threadIdx.x; i < T; i += blockDim.x) center[(size_t)b * T + i] = src[i];
+}
+
+// ensembles/dtwa.py:141: centre = updated_center / n_elements (sums grouped per series, k increasing)
+__global__ void k_dba_mean_update(double* __restrict__ center, const double* __restrict__ v,
+                                  const double* __restrict__ wx, int B, int T, int R) {
+    const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= (size_t)B * T) return;
+    const int b = (int)(gid / T), i = (int)(gid % T);
+    double s = 0.0, n = 0.0;
+    for (int k = 0; k < R; ++k) {
+        s = __dadd_rn(s, wx[((size_t)b * R + k) * T + i]);
+        n = __dadd_rn(n, v[((size_t)b * R + k) * T + i]);
+    }
+    center[gid] = s / n;
+}
+
+// _init_avg (tslearn dba.py): the mean over series when barycenter_size == T
+__global__ void k_dba_init_mean(const double* __restrict__ X, int B, int R, int T, double* __restrict__ bary) {
+    const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= (size_t)B * T) return;
+    const int b = (int)(gid / T), i = (int)(gid % T);
+    double s = 0.0;
+    for (int k = 0; k < R; ++k) s = __dadd_rn(s, X[((size_t)b * R + k) * T + i]);
+    bary[gid] = s / (double)R;
+}
+
+__global__ void k_dba_state_init(int B, int* active, double* cost_prev, double* cost_last, int* n_iter, int* n_active) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b == 0) *n_active = B;
+    if (b >= B) return;
+    active[b] = 1;
+    cost_prev[b] = __longlong_as_double(0x7ff0000000000000LL);
+    cost_last[b] = __longlong_as_double(0x7ff0000000000000LL);
+    n_iter[b] = 0;
+}
+
+}  // namespace be

@@ -60,12 +60,14 @@ def wave_size(be: Backend, C: int, M: int, R: int, T: int, keep_posteriors: bool
 
 def fit_weight_barycentre(realisations, observations, variance, lengthscale, *, jitter=DEFAULT_JITTER,
                           standardisation_constant=1.0, time_mean_weights=False, keep_posteriors=False,
-                          cells_per_wave=None, tolerance=1e-6, init_var=1.0) -> CellBatchResult:
+                          cells_per_wave=None, tolerance=1e-6, init_var=1.0, y_mean="mean") -> CellBatchResult:
     """realisations [C,M,R,T], observations [C,Ro,T] (host arrays or device tensors);
     variance / lengthscale: scalar, [M] or [C,M] kernel hyper-parameters (fixed-theta posterior,
     the fixed point of models.py:208-215).  Order of operations follows
     ``PerfectModelTest._run_single_test`` (utils.py:102-135); ``time_mean_weights`` reproduces
-    utils.py:111,133 (NaN-skipping mean over time, broadcast back)."""
+    utils.py:111,133 (NaN-skipping mean over time, broadcast back).  ``y_mean``: "mean" = arithmetic
+    mean over realisations (the y_mean-given path BASELINE's metric is quoted on), "dba" = the DTW
+    barycentre average of models.py:176-178 computed on the device, or a [C,M,T] array."""
     be = Backend.get()
     r = be._in(realisations)
     o = be._in(observations)
@@ -80,6 +82,13 @@ def fit_weight_barycentre(realisations, observations, variance, lengthscale, *, 
         c1 = min(C, c0 + cells_per_wave)
         Cw = c1 - c0
         X, ym, yv = be.gpdtw1d_inputs(r[c0:c1].reshape(Cw * M, R, T))
+        if isinstance(y_mean, str):
+            if y_mean == "dba":
+                ym = be.dtw_barycenter_averaging_subgradient(r[c0:c1].reshape(Cw * M, R, T), max_iter=50, tol=1e-3)
+            elif y_mean != "mean":
+                raise ValueError(f"y_mean must be 'mean', 'dba' or an array, got {y_mean!r}")
+        else:
+            ym = be._in(y_mean, (C, M, T), "y_mean")[c0:c1].reshape(Cw * M, T)
         post = be.gp_posterior(X, ym, yv, var[c0 * M:c1 * M], ls[c0 * M:c1 * M], jitter,
                                want_cov=keep_posteriors, want_scale_tri=keep_posteriors)
         w = be.loglik_weights_mvn(post.mvn_stats, o[c0:c1], M, standardisation_constant)

@@ -2,9 +2,11 @@
 same public signature, computed on the GPU through the C ABI.
 
 Differences that are stated, not hidden:
-* the DTW-barycentre-averaging mean (models.py:176-178, tslearn, unseeded) is OUTSIDE the hot
-  path: ``y_mean`` defaults to the arithmetic mean over realisations
-  (tslearn's DBA initialiser) and can be supplied through ``y_mean_fn``;
+* the DTW-barycentre-averaging mean (models.py:176-178: tslearn's
+  ``dtw_barycenter_averaging_subgradient(realisation_set, max_iter=50, tol=1e-3)``) runs on the
+  device too (``be_dtw_barycenter_averaging_subgradient``) and is the default,
+  ``y_mean="dba"``; ``y_mean="mean"`` uses the arithmetic mean over realisations (tslearn's DBA
+  initialiser) instead, and ``y_mean_fn`` supplies any other mean from the host;
 * ``hyperparameters=(variance, lengthscale)`` selects the fixed-hyper-parameter posterior --
   the natural-gradient fixed point the reference's loop converges to -- without iterating;
   otherwise the natgrad(0.5)+Adam(0.01) loop of models.py:191-215 runs on the device for
@@ -22,10 +24,13 @@ from .labelled import ones_like
 
 
 class GPDTW1D:
-    def __init__(self, name: str = "GPRegressor", hyperparameters=None, y_mean_fn=None) -> None:
+    def __init__(self, name: str = "GPRegressor", hyperparameters=None, y_mean_fn=None, y_mean: str = "dba") -> None:
+        if y_mean not in ("dba", "mean"):
+            raise ValueError(f"y_mean must be 'dba' or 'mean', got {y_mean!r}")
         self.name = name
         self.hyperparameters = hyperparameters
         self.y_mean_fn = y_mean_fn
+        self.y_mean = y_mean
 
     # reference signature: models.py:164-170
     def fit(self, model, n_optim_nits: int = 500, compile_objective: bool = False, progress_bar: bool = True):
@@ -46,6 +51,8 @@ class GPDTW1D:
             reals = np.stack([np.asarray(models[i].model_data.values, dtype=np.float64) for i in idxs])
             r_dev = be._in(reals)
             X, y_mean, y_var = be.gpdtw1d_inputs(r_dev)  # models.py:175-182
+            if self.y_mean_fn is None and self.y_mean == "dba":  # models.py:176-178
+                y_mean = be.dtw_barycenter_averaging_subgradient(r_dev, max_iter=50, tol=1e-3)
             if self.y_mean_fn is not None:
                 y_mean = be._in(np.stack([np.asarray(self.y_mean_fn(reals[k])).ravel() for k in range(len(idxs))]))
             B = len(idxs)

@@ -232,6 +232,27 @@ int be_w2_collapse(be_ctx* ctx, const double* w2, int C, int M, int N, double* w
 int be_similarity_weights_pointwise(be_ctx* ctx, const double* mean, const double* var,
                                     int C, int M, int N, double* weights, double* w2_out);
 
+/* ---- SURVEY 8f "next" row 1: DTW barycentre averaging (the step that produces y_mean) ----------
+ * be_dtw_barycenter_averaging_subgradient: tslearn 0.5.1.0 dtw_barycenter_averaging_subgradient as
+ *   called at ensembles/models.py:176-178 (max_iter=50, tol=1e-3) and :251-253, batched over B
+ *   independent (cell, member) problems.  X [B,R,T] realisations; init_barycenter [B,T] or NULL
+ *   (= the mean over realisations, tslearn's _init_avg); barycenter [B,T] out; n_iter [B] (device,
+ *   may be NULL) iterations run per problem; cost [B] (device, may be NULL) last cost evaluated.
+ *   weights = None, barycenter_size = None, metric_params = None (the reference passes none).
+ *   T <= 4096 (BE_ERR_UNSUPPORTED above).  Synchronises the ctx stream once per iteration.
+ * be_perform_dba: the reference's own NumPy DBA, ensembles/dtwa.py:6-20 (medoid initialisation
+ *   :23-37, n_iterations of DBA_update :84-141), R <= 50 series of equal length; center [B,T] out,
+ *   medoid [B] (device int, may be NULL).
+ * be_dtw_squared: ensembles/dtwa.py:48-75 squared_DTW for P independent pairs A[p], X[p] ([P,T]). */
+size_t be_dtw_dba_workspace_bytes(int B, int R, int T);
+int be_dtw_barycenter_averaging_subgradient(be_ctx* ctx, const double* X, int B, int R, int T, int max_iter,
+                                            double initial_step_size, double final_step_size, double tol,
+                                            const double* init_barycenter, double* barycenter, int* n_iter,
+                                            double* cost, void* workspace, size_t workspace_bytes);
+int be_perform_dba(be_ctx* ctx, const double* X, int B, int R, int T, int n_iterations, double* center,
+                   int* medoid, void* workspace, size_t workspace_bytes);
+int be_dtw_squared(be_ctx* ctx, const double* A, const double* X, int P, int T, double* sqcost);
+
 #ifdef __cplusplus
 }
 #endif

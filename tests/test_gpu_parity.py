@@ -336,7 +336,8 @@ def test_reference_api_end_to_end(backend):
     obs_pm = es.ProcessModel(DataArray(obs, ("realisation", "time"), {"realisation": np.arange(Ro), "time": time}),
                              "obs")
     mc = es.ModelCollection(pms)
-    mc.fit(es.GPDTW1D(hyperparameters=(0.5, 6.0)), compile_objective=True, n_optim_nits=2, progress_bar=False)
+    mc.fit(es.GPDTW1D(hyperparameters=(0.5, 6.0), y_mean="mean"), compile_objective=True, n_optim_nits=2,
+           progress_bar=False)
     weights = es.LogLikelihoodWeight()(mc, obs_pm)
     assert weights.shape == (M, T) and weights.dims == ("model", "time")
     o = rp.cell_pipeline_L1(reals, obs, 0.5, 6.0)
@@ -405,8 +406,11 @@ def test_reference_api_default_fit_runs_training_loop(backend):
     pms = [es.ProcessModel(DataArray(reals[m], ("realisation", "time")), f"model{m}") for m in range(M)]
     mc = es.ModelCollection(pms)
     mc.fit(model=es.GPDTW1D(), compile_objective=True, n_optim_nits=2, progress_bar=False)
+    from oracle import dba
+
     for m in range(M):
-        mu_o, cov_o = rp.gpdtw1d_fit(reals[m], n_optim_nits=2)
+        y_dba = dba.dba_subgradient(reals[m], max_iter=50, tol=1e-3)[0]  # models.py:176-178
+        mu_o, cov_o = rp.gpdtw1d_fit(reals[m], n_optim_nits=2, y_mean=y_dba)
         assert rel_err(mc[m].distribution.mean.values, mu_o) <= L2_TOL
         assert rel_err(mc[m].distribution._dist.covariance(), cov_o) <= L2_TOL
     obs_pm = es.ProcessModel(DataArray(obs, ("realisation", "time")), "obs")

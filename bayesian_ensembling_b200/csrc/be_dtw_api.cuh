@@ -9,7 +9,7 @@ struct DtwShape {
     int word_bytes;   // bytes of one direction word
 };
 
-// T -> (W, NWARPS): one warp per pair while T <= 512, else a 256-thread CTA per pair
+// T -> (W, NWARPS): one warp per pair while T <= 512, else one CTA of 7-8 warps per pair
 inline bool dtw_shape(int T, DtwShape& s) {
     if (T <= 32) s = {1, 1, 1};
     else if (T <= 64) s = {2, 1, 1};
@@ -18,7 +18,7 @@ inline bool dtw_shape(int T, DtwShape& s) {
     else if (T <= 512) s = {16, 1, 4};
     else if (T <= 1024) s = {4, 8, 1};
     else if (T <= 2048) s = {8, 8, 2};
-    else if (T <= 3072) s = {12, 8, 4};
+    else if (T <= 3136) s = {14, 7, 4};
     else if (T <= 4096) s = {16, 8, 4};
     else return false;
     return true;
@@ -90,7 +90,7 @@ int launch_dtw_dp_w(be_ctx* ctx, int tie, bool want_dirs, const double* A, const
             case 116: return FN<16, 1>(__VA_ARGS__);                      \
             case 804: return FN<4, 8>(__VA_ARGS__);                       \
             case 808: return FN<8, 8>(__VA_ARGS__);                       \
-            case 812: return FN<12, 8>(__VA_ARGS__);                      \
+            case 714: return FN<14, 7>(__VA_ARGS__);                      \
             case 816: return FN<16, 8>(__VA_ARGS__);                      \
         }                                                                 \
         return BE_ERR_UNSUPPORTED;                                        \

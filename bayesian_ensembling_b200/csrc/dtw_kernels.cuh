@@ -29,11 +29,18 @@ template <> struct DtwWord<8> { typedef uint16_t type; };
 __host__ __device__ inline int dtw_threads_used(int T, int W) { return (T + W - 1) / W; }
 __host__ __device__ inline int dtw_steps(int T, int W) { return T + dtw_threads_used(T, W) - 1; }
 
+// resident CTAs per SM the DP kernel is compiled for: the kernel is issue-bound, so what matters is that
+// the register budget leaves no spill and that the CTAs of a launch fill the SMs without a long tail
+// (T = 3012: 14 columns x 7 warps -> 94 registers x 224 threads -> 3 CTAs per SM)
+__host__ __device__ constexpr int dtw_min_ctas(int W, int NWARPS) {
+    return NWARPS == 1 ? 4 : (NWARPS == 7 || W <= 8) ? 3 : 2;
+}
+
 // One pair = (row sequence a = A[pair / R], column sequence x = X[(pair / x_group) * R + pair % R]).
 // NWARPS == 1: one warp per pair, 4 pairs per 128-thread CTA, shuffles only.
 // NWARPS  > 1: one CTA of NWARPS warps per pair.
 template <int W, int NWARPS, int TIE, bool DIRS>
-__global__ void __launch_bounds__(NWARPS == 1 ? 128 : NWARPS * 32)
+__global__ void __launch_bounds__(NWARPS == 1 ? 128 : NWARPS * 32, dtw_min_ctas(W, NWARPS))
 k_dtw_dp(const double* __restrict__ A, const double* __restrict__ X, int T, int R, int x_group, int n_pairs,
          const int* __restrict__ active, typename DtwWord<W>::type* __restrict__ dirs, size_t dirs_stride,
          double* __restrict__ sqcost) {

@@ -220,6 +220,63 @@ def measure_hbm_stages(be, cfg, n_points, hbm_peak, reps=5):
 
 
 # ------------------------------------------------------------------------------------------------
+# the DTW-barycentre-averaging step that produces y_mean (models.py:176-178)
+# ------------------------------------------------------------------------------------------------
+def measure_dba(be, r_dev, cfg, step_ms, max_iter, with_cpu):
+    """be_dtw_barycenter_averaging_subgradient (max_iter=50, tol=1e-3 as the reference calls it) on the
+    step's (cell, member) problems; CUDA events; per-kernel figures from the C ABI profiler.  The CPU
+    figure is the C oracle (oracle/dba.c, one thread per member, all host cores)."""
+    import torch
+
+    C, M, R, T = r_dev.shape
+    X = r_dev.reshape(C * M, R, T)
+    be.dtw_barycenter_averaging_subgradient(X, max_iter=2, tol=1e-3)  # warm-up (workspace)
+    torch.cuda.synchronize()
+    be.profile(True)
+    be.profile_reset()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    _, n_iter, _ = be.dtw_barycenter_averaging_subgradient(X, max_iter=max_iter, tol=1e-3, want_info=True)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    prof = be.profile_read()
+    be.profile(False)
+    dp = prof.get("k_dtw_dp")
+    out = {
+        "ms_per_step": ms, "problems": C * M, "series_per_problem": R, "time_steps": T, "max_iter": max_iter, "tol": 1e-3,
+        "iterations_mean": float(n_iter.float().mean()), "iterations_max": int(n_iter.max()),
+        "cells_per_sec_dba_only": C / ms * 1e3,
+        "cells_per_sec_fit_weight_barycentre_with_dba": C / (ms + step_ms) * 1e3,
+        "kernels": {k: {"ms": v["ms"], "launches": v["launches"]} for k, v in prof.items()
+                    if k in ("k_dtw_dp", "k_dtw_backtrack", "k_dba_update")},
+        "k_dtw_dp": None if not dp else {
+            "dtw_table_cells_per_sec": dp["flops"] / 5.0 / dp["ms"] * 1e3, "fp64_ops_per_cell": 5,
+            "tflops": dp["flops"] / dp["ms"] / 1e9,
+            "bound": "instruction issue: ~14 instructions per table cell (5 on the FP64 pipe); no tensor-core form "
+                     "exists for a min-plus recurrence, and the 2-bit-per-cell path record is 0.25 B of HBM per cell"},
+        "note": "optional stage in front of the timed step (y_mean = 'dba' in grid.fit_weight_barycentre / GPDTW1D); "
+                "the headline value keeps y_mean as an input, as SURVEY 8 scopes it",
+    }
+    if with_cpu:
+        from concurrent.futures import ThreadPoolExecutor
+
+        from oracle import dba as oracle_dba
+
+        host = r_dev[0].cpu().numpy()
+        n = min(os.cpu_count() or 1, M)
+        oracle_dba.dba_subgradient(host[0][:, :64], max_iter=1)  # loads the library
+        t0 = time.perf_counter()
+        with ThreadPoolExecutor(n) as ex:
+            its = list(ex.map(lambda m: oracle_dba.dba_subgradient(host[m], max_iter=max_iter, tol=1e-3)[1], range(n)))
+        dt = time.perf_counter() - t0
+        out["cpu"] = {"value": 1.0 / (dt * M / n), "unit": UNIT, "cores": n, "kind": "port",
+                      "sample": f"{n} of {M} members of one cell, one thread each (C oracle): {dt:.1f} s, "
+                                f"{float(np.mean(its)):.0f} iterations"}
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------
 TENSOR_FAMILIES = {"k_chol_update", "k_trtri_accum", "k_lauum_cov", "k_panel_scale", "k_diag_block"}
@@ -392,6 +449,10 @@ def run_ours(args, cfg):
     if args.hbm_points > 0 and rank == 0:
         hbm_stages = measure_hbm_stages(be, cfg, args.hbm_points, hbm_peak)
 
+    dba = None
+    if args.dba_iters > 0 and rank == 0:
+        dba = measure_dba(be, r_dev, cfg, ms / args.steps, args.dba_iters, world == 1 and not args.no_cpu_baseline)
+
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         _use_all_host_threads()
@@ -426,6 +487,7 @@ def run_ours(args, cfg):
             "stages": stages,
             "l2_training_loop": l2,
             "hbm_stages": hbm_stages,
+            "dtw_barycentre_averaging": dba,
             "cpu_baseline": cpu_baseline,
         }
         print(json.dumps(line), flush=True)
@@ -445,6 +507,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--hbm-points", type=int, default=4_000_000,
                     help="(cell, time) points of the stand-alone memory-bound stage measurements (0: skip)")
+    ap.add_argument("--dba-iters", type=int, default=50,
+                    help="max_iter of the stand-alone DTW-barycentre-averaging measurement (0: skip)")
     ap.add_argument("--l2-iters", type=int, default=3, help="training-loop iterations timed for the l2_training_loop line (0: skip)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)

@@ -21,7 +21,7 @@ pytestmark = pytest.mark.gpu
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "dba_reference.npz")
 # one T per kernel shape of be_dtw_api.cuh:dtw_shape, plus ragged sizes around the boundaries
-SHAPE_TS = [1, 2, 7, 32, 33, 64, 100, 128, 251, 257, 512, 513, 700, 1025, 1980, 2049, 3012, 3100]
+SHAPE_TS = [1, 2, 7, 32, 33, 64, 100, 128, 251, 257, 512, 513, 700, 1025, 1980, 2049, 3012, 3136, 3137]
 
 
 def _t(backend, a):

@@ -1,4 +1,11 @@
+#!/bin/bash
+# DBA parity tests + timing at BASELINE shapes (one gpurun call). usage: tools/gpu_dba_check.sh [tag] [skip_tests]
+tag=${1:-dba}
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_dba.py -x -q > gpurun_out/pytest_dba.log 2>&1; echo "pytest rc=$?"; tail -15 gpurun_out/pytest_dba.log
-timeout 300 python tools/prof_dba.py cfg2 6 50 1 > gpurun_out/prof_dba_cfg2.json 2> gpurun_out/prof_dba_cfg2.err; echo rc=$?; cat gpurun_out/prof_dba_cfg2.json; tail -3 gpurun_out/prof_dba_cfg2.err
-timeout 300 python tools/prof_dba.py cfg4 128 50 1 > gpurun_out/prof_dba_cfg4.json 2> gpurun_out/prof_dba_cfg4.err; echo rc=$?; cat gpurun_out/prof_dba_cfg4.json; tail -3 gpurun_out/prof_dba_cfg4.err
+if [ -z "$2" ]; then
+timeout 900 python -m pytest tests/test_gpu_dba.py -x -q > gpurun_out/pytest_$tag.log 2>&1; echo "pytest rc=$?"; tail -5 gpurun_out/pytest_$tag.log
+fi
+for c in "cfg2 6" "cfg3 6" "cfg4 128" "cfg1 64"; do
+set -- $c
+timeout 300 python tools/prof_dba.py $1 $2 50 1 > gpurun_out/prof_${tag}_$1.json 2> gpurun_out/prof_${tag}_$1.err; echo "$1 rc=$?"; cat gpurun_out/prof_${tag}_$1.json; tail -2 gpurun_out/prof_${tag}_$1.err
+done

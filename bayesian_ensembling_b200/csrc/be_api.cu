@@ -133,6 +133,11 @@ int ensure_kernel_attrs(be_ctx* ctx) {
     BE_CUDA(cudaFuncSetAttribute(k_gemm_nt<EpiDB>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
     BE_CUDA(cudaFuncSetAttribute(k_gemm_nt<EpiSym>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
     BE_CUDA(cudaFuncSetAttribute(k_gemm_nt<EpiPlain>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
+    BE_CUDA(cudaFuncSetAttribute(k_loglik_weights_mvn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WEIGHT_STAGE_MAX_BYTES));
+    BE_CUDA(cudaFuncSetAttribute(k_loglik_weights_normal, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WEIGHT_STAGE_MAX_BYTES));
+    BE_CUDA(cudaFuncSetAttribute(k_crps_weights, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WEIGHT_STAGE_MAX_BYTES));
+    BE_CUDA(cudaFuncSetAttribute(k_w2_collapse, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WEIGHT_STAGE_MAX_BYTES));
+    BE_CUDA(cudaFuncSetAttribute(k_similarity_pointwise, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WEIGHT_STAGE_MAX_BYTES));
     g_attr_done = true;
     return BE_OK;
 }
@@ -623,8 +628,10 @@ int be_loglik_weights_mvn(be_ctx* ctx, const double* mvn_stats, const double* ob
     const int nout = 1 + (lls_exp ? 1 : 0) + (lls_mean ? 1 : 0);
     Prof pr(ctx, F_WEIGHTS, (double)C * M * T * (8.0 * Ro + 24.0),
             ((double)C * Ro * T + (double)C * M * 4 + (double)(nout + 1) * C * M * T) * 8);
-    k_loglik_weights_mvn<<<grid1d((size_t)C * T, 128), 128, 0, ctx->stream>>>(
-        mvn_stats, obs, C, M, Ro, T, standardisation_constant, weights, lls_exp, lls_mean);
+    const int wb = weight_stage_block(M);
+    const size_t wsm = weight_stage_bytes(M);
+    k_loglik_weights_mvn<<<grid1d((size_t)C * T, wb), wb, wsm, ctx->stream>>>(
+        mvn_stats, obs, C, M, Ro, T, standardisation_constant, weights, lls_exp, lls_mean, wsm > 0);
     BE_LAUNCHED();
     return BE_OK;
 }
@@ -669,8 +676,10 @@ int be_loglik_weights_normal(be_ctx* ctx, const double* loc, const double* scale
     if (Ro <= 0) return -7;
     if (N <= 0) return -8;
     if (!weights) return -10;
-    k_loglik_weights_normal<<<grid1d((size_t)C * N, 128), 128, 0, ctx->stream>>>(
-        loc, scale, obs, C, M, Ro, N, standardisation_constant, weights, lls_exp, lls_mean);
+    const int wb = weight_stage_block(M);
+    const size_t wsm = weight_stage_bytes(M);
+    k_loglik_weights_normal<<<grid1d((size_t)C * N, wb), wb, wsm, ctx->stream>>>(
+        loc, scale, obs, C, M, Ro, N, standardisation_constant, weights, lls_exp, lls_mean, wsm > 0);
     BE_LAUNCHED();
     return BE_OK;
 }

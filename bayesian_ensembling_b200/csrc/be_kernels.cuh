@@ -549,6 +549,28 @@ __global__ void k_mvn_constvec_logprob(const double* __restrict__ stats, const d
     ll[gid] = constvec_ll(stats + ((size_t)c * M + m) * 4, obs[((size_t)c * Ro + r) * T + i], T);
 }
 
+// Un-normalised weights of one point are staged in SHARED memory (one column per thread, [M][blockDim.x],
+// conflict-free) between the pass that forms them and the pass that divides by their sum, so that the
+// weights cross HBM once (the first version wrote them, re-read them and wrote them again: 2.4x the
+// algorithmic bytes at M = 24).  When M * blockDim.x * 8 bytes do not fit the launch passes smem_ok = 0 and
+// the output array itself is the staging buffer, as before.
+struct WeightStage {
+    double* p;
+    size_t stride;
+    __device__ __forceinline__ WeightStage(double* smem, bool smem_ok, double* w_point, size_t w_stride) {
+        p = smem_ok ? smem + threadIdx.x : w_point;
+        stride = smem_ok ? blockDim.x : w_stride;
+    }
+    __device__ __forceinline__ double& operator[](int m) { return p[(size_t)m * stride]; }
+};
+constexpr size_t WEIGHT_STAGE_MAX_BYTES = 96 * 1024;
+__host__ inline int weight_stage_block(int M) { return M <= 32 ? 128 : 64; }
+__host__ inline size_t weight_stage_bytes(int M) {
+    size_t b = (size_t)M * weight_stage_block(M) * sizeof(double);
+    return b <= WEIGHT_STAGE_MAX_BYTES ? b : 0;
+}
+
+
 // one thread per (cell, time): mean over obs realisations (weights.py:103-104), exp(c .) (:107),
 // normalise over models (:122-123).  The constant-vector log-density is quadratic in the observation,
 // so its mean over the Ro realisations needs only mean(o) and mean(o^2):
@@ -561,10 +583,12 @@ __global__ void k_mvn_constvec_logprob(const double* __restrict__ stats, const d
 // at the occupancy those variants allow, not ALU- or traffic-bound.)
 __global__ void k_loglik_weights_mvn(const double* __restrict__ stats, const double* __restrict__ obs, int C, int M,
                                      int Ro, int T, double cst, double* __restrict__ w, double* __restrict__ lls_exp,
-                                     double* __restrict__ lls_mean) {
+                                     double* __restrict__ lls_mean, int smem_ok) {
+    extern __shared__ double wstage[];
     size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (gid >= (size_t)C * T) return;
     int c = (int)(gid / T), i = (int)(gid % T);
+    WeightStage st(wstage, smem_ok, w + (size_t)c * M * T + i, (size_t)T);
     const double* ob = obs + (size_t)c * Ro * T + i;
     double m1 = 0.0, m2 = 0.0;
     for (int r = 0; r < Ro; ++r) {
@@ -585,13 +609,10 @@ __global__ void k_loglik_weights_mvn(const double* __restrict__ stats, const dou
         size_t o = ((size_t)c * M + m) * T + i;
         if (lls_mean) lls_mean[o] = mean;
         if (lls_exp) lls_exp[o] = e;
-        w[o] = e;
+        st[m] = e;
         total += e;
     }
-    for (int m = 0; m < M; ++m) {
-        size_t o = ((size_t)c * M + m) * T + i;
-        w[o] = w[o] / total;
-    }
+    for (int m = 0; m < M; ++m) w[((size_t)c * M + m) * T + i] = st[m] / total;
 }
 
 __global__ void k_normal_logprob(const double* __restrict__ loc, const double* __restrict__ scale,
@@ -605,10 +626,12 @@ __global__ void k_normal_logprob(const double* __restrict__ loc, const double* _
 __global__ void k_loglik_weights_normal(const double* __restrict__ loc, const double* __restrict__ scale,
                                         const double* __restrict__ obs, int C, int M, int Ro, int N, double cst,
                                         double* __restrict__ w, double* __restrict__ lls_exp,
-                                        double* __restrict__ lls_mean) {
+                                        double* __restrict__ lls_mean, int smem_ok) {
+    extern __shared__ double wstage[];
     size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (gid >= (size_t)C * N) return;
     int c = (int)(gid / N), i = (int)(gid % N);
+    WeightStage st(wstage, smem_ok, w + (size_t)c * M * N + i, (size_t)N);
     const double* ob = obs + (size_t)c * Ro * N + i;
     double total = 0.0;
     for (int m = 0; m < M; ++m) {
@@ -624,13 +647,10 @@ __global__ void k_loglik_weights_normal(const double* __restrict__ loc, const do
         double e = exp(cst * mean);
         if (lls_mean) lls_mean[o] = mean;
         if (lls_exp) lls_exp[o] = e;
-        w[o] = e;
+        st[m] = e;
         total += e;
     }
-    for (int m = 0; m < M; ++m) {
-        size_t o = ((size_t)c * M + m) * N + i;
-        w[o] = w[o] / total;
-    }
+    for (int m = 0; m < M; ++m) w[((size_t)c * M + m) * N + i] = st[m] / total;
 }
 
 // member-sharded normalisation: w = lls_exp / total  (weights.py:122-123 after an all-reduce of the sum)

@@ -330,7 +330,10 @@ int be_crps_weights(be_ctx* ctx, const double* loc, const double* scale, const d
     if (Ro <= 0) return -7;
     if (N <= 0) return -8;
     if (!weights) return -9;
-    k_crps_weights<<<grid1d((size_t)C * N, 128), 128, 0, ctx->stream>>>(loc, scale, obs, C, M, Ro, N, weights, crps_mean);
+    const int wb = weight_stage_block(M);
+    const size_t wsm = weight_stage_bytes(M);
+    k_crps_weights<<<grid1d((size_t)C * N, wb), wb, wsm, ctx->stream>>>(loc, scale, obs, C, M, Ro, N, weights, crps_mean,
+                                                                       wsm > 0);
     BE_LAUNCHED();
     return BE_OK;
 }
@@ -342,7 +345,9 @@ int be_w2_collapse(be_ctx* ctx, const double* w2, int C, int M, int N, double* w
     if (M <= 0) return -4;
     if (N <= 0) return -5;
     if (!weights) return -6;
-    k_w2_collapse<<<grid1d((size_t)C * N, 128), 128, 0, ctx->stream>>>(w2, C, M, N, weights);
+    const int wb = weight_stage_block(M);
+    const size_t wsm = weight_stage_bytes(M);
+    k_w2_collapse<<<grid1d((size_t)C * N, wb), wb, wsm, ctx->stream>>>(w2, C, M, N, weights, wsm > 0);
     BE_LAUNCHED();
     return BE_OK;
 }
@@ -356,7 +361,10 @@ int be_similarity_weights_pointwise(be_ctx* ctx, const double* mean, const doubl
     if (M <= 0) return -5;
     if (N <= 0) return -6;
     if (!weights) return -7;
-    k_similarity_pointwise<<<grid1d((size_t)C * N, 128), 128, 0, ctx->stream>>>(mean, var, C, M, N, weights, w2_out);
+    const int wb = weight_stage_block(M);
+    const size_t wsm = weight_stage_bytes(M);
+    k_similarity_pointwise<<<grid1d((size_t)C * N, wb), wb, wsm, ctx->stream>>>(mean, var, C, M, N, weights, w2_out,
+                                                                               wsm > 0);
     BE_LAUNCHED();
     return BE_OK;
 }

@@ -21,10 +21,12 @@ __device__ __forceinline__ double crps_gaussian_d(double x, double mu, double si
 // reference builds at :497 that is the member's VARIANCE (quirk Q-SCALE); the caller passes it.
 __global__ void k_crps_weights(const double* __restrict__ loc, const double* __restrict__ scale,
                                const double* __restrict__ obs, int C, int M, int Ro, int N, double* __restrict__ w,
-                               double* __restrict__ crps_mean) {
+                               double* __restrict__ crps_mean, int smem_ok) {
+    extern __shared__ double wstage[];
     size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (gid >= (size_t)C * N) return;
     int c = (int)(gid / N), i = (int)(gid % N);
+    WeightStage st(wstage, smem_ok, w + (size_t)c * M * N + i, (size_t)N);
     const double* ob = obs + (size_t)c * Ro * N + i;
     double total = 0.0;
     for (int m = 0; m < M; ++m) {
@@ -35,21 +37,20 @@ __global__ void k_crps_weights(const double* __restrict__ loc, const double* __r
         double mean = s / Ro;
         if (crps_mean) crps_mean[o] = mean;
         double inv = 1.0 / mean;
-        w[o] = inv;
+        st[m] = inv;
         total += inv;
     }
-    for (int m = 0; m < M; ++m) {
-        size_t o = ((size_t)c * M + m) * N + i;
-        w[o] = w[o] / total;
-    }
+    for (int m = 0; m < M; ++m) w[((size_t)c * M + m) * N + i] = st[m] / total;
 }
 
 // nanmean over j of d[c, i, j, n], then normalise over i (weights.py:259,296,321 and :331).
 // One thread per (cell, n); the M x M distances of a point are read once.
-__global__ void k_w2_collapse(const double* __restrict__ d, int C, int M, int N, double* __restrict__ w) {
+__global__ void k_w2_collapse(const double* __restrict__ d, int C, int M, int N, double* __restrict__ w, int smem_ok) {
+    extern __shared__ double wstage[];
     size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (gid >= (size_t)C * N) return;
     int c = (int)(gid / N), n = (int)(gid % N);
+    WeightStage st(wstage, smem_ok, w + (size_t)c * M * N + n, (size_t)N);
     const double* dc = d + (size_t)c * M * M * N + n;
     double total = 0.0;
     for (int i = 0; i < M; ++i) {
@@ -62,13 +63,10 @@ __global__ void k_w2_collapse(const double* __restrict__ d, int C, int M, int N,
             }
         }
         double m = s / cnt;
-        w[((size_t)c * M + i) * N + n] = m;
+        st[i] = m;
         total += m;
     }
-    for (int i = 0; i < M; ++i) {
-        size_t o = ((size_t)c * M + i) * N + n;
-        w[o] = w[o] / total;
-    }
+    for (int i = 0; i < M; ++i) w[((size_t)c * M + i) * N + n] = st[i] / total;
 }
 
 // mode="temporal" (weights.py:302-325): per point n and pair (i, j) the 1-dimensional
@@ -76,10 +74,12 @@ __global__ void k_w2_collapse(const double* __restrict__ d, int C, int M, int N,
 // v = the distributions' variance() (the caller passes it: variance**2 for the reference's
 // dx.Normal(mean, variance)); nanmean over j; normalise over i.  Optionally writes the distances.
 __global__ void k_similarity_pointwise(const double* __restrict__ mean, const double* __restrict__ var, int C, int M,
-                                       int N, double* __restrict__ w, double* __restrict__ w2_out) {
+                                       int N, double* __restrict__ w, double* __restrict__ w2_out, int smem_ok) {
+    extern __shared__ double wstage[];
     size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (gid >= (size_t)C * N) return;
     int c = (int)(gid / N), n = (int)(gid % N);
+    WeightStage st(wstage, smem_ok, w + (size_t)c * M * N + n, (size_t)N);
     const double* mc = mean + (size_t)c * M * N + n;
     const double* vc = var + (size_t)c * M * N + n;
     double total = 0.0;
@@ -97,13 +97,10 @@ __global__ void k_similarity_pointwise(const double* __restrict__ mean, const do
             }
         }
         double m = s / cnt;
-        w[((size_t)c * M + i) * N + n] = m;
+        st[i] = m;
         total += m;
     }
-    for (int i = 0; i < M; ++i) {
-        size_t o = ((size_t)c * M + i) * N + n;
-        w[o] = w[o] / total;
-    }
+    for (int i = 0; i < M; ++i) w[((size_t)c * M + i) * N + n] = st[i] / total;
 }
 
 }  // namespace be

@@ -549,6 +549,34 @@ def test_fullcov_barycentre_cells_batched(backend):
 
 
 # ------------------------------------------------------------------------------------ SURVEY 8f "next": CRPS / similarity weights
+@pytest.mark.parametrize("M", [24, 40, 200])
+def test_weight_kernels_staging_regimes(backend, M):
+    """The normalising kernels stage un-normalised weights in shared memory ([M][128] up to M = 32, [M][64]
+    up to 96 KB, the output array itself beyond): all three regimes against the oracle."""
+    rng = np.random.default_rng(M)
+    C, Ro, N = 2, 3, 151
+    loc = rng.normal(size=(C, M, N))
+    scale = rng.uniform(0.2, 0.6, size=(C, M, N))
+    obs = rng.normal(size=(C, Ro, N))
+    w = backend.loglik_weights_normal(_t(backend, loc), _t(backend, scale), _t(backend, obs))
+    wc = backend.crps_weights(_t(backend, loc), _t(backend, scale), _t(backend, obs))
+    ws = backend.similarity_weights_pointwise(_t(backend, loc), _t(backend, scale * scale))  # variance() = scale**2
+    a2 = rng.uniform(0.5, 1.5, size=C * M)
+    stats = np.stack([a2, a2 * rng.uniform(0.9, 1.1, C * M), a2 * rng.uniform(1.0, 1.2, C * M),
+                      -0.5 * N * 1.8378770664093453 + rng.random(C * M)], axis=1)
+    wm = backend.loglik_weights_mvn(_t(backend, stats), _t(backend, obs), M).cpu().numpy()
+    for c in range(C):
+        _nan_equal_close(w[c].cpu().numpy(), rp.loglik_weights_normal(loc[c], scale[c], obs[c])[0], 1e-12, "normal")
+        assert rel_err(wc[c].cpu().numpy(), rp.crps_weights(loc[c], scale[c], obs[c])[0]) < 1e-12
+        assert rel_err(ws[c].cpu().numpy(), rp.model_similarity_weights_temporal(loc[c], scale[c])[0]) < 1e-10
+        st = stats[c * M:(c + 1) * M]
+        m1, m2 = obs[c].mean(axis=0), (obs[c] ** 2).mean(axis=0)
+        ll = -0.5 * (m2[None] * st[:, :1] - 2.0 * m1[None] * st[:, 1:2] + st[:, 2:3]) - 0.5 * N * np.log(2 * np.pi) - st[:, 3:4]
+        e = np.exp(ll)
+        assert rel_err(wm[c], e / e.sum(axis=0)) < 1e-10
+        assert np.abs(wm[c].sum(axis=0) - 1.0).max() < 1e-12
+
+
 def test_crps_weights_vs_oracle(backend):
     rng = np.random.default_rng(3)
     C, M, Ro, N = 2, 5, 3, 57

@@ -1,6 +1,7 @@
 // C ABI of the B200 hot path (see include/be_b200.h).  Host-side orchestration only: every
 // arithmetic operation is a kernel from be_kernels.cuh.  There is no CPU fallback.
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -133,7 +134,7 @@ int ensure_kernel_attrs(be_ctx* ctx) {
     BE_CUDA(cudaFuncSetAttribute(k_gemm_nt<EpiDB>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
     BE_CUDA(cudaFuncSetAttribute(k_gemm_nt<EpiSym>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
     BE_CUDA(cudaFuncSetAttribute(k_gemm_nt<EpiPlain>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
-    BE_CUDA(cudaFuncSetAttribute(k_loglik_weights_mvn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WEIGHT_STAGE_MAX_BYTES));
+    BE_CUDA(cudaFuncSetAttribute(k_loglik_weights_mvn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WEIGHT_STAGE_MAX_BYTES + 16384));
     BE_CUDA(cudaFuncSetAttribute(k_loglik_weights_normal, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WEIGHT_STAGE_MAX_BYTES));
     BE_CUDA(cudaFuncSetAttribute(k_crps_weights, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WEIGHT_STAGE_MAX_BYTES));
     BE_CUDA(cudaFuncSetAttribute(k_w2_collapse, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WEIGHT_STAGE_MAX_BYTES));
@@ -627,11 +628,13 @@ int be_loglik_weights_mvn(be_ctx* ctx, const double* mvn_stats, const double* ob
     if (!weights) return -9;
     const int nout = 1 + (lls_exp ? 1 : 0) + (lls_mean ? 1 : 0);
     Prof pr(ctx, F_WEIGHTS, (double)C * M * T * (8.0 * Ro + 24.0),
-            ((double)C * Ro * T + (double)C * M * 4 + (double)(nout + 1) * C * M * T) * 8);
+            ((double)C * Ro * T + (double)C * M * 4 + (double)nout * C * M * T) * 8);
     const int wb = weight_stage_block(M);
     const size_t wsm = weight_stage_bytes(M);
-    k_loglik_weights_mvn<<<grid1d((size_t)C * T, wb), wb, wsm, ctx->stream>>>(
-        mvn_stats, obs, C, M, Ro, T, standardisation_constant, weights, lls_exp, lls_mean, wsm > 0);
+    const size_t ssm = weight_stats_bytes(M) <= 16384 ? weight_stats_bytes(M) : 0;
+    k_loglik_weights_mvn<<<grid1d((size_t)C * T, wb), wb, wsm + ssm, ctx->stream>>>(
+        mvn_stats, obs, C, M, Ro, T, standardisation_constant, weights, lls_exp, lls_mean,
+        (wsm > 0 ? 1 : 0) | (ssm > 0 ? 2 : 0));
     BE_LAUNCHED();
     return BE_OK;
 }

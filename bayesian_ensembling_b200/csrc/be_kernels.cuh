@@ -569,6 +569,8 @@ __host__ inline size_t weight_stage_bytes(int M) {
     size_t b = (size_t)M * weight_stage_block(M) * sizeof(double);
     return b <= WEIGHT_STAGE_MAX_BYTES ? b : 0;
 }
+// k_loglik_weights_mvn also keeps the statistics of up to two cells ([2][M][4]) behind the staging area
+__host__ inline size_t weight_stats_bytes(int M) { return (size_t)2 * M * 4 * sizeof(double); }
 
 
 // one thread per (cell, time): mean over obs realisations (weights.py:103-104), exp(c .) (:107),
@@ -581,16 +583,34 @@ __host__ inline size_t weight_stage_bytes(int M) {
 // (Variants that interleave four fast-exp chains, or keep the un-normalised weights in registers instead of
 // re-reading them, measured SLOWER at 4M points -- 0.44 / 0.52 ms against 0.40 ms: the kernel is latency-bound
 // at the occupancy those variants allow, not ALU- or traffic-bound.)
+// The (|a|^2, a.b, |b|^2, sum log diag L) statistics of the one or two cells a CTA's points belong to are
+// copied to shared memory first (read per member from global memory they are a dependent L2 round trip per
+// loop trip: the staging buffer leaves almost no L1).  exp and the division are the library's: variants with
+// a branch-free exp core and a shared-reciprocal division, four members interleaved, measured SLOWER
+// (0.42 against 0.36 ms at 4 M points, 24 members: more registers, fewer resident warps).
 __global__ void k_loglik_weights_mvn(const double* __restrict__ stats, const double* __restrict__ obs, int C, int M,
                                      int Ro, int T, double cst, double* __restrict__ w, double* __restrict__ lls_exp,
                                      double* __restrict__ lls_mean, int smem_ok) {
     extern __shared__ double wstage[];
-    size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (gid >= (size_t)C * T) return;
-    int c = (int)(gid / T), i = (int)(gid % T);
-    WeightStage st(wstage, smem_ok, w + (size_t)c * M * T + i, (size_t)T);
+    const size_t gid0 = (size_t)blockIdx.x * blockDim.x;
+    const size_t gid = gid0 + threadIdx.x;
+    const size_t n_pts = (size_t)C * T;
+    const int c0 = (int)(gid0 / T);
+    const int c_last = (int)((min(gid0 + blockDim.x, n_pts) - 1) / T);
+    // smem_ok: bit 0 = the staging area exists, bit 1 = room for the statistics behind it
+    double* sst = wstage + ((smem_ok & 1) ? (size_t)M * blockDim.x : 0);
+    const bool stats_in_smem = (smem_ok & 2) && c_last - c0 <= 1;
+    if (stats_in_smem) {
+        const int n = (c_last - c0 + 1) * M * 4;
+        for (int e = threadIdx.x; e < n; e += blockDim.x) sst[e] = stats[(size_t)c0 * M * 4 + e];
+    }
+    __syncthreads();
+    if (gid >= n_pts) return;
+    const int c = (int)(gid / T), i = (int)(gid - (size_t)c * T);
+    WeightStage st(wstage, smem_ok & 1, w + (size_t)c * M * T + i, (size_t)T);
     const double* ob = obs + (size_t)c * Ro * T + i;
     double m1 = 0.0, m2 = 0.0;
+#pragma unroll 5
     for (int r = 0; r < Ro; ++r) {
         double o = ob[(size_t)r * T];
         m1 += o;
@@ -600,9 +620,12 @@ __global__ void k_loglik_weights_mvn(const double* __restrict__ stats, const dou
     m2 /= Ro;
     const double base = -0.5 * (double)T * LOG_2PI;
     double total = 0.0;
+    const double2* sp = stats_in_smem ? reinterpret_cast<const double2*>(sst + (size_t)(c - c0) * M * 4)
+                                      : reinterpret_cast<const double2*>(stats + (size_t)c * M * 4);
+    double* wp = w + (size_t)c * M * T + i;
+#pragma unroll 4
     for (int m = 0; m < M; ++m) {
-        const double2* sp = reinterpret_cast<const double2*>(stats + ((size_t)c * M + m) * 4);
-        const double2 s01 = __ldg(sp), s23 = __ldg(sp + 1);
+        const double2 s01 = sp[2 * m], s23 = sp[2 * m + 1];
         double maha = (m2 * s01.x - 2.0 * m1 * s01.y) + s23.x;
         double mean = (-0.5 * maha + base) - s23.y;
         double e = exp(cst * mean);
@@ -612,7 +635,8 @@ __global__ void k_loglik_weights_mvn(const double* __restrict__ stats, const dou
         st[m] = e;
         total += e;
     }
-    for (int m = 0; m < M; ++m) w[((size_t)c * M + m) * T + i] = st[m] / total;
+#pragma unroll 4
+    for (int m = 0; m < M; ++m) wp[(size_t)m * T] = st[m] / total;
 }
 
 __global__ void k_normal_logprob(const double* __restrict__ loc, const double* __restrict__ scale,

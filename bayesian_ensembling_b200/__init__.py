@@ -8,7 +8,7 @@ from .labelled import DataArray  # noqa: F401
 from .models import GPDTW1D  # noqa: F401
 from .wasserstein import (gaussian_barycentre, gaussian_barycentre_fullcov, gaussian_w2_distance_distrax,  # noqa: F401
                           sqrtm, wasserstien_distance)
-from .weights import (CRPSWeight, InverseSquareWeight, LogLikelihoodWeight, ModelSimilarityWeight,  # noqa: F401
+from .weights import (CRPSWeight, InverseSquareWeight, KSDWeight, LogLikelihoodWeight, ModelSimilarityWeight,  # noqa: F401
                       UniformWeight)
 
 __version__ = "0.1.0"

@@ -65,6 +65,7 @@ SIGNATURES = {
     "be_w2_distance_diag": (_I, [_P, _P, _P, _P, _P, _I, _I, _P]),
     "be_barycentre_fullcov_workspace_bytes": (_Z, [_I, _I, _I]),
     "be_crps_weights": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _P, _P]),
+    "be_ksd_weights": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _P, _P]),
     "be_w2_collapse": (_I, [_P, _P, _I, _I, _I, _P]),
     "be_similarity_weights_pointwise": (_I, [_P, _P, _P, _I, _I, _I, _P, _P]),
     "be_dtw_dba_workspace_bytes": (_Z, [_I, _I, _I]),

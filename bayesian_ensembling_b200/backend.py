@@ -465,6 +465,20 @@ class Backend:
         _lib.check(self.ctx, rc, "be_crps_weights")
         return (w, cm) if want_crps else w
 
+    def ksd_weights(self, loc, scale, obs, want_ksd=False):
+        """loc/scale [C,M,N], obs [C,Ro,N] -> weights [C,M,N] (+ ksd) (weights.py:336-441)"""
+        loc = self._in(loc)
+        C, M, N = loc.shape
+        scale = self._in(scale, (C, M, N), "scale")
+        obs = self._in(obs)
+        Ro = obs.shape[1]
+        w = self._new(C, M, N)
+        k = self._new(C, M, N) if want_ksd else None
+        self._sync_stream()
+        rc = self.lib.be_ksd_weights(self.ctx, _ptr(loc), _ptr(scale), _ptr(obs), C, M, Ro, N, _ptr(w), _ptr(k))
+        _lib.check(self.ctx, rc, "be_ksd_weights")
+        return (w, k) if want_ksd else w
+
     def w2_collapse(self, w2):
         """w2 [C,M,M,N] -> weights [C,M,N]: nanmean over the second model, normalised over models"""
         w2 = self._in(w2)

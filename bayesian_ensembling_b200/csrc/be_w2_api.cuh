@@ -338,6 +338,25 @@ int be_crps_weights(be_ctx* ctx, const double* loc, const double* scale, const d
     return BE_OK;
 }
 
+int be_ksd_weights(be_ctx* ctx, const double* loc, const double* scale, const double* obs, int C, int M, int Ro,
+                   int N, double* weights, double* ksd) {
+    if (!ctx) return -1;
+    if (!loc) return -2;
+    if (!scale) return -3;
+    if (!obs) return -4;
+    if (C <= 0) return -5;
+    if (M <= 0) return -6;
+    if (Ro <= 0) return -7;
+    if (N <= 0) return -8;
+    if (!weights) return -9;
+    const int wb = weight_stage_block(M);
+    const size_t wsm = weight_stage_bytes(M);
+    k_ksd_weights<<<grid1d((size_t)C * N, wb), wb, wsm, ctx->stream>>>(loc, scale, obs, C, M, Ro, N, weights, ksd,
+                                                                      wsm > 0);
+    BE_LAUNCHED();
+    return BE_OK;
+}
+
 int be_w2_collapse(be_ctx* ctx, const double* w2, int C, int M, int N, double* weights) {
     if (!ctx) return -1;
     if (!w2) return -2;

@@ -43,6 +43,58 @@ __global__ void k_crps_weights(const double* __restrict__ loc, const double* __r
     for (int m = 0; m < M; ++m) w[((size_t)c * M + m) * N + i] = st[m] / total;
 }
 
+// KSDWeight._compute, ensembles/weights.py:396-441: per (cell, point) and model the IMQ kernel Stein
+// discrepancy of the Ro observation samples against N(loc, scale) (scale = the member's VARIANCE, Q-SCALE):
+//   g_a = -(x_a - loc) / scale^2 (:419);  k0(a, b) = the five terms of k_0_fun (:360-375) with dim = 1, c = 1,
+//   beta = -1/2, q = 1 + (x_a - x_b)^2:  g_a g_b q^-1/2 + g_a d q^-3/2 - g_b d q^-3/2 + q^-3/2 - 3 q^-5/2 d^2;
+//   ksd = sqrt(sum_ab k0) / Ro (:394);  weights = (1 / ksd) normalised over models (:434-438).
+// The q powers are 1/sqrt(q) divided by q (once, twice) instead of three pow calls.
+__global__ void k_ksd_weights(const double* __restrict__ loc, const double* __restrict__ scale,
+                              const double* __restrict__ obs, int C, int M, int Ro, int N, double* __restrict__ w,
+                              double* __restrict__ ksd_out, int smem_ok) {
+    extern __shared__ double wstage[];
+    size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= (size_t)C * N) return;
+    int c = (int)(gid / N), i = (int)(gid % N);
+    WeightStage st(wstage, smem_ok, w + (size_t)c * M * N + i, (size_t)N);
+    const double* ob = obs + (size_t)c * Ro * N + i;
+    double total = 0.0;
+    for (int m = 0; m < M; ++m) {
+        size_t o = ((size_t)c * M + m) * N + i;
+        const double l = loc[o], sc = scale[o];
+        const double s2 = sc * sc;
+        double sum = 0.0;
+        for (int a = 0; a < Ro; ++a) {
+            const double xa = ob[(size_t)a * N];
+            const double ga = -(xa - l) / s2;
+            double row = 0.0;
+            for (int b = 0; b < Ro; ++b) {
+                const double xb = ob[(size_t)b * N];
+                const double gb = -(xb - l) / s2;
+                const double d = xa - xb;
+                const double d2 = d * d;
+                const double q = 1.0 + d2;
+                const double p05 = 1.0 / sqrt(q);  // q^-1/2
+                const double p15 = p05 / q;        // q^-3/2
+                const double p25 = p15 / q;        // q^-5/2
+                double k0 = (ga * gb) * p05;
+                k0 += (ga * d) * p15;
+                k0 += -1.0 * (gb * d) * p15;
+                k0 += p15;
+                k0 += -3.0 * p25 * d2;
+                row += k0;
+            }
+            sum += row;
+        }
+        const double ksd = sqrt(sum) / (double)Ro;
+        if (ksd_out) ksd_out[o] = ksd;
+        const double inv = 1.0 / ksd;
+        st[m] = inv;
+        total += inv;
+    }
+    for (int m = 0; m < M; ++m) w[((size_t)c * M + m) * N + i] = st[m] / total;
+}
+
 // nanmean over j of d[c, i, j, n], then normalise over i (weights.py:259,296,321 and :331).
 // One thread per (cell, n); the M x M distances of a point are read once.
 __global__ void k_w2_collapse(const double* __restrict__ d, int C, int M, int N, double* __restrict__ w, int smem_ok) {

@@ -125,6 +125,32 @@ class CRPSWeight(AbstractWeight):
         return concat(per_model, dim="model").rename("Continuous Ranked Probability Scores weights")
 
 
+class KSDWeight(AbstractWeight):
+    """ensembles/weights.py:336-441 on the GPU: per model and point the IMQ kernel Stein discrepancy of the
+    observation realisations against ``dx.Normal(model_mean[i], model_var[i])`` (the variance is the scale,
+    :417, quirk Q-SCALE), then ``1 / ksd`` normalised over models."""
+
+    def __init__(self, name: str = "KernelSteinDiscrepancyWeight") -> None:
+        super().__init__(name)
+
+    def _compute(self, process_models, observations):
+        assert len(process_models.time) == len(observations.time), \
+            "Time coordinates do not match between models and observations"
+        assert hasattr(process_models[0].distribution, "_dist"), "Distribution not defined - fit models first"
+        be = Backend.get()
+        models = list(process_models.models)
+        obs_flat = np.asarray(observations.model_data.values, dtype=np.float64).reshape(observations.n_realisations, -1)
+        loc = torch.stack([_dev_vec(be, m.distribution._dist, "mean") for m in models])[None]
+        var = torch.stack([_dev_vec(be, m.distribution._dist, "variance") for m in models])[None]
+        w = be.ksd_weights(loc, var, be._in(obs_flat[None]))[0].cpu().numpy()
+        per_model = []
+        for m, v in zip(models, w):  # weights.py:423-429
+            x = copy.deepcopy(m.model_data.isel(realisation=0)).drop_vars("realisation")
+            x.data = v.reshape(x.shape)
+            per_model.append(x.assign_coords(model=m.model_name))
+        return concat(per_model, dim="model").rename("Kernel Stein Discrepancy weights")
+
+
 class ModelSimilarityWeight(AbstractWeight):
     """ensembles/weights.py:214-333 on the GPU: pairwise Gaussian W2 "distances" between the members'
     posteriors (wasserstein.py:21-47, un-squared location term), ``nanmean`` over the second model,

@@ -221,6 +221,12 @@ int be_barycentre_fullcov(be_ctx* ctx, const double* mus, const double* sigmas, 
  * weights [C,M,N]; crps_mean [C,M,N] may be NULL. */
 int be_crps_weights(be_ctx* ctx, const double* loc, const double* scale, const double* obs,
                     int C, int M, int Ro, int N, double* weights, double* crps_mean);
+/* KSDWeight._compute, ensembles/weights.py:336-441: ksd[c,m,n] = IMQ kernel Stein discrepancy (k_0_fun :360-375,
+ * imq_KSD :380-394, c = 1, beta = -1/2) of the Ro observation samples at point n against
+ * dx.Normal(loc, scale) (:417; scale = the member's VARIANCE, Q-SCALE), with grad log p = -(x - loc) / scale^2
+ * (:419); weights = (1 / ksd) normalised over models (:434-438).  Layouts as be_crps_weights; ksd may be NULL. */
+int be_ksd_weights(be_ctx* ctx, const double* loc, const double* scale, const double* obs,
+                   int C, int M, int Ro, int N, double* weights, double* ksd);
 /* ModelSimilarityWeight._compute, ensembles/weights.py:214-333.
  * be_w2_collapse: w2 [C,M,M,N] pairwise distances (from be_w2_distance / be_w2_distance_diag)
  *   -> nanmean over the second model (:259,296,321), normalised over models (:331): weights [C,M,N]

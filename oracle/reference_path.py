@@ -527,6 +527,43 @@ def crps_weights(locs, variances, obs):
         return inv / inv.sum(axis=0), crps
 
 
+def ksd_imq(samples, grads, c=1.0, beta=-0.5):
+    """``imq_KSD`` of ``KSDWeight._compute`` (ensembles/weights.py:360-394) for 1-dimensional samples:
+    ``sqrt(sum_ab k0(x_a, x_b, g_a, g_b)) / N`` with the five IMQ Stein-kernel terms of ``k_0_fun`` (:360-375),
+    dim = 1.  ``samples, grads [N]`` (the reference feeds ``[N,1]``)."""
+    x = np.asarray(samples, dtype=np.float64).ravel()
+    g = np.asarray(grads, dtype=np.float64).ravel()
+    diff = x[:, None] - x[None, :]
+    q = c ** 2 + diff * diff
+    t1 = (g[:, None] * g[None, :]) * q ** beta
+    t2 = -2.0 * beta * (g[:, None] * diff) * q ** (beta - 1.0)
+    t3 = 2.0 * beta * (g[None, :] * diff) * q ** (beta - 1.0)
+    t4 = -2.0 * 1 * beta * q ** (beta - 1.0)
+    t5 = -4.0 * beta * (beta - 1.0) * q ** (beta - 2.0) * (diff * diff)
+    k0 = t1 + t2 + t3 + t4 + t5
+    with np.errstate(invalid="ignore"):
+        return np.sqrt(k0.sum(axis=1).sum()) / x.size
+
+
+def ksd_weights(locs, variances, obs):
+    """``KSDWeight._compute``, ensembles/weights.py:396-441: per model and point the target is
+    ``dx.Normal(model_mean[i], model_var[i])`` (:417; the variance is the SCALE, quirk Q-SCALE), the samples
+    are the observation realisations at that point (:418), ``grad log p(x) = -(x - mu) / scale^2`` (:419),
+    ``ksd = imq_KSD(samples, grads)`` (:420); weights = ``1 / ksd`` normalised over models (:434-438).
+    ``locs, variances [M,N]``, ``obs [Ro,N]``.  Returns ``(weights [M,N], ksd [M,N])``."""
+    locs, variances, obs = (np.asarray(a, dtype=np.float64) for a in (locs, variances, obs))
+    M, N = locs.shape
+    ksd = np.empty((M, N))
+    for m in range(M):
+        for i in range(N):
+            x = obs[:, i]
+            g = -(x - locs[m, i]) / (variances[m, i] * variances[m, i])
+            ksd[m, i] = ksd_imq(x, g)
+    with np.errstate(over="ignore", invalid="ignore", divide="ignore"):
+        inv = 1.0 / ksd
+        return inv / inv.sum(axis=0), ksd
+
+
 def inverse_square_weights(model_means, obs_mean):
     """``InverseSquareWeight._compute``, ensembles/weights.py:158-169: ``(mean_r model - mean_r obs)^-2``
     normalised over models.  ``model_means [M,N]``, ``obs_mean [N]``."""

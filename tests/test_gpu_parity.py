@@ -617,6 +617,25 @@ def test_crps_weights_vs_oracle(backend):
         assert np.abs(w[c].cpu().numpy().sum(axis=0) - 1.0).max() < 1e-12
 
 
+def test_ksd_weights_vs_oracle(backend):
+    """KSDWeight (weights.py:336-441): IMQ kernel Stein discrepancy per model and point."""
+    rng = np.random.default_rng(4)
+    C, M, Ro, N = 2, 5, 6, 43
+    loc = rng.normal(size=(C, M, N))
+    var = rng.uniform(0.05, 0.6, size=(C, M, N))  # passed as the SCALE (quirk Q-SCALE)
+    obs = rng.normal(size=(C, Ro, N))
+    w, k = backend.ksd_weights(_t(backend, loc), _t(backend, var), _t(backend, obs), want_ksd=True)
+    for c in range(C):
+        wo, ko = rp.ksd_weights(loc[c], var[c], obs[c])
+        assert rel_err(k[c].cpu().numpy(), ko) < 1e-12
+        assert rel_err(w[c].cpu().numpy(), wo) < 1e-12
+        assert np.abs(w[c].cpu().numpy().sum(axis=0) - 1.0).max() < 1e-12
+    # a single observation realisation: k0(a, a) = g^2 + 1
+    w1, k1 = backend.ksd_weights(_t(backend, loc), _t(backend, var), _t(backend, obs[:, :1]), want_ksd=True)
+    g = -(obs[:, :1] - loc) / var ** 2
+    assert rel_err(k1.cpu().numpy(), np.sqrt(g * g + 1.0)) < 1e-14
+
+
 def test_similarity_weights_vs_oracle(backend):
     mus, covs = _posterior_covs(4, 5, 30, seed=17)
     M = 4
@@ -660,7 +679,7 @@ def test_reference_weight_classes_shapes_and_sums(backend):
     mus = np.stack([m.distribution._dist.mean() for m in mc])
     covs = np.stack([m.distribution._dist.covariance() for m in mc])
     var = np.stack([m.distribution._dist.variance() for m in mc])
-    for cls, kwargs in ((es.InverseSquareWeight, {}), (es.UniformWeight, {}), (es.CRPSWeight, {}),
+    for cls, kwargs in ((es.InverseSquareWeight, {}), (es.UniformWeight, {}), (es.CRPSWeight, {}), (es.KSDWeight, {}),
                         (es.ModelSimilarityWeight, {"mode": "temporal"})):
         w = cls()(mc, obs_pm, **kwargs)
         assert w.shape == (M, T), cls
@@ -669,6 +688,8 @@ def test_reference_weight_classes_shapes_and_sums(backend):
     assert rel_err(wc, rp.crps_weights(mus, var, obs)[0]) < 1e-10
     ws = es.ModelSimilarityWeight()(mc, mode="temporal").values
     assert rel_err(ws, rp.model_similarity_weights_temporal(mus, var)[0]) < 1e-10
+    wk = es.KSDWeight()(mc, obs_pm).values
+    assert rel_err(wk, rp.ksd_weights(mus, var, obs)[0]) < 1e-10
     w1 = es.ModelSimilarityWeight()(mc, mode="single")
     assert w1.shape == (M, 1) and w1.dims == ("model", "time")
     assert rel_err(w1.values[:, 0], rp.model_similarity_weights_single(mus, covs)[0]) < 1e-8

@@ -216,3 +216,24 @@ def test_next_row_weights_normalise_over_models():
     S = [np.diag(v) for v in var]
     ws, d = rp.model_similarity_weights_single(list(means), S)
     assert abs(ws.sum() - 1.0) < 1e-12 and np.abs(np.diag(d)).max() < 1e-12
+
+
+def test_ksd_oracle_matches_literal_k0():
+    """ksd_imq (vectorised) against a literal transcription of k_0_fun / imq_KSD (weights.py:360-394)."""
+    def k0(p1, p2, g1, g2, c=1.0, beta=-0.5):
+        diff = p1 - p2
+        dim = p1.shape[0]
+        q = c ** 2 + np.dot(diff, diff)
+        return (np.dot(g1, g2) * q ** beta + -2 * beta * np.dot(g1, diff) * q ** (beta - 1)
+                + 2 * beta * np.dot(g2, diff) * q ** (beta - 1) + -2 * dim * beta * q ** (beta - 1)
+                + -4 * beta * (beta - 1) * q ** (beta - 2) * np.sum(np.square(diff)))
+
+    rng = np.random.default_rng(2)
+    x = rng.normal(size=(7, 1))
+    mu, scale = 0.3, 0.4
+    g = -(x - mu) / scale ** 2  # d/dx log N(x | mu, scale)
+    tot = sum(k0(x[a], x[b], g[a], g[b]) for a in range(7) for b in range(7))
+    assert abs(rp.ksd_imq(x, g) - np.sqrt(tot) / 7) < 1e-13 * np.sqrt(tot)
+    w, k = rp.ksd_weights(np.full((2, 1), mu), np.array([[scale], [2 * scale]]), x)
+    assert abs(k[0, 0] - np.sqrt(tot) / 7) < 1e-13 * np.sqrt(tot)
+    assert abs(w.sum() - 1.0) < 1e-15

@@ -36,6 +36,10 @@ __host__ __device__ constexpr int dtw_min_ctas(int W, int NWARPS) {
     return NWARPS == 1 ? 4 : (NWARPS == 7 || W <= 8) ? 3 : 2;
 }
 
+// (A barrier-free variant was tried for the multi-warp form: neighbouring warps decoupled through a 64-row
+// shared-memory ring, flag and value in one 8-byte word, consumer kept 24 rows behind.  Bit-exact, but 2.5x
+// SLOWER -- 9.5 G instead of 3.8 G warp instructions per launch, a quarter of the stall samples at the
+// shuffle that re-gathers the lanes after the first lane's divergent wait (ncu r01o) -- so the barrier stays.)
 // One pair = (row sequence a = A[pair / R], column sequence x = X[(pair / x_group) * R + pair % R]).
 // NWARPS == 1: one warp per pair, 4 pairs per 128-thread CTA, shuffles only.
 // NWARPS  > 1: one CTA of NWARPS warps per pair.

@@ -106,8 +106,12 @@ int launch_dtw_backtrack_w(be_ctx* ctx, const double* X, int T, int R, int n_pai
                            size_t stride, double* v, double* wx) {
     typedef typename DtwWord<W>::type word_t;
     Prof p(ctx, F_DTW_BACK, 0.0, 40.0 * T * n_pairs);
-    k_dtw_backtrack<W, NW><<<(unsigned)((n_pairs + 3) / 4), 128, 0, ctx->stream>>>(X, T, R, n_pairs, active,
-                                                                                  (const word_t*)dirs, stride, v, wx);
+    if (NW == 1)
+        k_dtw_backtrack_w1<W><<<(unsigned)((n_pairs + 3) / 4), 128, 0, ctx->stream>>>(X, T, R, n_pairs, active,
+                                                                                     (const word_t*)dirs, stride, v, wx);
+    else
+        k_dtw_backtrack<W, NW><<<(unsigned)((n_pairs + 3) / 4), 128, 0, ctx->stream>>>(
+            X, T, R, n_pairs, active, (const word_t*)dirs, stride, v, wx);
     BE_LAUNCHED();
     return BE_OK;
 }
@@ -115,6 +119,14 @@ int launch_dtw_backtrack_w(be_ctx* ctx, const double* X, int T, int R, int n_pai
 int launch_dtw_backtrack(be_ctx* ctx, const DtwShape& shape, const double* X, int T, int R, int n_pairs,
                          const int* active, const void* dirs, size_t stride, double* v, double* wx) {
     BE_DTW_DISPATCH(launch_dtw_backtrack_w, ctx, X, T, R, n_pairs, active, dirs, stride, v, wx);
+}
+
+// table fill + path walk of every (problem, realisation) pair of one DBA iteration
+int dtw_paths(be_ctx* ctx, const DtwShape& shape, int tie, const double* A, const double* X, int T, int R, int n_pairs,
+              const int* active, void* dirs, size_t stride, double* sq, double* v, double* wx) {
+    int rc = launch_dtw_dp(ctx, shape, tie, true, A, X, T, R, R, n_pairs, active, dirs, stride, sq);
+    if (rc != BE_OK) return rc;
+    return launch_dtw_backtrack(ctx, shape, X, T, R, n_pairs, active, dirs, stride, v, wx);
 }
 
 }  // namespace
@@ -174,10 +186,8 @@ int be_dtw_barycenter_averaging_subgradient(be_ctx* ctx, const double* X, int B,
     BE_LAUNCHED();
     double eta = initial_step_size;
     for (int it = 0; it < max_iter; ++it) {
-        if ((rc = launch_dtw_dp(ctx, shape, DTW_TIE_TSLEARN, true, barycenter, X, T, R, R, pairs, w.active, w.dirs,
-                                stride, w.sq)) != BE_OK)
-            return rc;
-        if ((rc = launch_dtw_backtrack(ctx, shape, X, T, R, pairs, w.active, w.dirs, stride, w.v, w.wx)) != BE_OK)
+        if ((rc = dtw_paths(ctx, shape, DTW_TIE_TSLEARN, barycenter, X, T, R, pairs, w.active, w.dirs, stride, w.sq, w.v,
+                            w.wx)) != BE_OK)
             return rc;
         {
             Prof p(ctx, F_DBA_UPDATE, 4.0 * R * T * (double)B, (16.0 * R + 16.0) * T * (double)B);
@@ -221,10 +231,8 @@ int be_perform_dba(be_ctx* ctx, const double* X, int B, int R, int T, int n_iter
     k_dba_medoid<<<B, 256, 0, ctx->stream>>>(X, w.sq, T, R, center, medoid);
     BE_LAUNCHED();
     for (int it = 0; it < n_iterations; ++it) {
-        if ((rc = launch_dtw_dp(ctx, shape, DTW_TIE_DTWA, true, center, X, T, R, R, pairs, nullptr, w.dirs, stride,
-                                w.sq)) != BE_OK)
-            return rc;
-        if ((rc = launch_dtw_backtrack(ctx, shape, X, T, R, pairs, nullptr, w.dirs, stride, w.v, w.wx)) != BE_OK)
+        if ((rc = dtw_paths(ctx, shape, DTW_TIE_DTWA, center, X, T, R, pairs, nullptr, w.dirs, stride, w.sq, w.v,
+                            w.wx)) != BE_OK)
             return rc;
         Prof p(ctx, F_DBA_UPDATE, 2.0 * R * T * (double)B, (16.0 * R + 8.0) * T * (double)B);
         k_dba_mean_update<<<grid1d((size_t)B * T, 256), 256, 0, ctx->stream>>>(center, w.v, w.wx, B, T, R);

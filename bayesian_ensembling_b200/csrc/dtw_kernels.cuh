@@ -29,6 +29,40 @@ template <> struct DtwWord<8> { typedef uint16_t type; };
 __host__ __device__ inline int dtw_threads_used(int T, int W) { return (T + W - 1) / W; }
 __host__ __device__ inline int dtw_steps(int T, int W) { return T + dtw_threads_used(T, W) - 1; }
 
+// One row of the table for the W columns a thread owns: up[] (the previous row) is replaced by this row, left
+// enters as cost[i, j0-1] and leaves as cost[i, j0+W-1], diag enters as cost[i-1, j0-1]; returns the W 2-bit
+// argmin codes (0 diag, 1 top = (i-1, j), 2 left = (i, j-1)).
+template <int W, int TIE>
+__device__ __forceinline__ unsigned dtw_row(double ai, const double (&xj)[W], double (&up)[W], double& left,
+                                            double diag) {
+    unsigned codes = 0;
+#pragma unroll
+    for (int k = 0; k < W; ++k) {
+        const double diff = __dsub_rn(ai, xj[k]);
+        const double d = __dmul_rn(diff, diff);
+        const double top = up[k];
+        double m;
+        unsigned code;
+        if (TIE == DTW_TIE_TSLEARN) {
+            m = diag; code = 0;
+            if (top < m) { m = top; code = 1; }
+            if (left < m) { m = left; code = 2; }
+        } else {
+            if (diag <= left) {
+                if (diag <= top) { m = diag; code = 0; } else { m = top; code = 1; }
+            } else {
+                if (left <= top) { m = left; code = 2; } else { m = top; code = 1; }
+            }
+        }
+        const double cur = __dadd_rn(m, d);
+        diag = top;
+        up[k] = cur;
+        left = cur;
+        codes |= code << (2 * k);
+    }
+    return codes;
+}
+
 // resident CTAs per SM the DP kernel is compiled for: the kernel is issue-bound, so what matters is that
 // the register budget leaves no spill and that the CTAs of a launch fill the SMs without a long tail
 // (T = 3012: 14 columns x 7 warps -> 94 registers x 224 threads -> 3 CTAs per SM)
@@ -87,33 +121,8 @@ k_dtw_dp(const double* __restrict__ A, const double* __restrict__ X, int T, int 
         if (t == 0) in = INF;
         const int i = s - t;
         if (i >= 0 && i < T && t < nthr) {
-            const double ai = a_cur;
-            double left = in, diag = diag_in;
-            unsigned codes = 0;
-#pragma unroll
-            for (int k = 0; k < W; ++k) {
-                const double diff = __dsub_rn(ai, xj[k]);
-                const double d = __dmul_rn(diff, diff);
-                const double top = up[k];
-                double m;
-                unsigned code;
-                if (TIE == DTW_TIE_TSLEARN) {
-                    m = diag; code = 0;
-                    if (top < m) { m = top; code = 1; }
-                    if (left < m) { m = left; code = 2; }
-                } else {
-                    if (diag <= left) {
-                        if (diag <= top) { m = diag; code = 0; } else { m = top; code = 1; }
-                    } else {
-                        if (left <= top) { m = left; code = 2; } else { m = top; code = 1; }
-                    }
-                }
-                const double cur = __dadd_rn(m, d);
-                diag = top;
-                up[k] = cur;
-                left = cur;
-                codes |= code << (2 * k);
-            }
+            double left = in;
+            const unsigned codes = dtw_row<W, TIE>(a_cur, xj, up, left, diag_in);
             out = left;
             diag_in = in;
             if (DIRS) drow[(size_t)s * NT] = (word_t)codes;
@@ -131,6 +140,84 @@ k_dtw_dp(const double* __restrict__ A, const double* __restrict__ X, int T, int 
         if (NWARPS > 1) {
             if (lane == 31) edge[s & 1][warp] = out;
             __syncthreads();
+        }
+    }
+}
+
+// Path walk for the one-warp-per-pair shapes (T <= 512).  In the step-major layout the words of 32 consecutive
+// steps of a pair are one contiguous block (32 steps x 32 lanes x 1/2/4 bytes), so the warp copies such a
+// block to shared memory with fully used 128-byte lines and walks inside it -- a move lowers the step index
+// i + j/W by at most two, so a block lasts for at least 16 moves and typically ~40.  With the block copy
+// batched and x in a register window the kernel is ISSUE-bound (ncu r01o: issue active 80 %, ~50 warp
+// instructions per move, every lane walking the same path); a lane-per-pair walk would use the lanes but
+// turn every move into a dependent L2 round trip, which only pays with >= 10^4 pairs in flight -- not done.
+// (A fused fill+walk kernel with the words of the whole pair in shared memory was slower: 18 KB per pair
+// leaves 12 warps per SM for the issue-bound fill.)
+template <int W>
+__global__ void __launch_bounds__(128)
+k_dtw_backtrack_w1(const double* __restrict__ X, int T, int R, int n_pairs, const int* __restrict__ active,
+                   const typename DtwWord<W>::type* __restrict__ dirs, size_t dirs_stride, double* __restrict__ v,
+                   double* __restrict__ wx) {
+    typedef typename DtwWord<W>::type word_t;
+    __shared__ __align__(16) word_t win[4][32 * 32];
+    const int lane = threadIdx.x & 31;
+    const int wslot = threadIdx.x >> 5;
+    const int pair = blockIdx.x * 4 + wslot;
+    if (pair >= n_pairs) return;
+    if (active && !active[pair / R]) return;
+    const double* x = X + (size_t)pair * T;
+    const word_t* d = dirs + (size_t)pair * dirs_stride;
+    double* vo = v + (size_t)pair * T;
+    double* wo = wx + (size_t)pair * T;
+    word_t* wn = win[wslot];
+    int i = T - 1, j = T - 1;
+    double acc = 0.0, cnt = 0.0;
+    // x[j] comes from a 32-wide register window (lane l holds x[jw - l]) refilled by one coalesced load: a
+    // dependent global load per move would stall the in-order warp for an L2 round trip every step
+    int jw = j;
+    double xw = (jw - lane >= 0) ? x[jw - lane] : 0.0;
+    for (;;) {
+        const int s_hi = i + j / W;            // step index of the current cell
+        const int s_lo = max(s_hi - 31, 0);    // block = steps s_lo .. s_hi
+        __syncwarp();
+        {   // all of a lane's 16-byte pieces are requested before the first is stored: one memory latency per block
+            constexpr int PIECES = 2 * (int)sizeof(word_t);  // 32 steps x 32 lanes x sizeof(word) / 16 B / 32 lanes
+            const int n_pieces = (s_hi - s_lo + 1) * 2 * (int)sizeof(word_t);
+            const uint4* src = reinterpret_cast<const uint4*>(d + (size_t)s_lo * 32);
+            uint4* dst = reinterpret_cast<uint4*>(wn);
+            uint4 tmp[PIECES];
+#pragma unroll
+            for (int k = 0; k < PIECES; ++k)
+                if (k * 32 + lane < n_pieces) tmp[k] = src[k * 32 + lane];
+#pragma unroll
+            for (int k = 0; k < PIECES; ++k)
+                if (k * 32 + lane < n_pieces) dst[k * 32 + lane] = tmp[k];
+        }
+        __syncwarp();
+        bool done = false;
+        for (;;) {
+            if (j < jw - 31) {
+                jw = j;
+                xw = (jw - lane >= 0) ? x[jw - lane] : 0.0;
+            }
+            cnt += 1.0;
+            acc = __dadd_rn(acc, __shfl_sync(0xffffffffu, xw, jw - j));
+            if (i == 0 && j == 0) { done = true; break; }
+            const int t = j / W;
+            const unsigned code = ((unsigned)wn[(i + t - s_lo) * 32 + t] >> (2 * (j - t * W))) & 3u;
+            const int ni = i - (code != 2u), nj = j - (code != 1u);
+            if (ni != i) {
+                if (lane == 0) { vo[i] = cnt; wo[i] = acc; }
+                cnt = 0.0;
+                acc = 0.0;
+            }
+            i = ni;
+            j = nj;
+            if (i + j / W < s_lo) break;
+        }
+        if (done) {
+            if (lane == 0) { vo[0] = cnt; wo[0] = acc; }
+            break;
         }
     }
 }
@@ -157,6 +244,8 @@ k_dtw_backtrack(const double* __restrict__ X, int T, int R, int n_pairs, const i
     double* wo = wx + (size_t)pair * T;
     int i = T - 1, j = T - 1;
     double acc = 0.0, cnt = 0.0;
+    int jw = j;  // 32-wide register window of x (see k_dtw_backtrack_w1)
+    double xw = (jw - lane >= 0) ? x[jw - lane] : 0.0;
     for (;;) {
         const int i0 = i, t0 = j / W;
         const int row = i0 - lane;
@@ -167,8 +256,12 @@ k_dtw_backtrack(const double* __restrict__ X, int T, int R, int n_pairs, const i
         }
         bool done = false;
         for (;;) {
+            if (j < jw - 31) {
+                jw = j;
+                xw = (jw - lane >= 0) ? x[jw - lane] : 0.0;
+            }
             cnt += 1.0;
-            acc = __dadd_rn(acc, x[j]);
+            acc = __dadd_rn(acc, __shfl_sync(0xffffffffu, xw, jw - j));
             if (i == 0 && j == 0) { done = true; break; }
             const int t = j / W;
             const unsigned word = __shfl_sync(0xffffffffu, (t == t0) ? wA : wB, i0 - i);

@@ -45,6 +45,8 @@ SIGNATURES = {
     "be_potrf_batched": (_I, [_P, _P, _I, _I, _P, _P, _P, _Z]),
     "be_gp_posterior_workspace_bytes": (_Z, [_I, _I, _I]),
     "be_gp_posterior": (_I, [_P, _P, _P, _P, _P, _P, _D, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _Z]),
+    "be_gp_posterior_factored_workspace_bytes": (_Z, [_I, _I, _I]),
+    "be_gp_posterior_factored": (_I, [_P, _P, _P, _P, _P, _P, _D, _I, _I, _I, _P, _P, _P, _P, _P, _P, _Z]),
     "be_vgp_fit_workspace_bytes": (_Z, [_I, _I, _I]),
     "be_vgp_fit": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _D, _D, _I, _D, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _Z]),
     "be_mvn_from_cov_workspace_bytes": (_Z, [_I, _I]),

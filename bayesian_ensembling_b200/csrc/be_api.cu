@@ -581,6 +581,108 @@ int be_gp_posterior(be_ctx* ctx, const double* X, const double* y_mean, const do
     return BE_OK;
 }
 
+/* Same inputs and (mu, var_diag, mvn_stats, info) outputs as be_gp_posterior without the dense cov / scale_tri:
+ * the posterior covariance stays in factored form (Woodbury), T^3 instead of 4/3 T^3 tensor flops. */
+size_t be_gp_posterior_factored_workspace_bytes(int B, int T, int R) {
+    return be_gp_posterior_workspace_bytes(B, T, R) + 3 * align_up((size_t)B * T * 8, 256) +
+           3 * align_up((size_t)B * 4 * 8, 256);
+}
+
+int be_gp_posterior_factored(be_ctx* ctx, const double* X, const double* y_mean, const double* y_var,
+                             const double* variance, const double* lengthscale, double jitter, int B, int T, int R,
+                             double* mu, double* var_diag, double* mvn_stats, int* info_fit, int* info_dist,
+                             void* workspace, size_t workspace_bytes) {
+    if (!ctx) return -1;
+    if (!X) return -2;
+    if (!y_mean) return -3;
+    if (!y_var) return -4;
+    if (!variance) return -5;
+    if (!lengthscale) return -6;
+    if (!(jitter >= 0.0)) return -7;
+    if (B <= 0) return -8;
+    if (T <= 0) return -9;
+    if (R <= 0 || matern_smem(R) > 200 * 1024) return -10;
+    if (!mu) return -11;
+    if (!var_diag) return -12;
+    if (!mvn_stats) return -13;
+    if (!info_fit) return -14;
+    if (!info_dist) return -15;
+    if (!workspace || workspace_bytes < be_gp_posterior_factored_workspace_bytes(B, T, R)) return BE_ERR_WORKSPACE;
+    const int Tp = pad_dim(T), ld = Tp, nblk = num_blocks(Tp);
+    Carver cv(workspace, workspace_bytes);
+    double* Mw = cv.take<double>(padded_matrix_doubles(B, T));  // M -> C, then N -> L_N
+    double* Vw = cv.take<double>(padded_matrix_doubles(B, T));  // V = C^-T
+    double* Dinv = cv.take<double>(dinv_doubles(B, T));
+    double* Pbuf = cv.take<double>(pbuf_doubles(B, T));
+    double* u = cv.take<double>((size_t)B * Tp);
+    double* nvar = cv.take<double>((size_t)B * T);
+    double* g = cv.take<double>((size_t)B * T);
+    double* gmu = cv.take<double>((size_t)B * T);
+    double* base = cv.take<double>((size_t)B * 4);
+    double* statsC = cv.take<double>((size_t)B * 4);
+    double* statsN = cv.take<double>((size_t)B * 4);
+    if (!Mw || !Vw || !Dinv || !Pbuf || !u || !nvar || !g || !gmu || !base || !statsC || !statsN) return BE_ERR_WORKSPACE;
+    BE_CUDA(cudaMemsetAsync(info_fit, 0, sizeof(int) * B, ctx->stream));
+    BE_CUDA(cudaMemsetAsync(info_dist, 0, sizeof(int) * B, ctx->stream));
+    const int ntl = nblk * (nblk + 1) / 2;
+    const double dT = (double)T, dB = (double)B;
+    // 1-2. M = K + E = C C^T, u = C^-1 y rides along; sum log diag C
+    {
+        Prof pr(ctx, F_GRAM, dB * 0.5 * dT * dT * (2.0 * R + 12.0), (dB * dT * R + dB * 0.5 * dT * dT) * 8);
+        k_matern32<1><<<(unsigned)((size_t)ntl * B), 256, matern_smem(R), ctx->stream>>>(
+            X, B, T, R, variance, lengthscale, y_mean, y_var, jitter, Mw, Tp, ld, ntl);
+        BE_LAUNCHED();
+    }
+    int rc = potrf_padded(ctx, Mw, Tp, T, B, Dinv, Pbuf, Vw, info_fit);
+    if (rc != BE_OK) return rc;
+    {
+        Prof pr(ctx, F_COPY, 0.0, dB * dT * 16);
+        k_extract_row<<<grid1d((size_t)B * T, 256), 256, 0, ctx->stream>>>(Mw, ld, Tp, T, T, u, B, 1);
+        BE_LAUNCHED();
+    }
+    {
+        Prof pr(ctx, F_STATS, 8.0 * dB * dT, dB * 3.0 * dT * 8);
+        k_mvn_stats<<<B, 256, 0, ctx->stream>>>(Mw, ld, Tp, T, statsC);
+        BE_LAUNCHED();
+    }
+    // 3-4. V = C^-T; mean = y - E V u and var_diag = D + E - E^2 diag(V V^T) in one pass over V
+    rc = trtri_padded(ctx, Vw, Mw, Tp, B, Dinv, Pbuf);
+    if (rc != BE_OK) return rc;
+    {
+        Prof pr(ctx, F_MEAN, 2.0 * dB * dT * dT, dB * (0.5 * dT * dT + 5.0 * dT) * 8);
+        k_posterior_mean<<<grid1d((size_t)B * T, 8), 256, 0, ctx->stream>>>(Vw, ld, Tp, T, u, y_mean, y_var, jitter,
+                                                                            mu, B, var_diag);
+        BE_LAUNCHED();
+    }
+    // 5. N = K + diag(E D / E') = L_N L_N^T with the rows (G 1, G mu) riding along
+    {
+        Prof pr(ctx, F_STATS, 12.0 * dB * dT, dB * 5.0 * dT * 8);
+        k_factored_prepare<<<B, 256, 0, ctx->stream>>>(y_var, mu, jitter, T, nvar, g, gmu, base);
+        BE_LAUNCHED();
+    }
+    {
+        Prof pr(ctx, F_GRAM, dB * 0.5 * dT * dT * (2.0 * R + 12.0), (dB * dT * R + dB * 0.5 * dT * dT) * 8);
+        k_matern32<1><<<(unsigned)((size_t)ntl * B), 256, matern_smem(R), ctx->stream>>>(
+            X, B, T, R, variance, lengthscale, g, nvar, 0.0, Mw, Tp, ld, ntl);
+        BE_LAUNCHED();
+    }
+    {
+        Prof pr(ctx, F_COPY, 0.0, dB * dT * 16);
+        k_set_row<<<grid1d((size_t)B * T, 256), 256, 0, ctx->stream>>>(Mw, ld, Tp, T, T + 1, gmu, B);
+        BE_LAUNCHED();
+    }
+    rc = potrf_padded(ctx, Mw, Tp, T, B, Dinv, Pbuf, nullptr, info_dist);
+    if (rc != BE_OK) return rc;
+    {
+        Prof pr(ctx, F_STATS, 8.0 * dB * dT, dB * 3.0 * dT * 8);
+        k_mvn_stats<<<B, 256, 0, ctx->stream>>>(Mw, ld, Tp, T, statsN);
+        BE_LAUNCHED();
+        k_factored_finish<<<grid1d((size_t)B * 4, 128), 128, 0, ctx->stream>>>(statsN, base, statsC, B, mvn_stats);
+        BE_LAUNCHED();
+    }
+    return BE_OK;
+}
+
 size_t be_mvn_from_cov_workspace_bytes(int B, int T) { return be_potrf_workspace_bytes(B, T); }
 
 int be_mvn_from_cov(be_ctx* ctx, const double* mu, const double* cov, int B, int T, double* scale_tri,

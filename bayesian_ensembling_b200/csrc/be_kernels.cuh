@@ -454,27 +454,96 @@ __global__ void k_extract_row(double* __restrict__ Mat, int ld, int Tp, int T, i
 __global__ void __launch_bounds__(256) k_posterior_mean(const double* __restrict__ V, int ld, int Tp, int T,
                                                         const double* __restrict__ u, const double* __restrict__ y_mean,
                                                         const double* __restrict__ y_var, double jitter,
-                                                        double* __restrict__ mu, int B) {
+                                                        double* __restrict__ mu, int B,
+                                                        double* __restrict__ var_diag = nullptr) {
     int warp_global = blockIdx.x * 8 + (threadIdx.x >> 5);
     int lane = threadIdx.x & 31;
     if (warp_global >= B * T) return;
     int b = warp_global / T, i = warp_global % T;
     const double* row = V + (size_t)b * Tp * ld + (size_t)i * ld;
     const double* ub = u + (size_t)b * T;
-    double s0 = 0.0, s1 = 0.0;
+    double s0 = 0.0, s1 = 0.0, q0 = 0.0, q1 = 0.0;
     int k0 = i & ~1;  // aligned start; element k0 < i (if any) is an explicit zero of the upper factor
     for (int k = k0 + 2 * lane; k < T; k += 64) {
         double2 v = *reinterpret_cast<const double2*>(row + k);
-        if (k >= i) s0 += v.x * ub[k];
-        if (k + 1 < T && k + 1 >= i) s1 += v.y * ub[k + 1];
+        if (k >= i) {
+            s0 += v.x * ub[k];
+            q0 = fma(v.x, v.x, q0);
+        }
+        if (k + 1 < T && k + 1 >= i) {
+            s1 += v.y * ub[k + 1];
+            q1 = fma(v.y, v.y, q1);
+        }
     }
-    double s = s0 + s1;
+    double s = s0 + s1, q = q0 + q1;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    for (int o = 16; o > 0; o >>= 1) {
+        s += __shfl_xor_sync(0xffffffffu, s, o);
+        q += __shfl_xor_sync(0xffffffffu, q, o);
+    }
     if (lane == 0) {
         size_t g = (size_t)b * T + i;
-        mu[g] = y_mean[g] - (y_var[g] + jitter) * s;
+        const double E = y_var[g] + jitter;
+        mu[g] = y_mean[g] - E * s;
+        // factored mode: cov_ii = D + E - E^2 (M^-1)_ii with (M^-1)_ii = |row i of V|^2
+        if (var_diag) var_diag[g] = (y_var[g] + E) - E * E * q;
     }
+}
+
+// ---- factored posterior (be_gp_posterior_factored): cov = E' - E M^-1 E is never formed.  Woodbury:
+//   cov^-1 = E'^-1 + G N^-1 G,  det cov = det N det E' / det M,  E' = D + E,  G = E / E',  N = K + diag(E D / E').
+// k_factored_prepare: per problem the diagonal n = E D / E' of N, the right-hand sides g = G 1 and g*mu that
+// ride along in chol(N), and the diagonal parts of the four statistics:
+//   base = (sum 1/E', sum mu/E', sum mu^2/E', 1/2 sum log E').  One CTA per problem.
+__global__ void __launch_bounds__(256) k_factored_prepare(const double* __restrict__ y_var, const double* __restrict__ mu,
+                                                          double jitter, int T, double* __restrict__ nvar,
+                                                          double* __restrict__ g, double* __restrict__ gmu,
+                                                          double* __restrict__ base) {
+    __shared__ double red[4][8];
+    const int b = blockIdx.x;
+    double v[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int j = threadIdx.x; j < T; j += 256) {
+        const size_t o = (size_t)b * T + j;
+        const double D = y_var[o], E = D + jitter, Ep = D + E, m = mu[o];
+        nvar[o] = E * D / Ep;
+        const double gg = E / Ep;
+        g[o] = gg;
+        gmu[o] = gg * m;
+        v[0] += 1.0 / Ep;
+        v[1] += m / Ep;
+        v[2] += m * m / Ep;
+        v[3] += 0.5 * log(Ep);
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v[q] += __shfl_xor_sync(0xffffffffu, v[q], o);
+        if ((threadIdx.x & 31) == 0) red[q][threadIdx.x >> 5] = v[q];
+    }
+    __syncthreads();
+    if (threadIdx.x < 4) {
+        double s = 0;
+        for (int w = 0; w < 8; ++w) s += red[threadIdx.x][w];
+        base[(size_t)b * 4 + threadIdx.x] = s;
+    }
+}
+
+// padded row `row` (cols < T) := src[b, 0:T]
+__global__ void k_set_row(double* __restrict__ Mat, int ld, int Tp, int T, int row, const double* __restrict__ src, int B) {
+    size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= (size_t)B * T) return;
+    int b = (int)(gid / T), j = (int)(gid % T);
+    Mat[(size_t)b * Tp * ld + (size_t)row * ld + j] = src[gid];
+}
+
+// mvn_stats = base + (|a'|^2, a'.b', |b'|^2, sum log diag L_N) - (0, 0, 0, sum log diag C)
+__global__ void k_factored_finish(const double* __restrict__ statsN, const double* __restrict__ base,
+                                  const double* __restrict__ statsC, int B, double* __restrict__ stats) {
+    int gid = blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= B * 4) return;
+    double v = base[gid] + statsN[gid];
+    if ((gid & 3) == 3) v -= statsC[gid];
+    stats[gid] = v;
 }
 
 // mvn_stats[b] = (|a|^2, a.b, |b|^2, sum log diag L) from rows T, T+1 and the diagonal

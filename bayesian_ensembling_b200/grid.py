@@ -60,14 +60,23 @@ def wave_size(be: Backend, C: int, M: int, R: int, T: int, keep_posteriors: bool
 
 def fit_weight_barycentre(realisations, observations, variance, lengthscale, *, jitter=DEFAULT_JITTER,
                           standardisation_constant=1.0, time_mean_weights=False, keep_posteriors=False,
-                          cells_per_wave=None, tolerance=1e-6, init_var=1.0, y_mean="mean") -> CellBatchResult:
+                          cells_per_wave=None, tolerance=1e-6, init_var=1.0, y_mean="mean",
+                          posterior="dense") -> CellBatchResult:
     """realisations [C,M,R,T], observations [C,Ro,T] (host arrays or device tensors);
     variance / lengthscale: scalar, [M] or [C,M] kernel hyper-parameters (fixed-theta posterior,
     the fixed point of models.py:208-215).  Order of operations follows
     ``PerfectModelTest._run_single_test`` (utils.py:102-135); ``time_mean_weights`` reproduces
     utils.py:111,133 (NaN-skipping mean over time, broadcast back).  ``y_mean``: "mean" = arithmetic
     mean over realisations (the y_mean-given path BASELINE's metric is quoted on), "dba" = the DTW
-    barycentre average of models.py:176-178 computed on the device, or a [C,M,T] array."""
+    barycentre average of models.py:176-178 computed on the device, or a [C,M,T] array.
+    ``posterior``: "dense" forms every member's T x T covariance and its Cholesky factor as the
+    reference does (data.py:38-39); "factored" keeps the covariance in Woodbury form and returns the
+    same weights / barycentre / posterior mean and variance at 3/4 of the flops
+    (``be_gp_posterior_factored``; not available with ``keep_posteriors``)."""
+    if posterior not in ("dense", "factored"):
+        raise ValueError(f"posterior must be 'dense' or 'factored', got {posterior!r}")
+    if posterior == "factored" and keep_posteriors:
+        raise ValueError("posterior='factored' does not form the dense covariance keep_posteriors asks for")
     be = Backend.get()
     r = be._in(realisations)
     o = be._in(observations)
@@ -89,8 +98,11 @@ def fit_weight_barycentre(realisations, observations, variance, lengthscale, *, 
                 raise ValueError(f"y_mean must be 'mean', 'dba' or an array, got {y_mean!r}")
         else:
             ym = be._in(y_mean, (C, M, T), "y_mean")[c0:c1].reshape(Cw * M, T)
-        post = be.gp_posterior(X, ym, yv, var[c0 * M:c1 * M], ls[c0 * M:c1 * M], jitter,
-                               want_cov=keep_posteriors, want_scale_tri=keep_posteriors)
+        if posterior == "factored":
+            post = be.gp_posterior_factored(X, ym, yv, var[c0 * M:c1 * M], ls[c0 * M:c1 * M], jitter)
+        else:
+            post = be.gp_posterior(X, ym, yv, var[c0 * M:c1 * M], ls[c0 * M:c1 * M], jitter,
+                                   want_cov=keep_posteriors, want_scale_tri=keep_posteriors)
         w = be.loglik_weights_mvn(post.mvn_stats, o[c0:c1], M, standardisation_constant)
         w_used = be.weights_time_mean(w) if time_mean_weights else w
         mu3, var3 = post.mu.view(Cw, M, T), post.var_diag.view(Cw, M, T)

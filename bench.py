@@ -449,6 +449,33 @@ def run_ours(args, cfg):
     if args.hbm_points > 0 and rank == 0:
         hbm_stages = measure_hbm_stages(be, cfg, args.hbm_points, hbm_peak)
 
+    # ---- the same step with the posterior covariance kept in factored (Woodbury) form ------------------
+    # (not the headline: BASELINE's config names a full-covariance posterior per member, which this mode never
+    # forms; weights, barycentre, posterior mean and variance agree with the dense path to ~1e-14)
+    factored = None
+    if args.factored_steps > 0:
+        def step_factored():
+            return grid.fit_weight_barycentre(r_dev, o_dev, var, ls, cells_per_wave=cps, posterior="factored")
+
+        for _ in range(2):
+            rf = step_factored()
+        barrier()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        for _ in range(args.factored_steps):
+            rf = step_factored()
+        g1.record()
+        barrier()
+        ms_f = max_over_ranks(g0.elapsed_time(g1))
+        dmu = float((rf.mu - res.mu).abs().max() / res.mu.abs().max())
+        dvar = float((rf.var_diag - res.var_diag).abs().max() / res.var_diag.abs().max())
+        factored = {"value": world * cps * args.factored_steps / (ms_f * 1e-3), "unit": UNIT,
+                    "ms_per_step": ms_f / args.factored_steps, "steps": args.factored_steps,
+                    "tensor_flops_per_member": "T^3 (chol M, triangular inverse, chol N) instead of 4/3 T^3",
+                    "max_rel_diff_vs_dense": {"posterior_mean": dmu, "posterior_variance": dvar},
+                    "note": "grid.fit_weight_barycentre(..., posterior='factored') -> be_gp_posterior_factored; "
+                            "optional mode, NOT the headline value"}
+
     dba = None
     if args.dba_iters > 0 and rank == 0:
         dba = measure_dba(be, r_dev, cfg, ms / args.steps, args.dba_iters, world == 1 and not args.no_cpu_baseline)
@@ -487,6 +514,7 @@ def run_ours(args, cfg):
             "stages": stages,
             "l2_training_loop": l2,
             "hbm_stages": hbm_stages,
+            "factored_posterior": factored,
             "dtw_barycentre_averaging": dba,
             "cpu_baseline": cpu_baseline,
         }
@@ -507,6 +535,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--hbm-points", type=int, default=4_000_000,
                     help="(cell, time) points of the stand-alone memory-bound stage measurements (0: skip)")
+    ap.add_argument("--factored-steps", type=int, default=3,
+                    help="steps timed for the factored_posterior line (0: skip)")
     ap.add_argument("--dba-iters", type=int, default=50,
                     help="max_iter of the stand-alone DTW-barycentre-averaging measurement (0: skip)")
     ap.add_argument("--l2-iters", type=int, default=3, help="training-loop iterations timed for the l2_training_loop line (0: skip)")

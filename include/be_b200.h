@@ -114,6 +114,20 @@ int be_vgp_fit(be_ctx* ctx, const double* X, const double* y_mean, const double*
                double* mu, double* var_diag, double* cov, double* scale_tri, double* mvn_stats,
                int* info_fit, int* info_dist, void* workspace, size_t workspace_bytes);
 
+/* be_gp_posterior_factored: the same fixed-theta posterior (a1 + a3) for callers that need only what
+ * LogLikelihoodWeight (weights.py:97-100) and Barycentre (ensemble_scheme.py:63-65) consume -- mu [B,T],
+ * var_diag [B,T] = diag(cov), mvn_stats [B,4] -- and not the dense cov / scale_tri.  The covariance
+ * cov = E' - E M^-1 E (E = diag(y_var) + jitter I, E' = diag(y_var) + E, M = K + E) is kept in factored form:
+ * cov^-1 = E'^-1 + G N^-1 G and det cov = det N det E' / det M with G = E E'^-1, N = K + diag(E D / E')
+ * (Woodbury), so the statistics come from chol(M), its triangular inverse and chol(N): T^3 tensor flops per
+ * problem instead of 4/3 T^3.  Agreement with be_gp_posterior: ~1e-12 relative (tests/test_gpu_parity.py).
+ * info_dist reports chol(N). */
+size_t be_gp_posterior_factored_workspace_bytes(int B, int T, int R);
+int be_gp_posterior_factored(be_ctx* ctx, const double* X, const double* y_mean, const double* y_var,
+                             const double* variance, const double* lengthscale, double jitter,
+                             int B, int T, int R, double* mu, double* var_diag, double* mvn_stats,
+                             int* info_fit, int* info_dist, void* workspace, size_t workspace_bytes);
+
 /* ---- a3: Distribution(mu, cov, MultivariateNormalFullCovariance), data.py:38-39 ---------
  * from an arbitrary covariance: scale_tri, diag and the log-prob statistics. */
 size_t be_mvn_from_cov_workspace_bytes(int B, int T);

@@ -92,6 +92,46 @@ def test_potrf_reports_non_pd_like_lapack(backend):
     assert info.cpu().numpy().tolist() == [0, 141]
 
 
+@pytest.mark.parametrize("T,R,M", [(3, 2, 2), (24, 3, 5), (126, 4, 2), (165, 10, 4), (251, 3, 3), (300, 5, 2)])
+def test_gp_posterior_factored_vs_dense_and_oracle(backend, T, R, M):
+    """be_gp_posterior_factored (Woodbury form, no dense covariance) returns the same mean, variance and
+    constant-vector statistics as the dense path and the oracle."""
+    reals, obs = _cell(M, R, T, 4, seed=T * 3 + R)
+    X, ym, yv = backend.gpdtw1d_inputs(_t(backend, reals))
+    var, ls = np.full(M, 0.5), np.linspace(4.0, 8.0, M)
+    dense = backend.gp_posterior(X, ym, yv, var, ls, want_cov=False, want_scale_tri=False)
+    fac = backend.gp_posterior_factored(X, ym, yv, var, ls)
+    assert int(fac.info_fit.abs().sum()) == 0 and int(fac.info_dist.abs().sum()) == 0
+    assert rel_err(fac.mu.cpu().numpy(), dense.mu.cpu().numpy()) <= 1e-13
+    assert rel_err(fac.var_diag.cpu().numpy(), dense.var_diag.cpu().numpy()) <= 1e-10
+    sd, sf = dense.mvn_stats.cpu().numpy(), fac.mvn_stats.cpu().numpy()
+    assert np.abs(sf - sd).max() <= 1e-9 * np.abs(sd).max()
+    ob = _t(backend, obs[None])
+    wd = backend.loglik_weights_mvn(dense.mvn_stats, ob, M).cpu().numpy()
+    wf = backend.loglik_weights_mvn(fac.mvn_stats, ob, M).cpu().numpy()
+    _nan_equal_close(wf, wd, TOL_WEIGHTS, "weights from factored statistics")
+    for m in range(M):
+        Xo, yo, so = rp.gpdtw1d_inputs(reals[m])
+        mu_o, cov_o = rp.gp_posterior_closed_form(Xo, yo, so, var[m], ls[m])
+        assert rel_err(fac.mu[m].cpu().numpy(), mu_o) <= TOL_POSTERIOR
+        assert rel_err(fac.var_diag[m].cpu().numpy(), np.diag(cov_o)) <= TOL_POSTERIOR
+
+
+def test_grid_factored_posterior_equals_dense(backend):
+    from bayesian_ensembling_b200 import grid
+
+    cfg = synthetic.Config("t", 9, 3, 4, 3, 140, 3, False, "")
+    reals, obs = synthetic.make_cells(cfg, seed=5)
+    a = grid.fit_weight_barycentre(reals, obs, 0.5, 6.0)
+    b = grid.fit_weight_barycentre(reals, obs, 0.5, 6.0, posterior="factored")
+    _nan_equal_close(b.weights.cpu().numpy(), a.weights.cpu().numpy(), TOL_WEIGHTS, "weights")
+    _nan_equal_close(b.bary_mu.cpu().numpy(), a.bary_mu.cpu().numpy(), TOL_WEIGHTS, "bary mu")
+    _nan_equal_close(b.bary_std.cpu().numpy(), a.bary_std.cpu().numpy(), TOL_WEIGHTS, "bary std")
+    assert rel_err(b.var_diag.cpu().numpy(), a.var_diag.cpu().numpy()) <= 1e-10
+    with pytest.raises(ValueError):
+        grid.fit_weight_barycentre(reals, obs, 0.5, 6.0, posterior="factored", keep_posteriors=True)
+
+
 def test_golden_scale_tri(backend, golden_members):
     """a3 against the reference's stored distrax factor (pinned parity)."""
     for T in (86, 165):

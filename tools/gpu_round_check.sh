@@ -10,7 +10,7 @@ python bench.py > $out/bench_$tag.json 2> $out/bench_$tag.err; echo "bench rc=$?
 python bench.py --impl reference --steps 2 --warmup 1 > $out/bench_ref_$tag.json 2> $out/bench_ref_$tag.err; echo "ref rc=$?"
 # the profiled command is the step alone (no L2 line, no stand-alone stage measurements), so that the
 # launch list's kernel shares can be compared with the bench line's "stages"
-CMD="python bench.py --steps 2 --warmup 3 --no-cpu-baseline --l2-iters 0 --hbm-points 0 --dba-iters 0"
+CMD="python bench.py --steps 2 --warmup 3 --no-cpu-baseline --l2-iters 0 --hbm-points 0 --dba-iters 0 --factored-steps 0"
 $CMD > $out/plain_$tag.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-file $out/launches_$tag.csv $CMD > $out/ncu_launches_$tag.log 2>&1
 echo "launch list rc=$?"

@@ -656,7 +656,9 @@ __host__ inline size_t weight_stats_bytes(int M) { return (size_t)2 * M * 4 * si
 // copied to shared memory first (read per member from global memory they are a dependent L2 round trip per
 // loop trip: the staging buffer leaves almost no L1).  exp and the division are the library's: variants with
 // a branch-free exp core and a shared-reciprocal division, four members interleaved, measured SLOWER
-// (0.42 against 0.36 ms at 4 M points, 24 members: more registers, fewer resident warps).
+// (0.42 against 0.36 ms at 4 M points, 24 members: more registers, fewer resident warps); so did a form with
+// four lanes per point (each lane a quarter of the members, normaliser by xor-shuffles, full occupancy):
+// 0.58 ms -- the 64-byte row segments it loads and stores quadruple the memory requests.
 __global__ void k_loglik_weights_mvn(const double* __restrict__ stats, const double* __restrict__ obs, int C, int M,
                                      int Ro, int T, double cst, double* __restrict__ w, double* __restrict__ lls_exp,
                                      double* __restrict__ lls_mean, int smem_ok) {

@@ -523,7 +523,16 @@ def run_ours(args, cfg):
         dist.destroy_process_group()
 
 
+def _stdout_json_only():
+    """C libraries (NCCL prints its version banner with printf) share fd 1 with us; the contract is ONE JSON
+    line on stdout.  fd 1 is pointed at stderr and Python's sys.stdout keeps the real stdout."""
+    real = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(real, "w", buffering=1)
+
+
 def main():
+    _stdout_json_only()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)

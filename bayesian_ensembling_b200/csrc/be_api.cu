@@ -114,9 +114,12 @@ struct Prof {
 
 inline unsigned grid1d(size_t n, int block) { return (unsigned)((n + block - 1) / block); }
 
-bool g_attr_done = false;
+// cudaFuncSetAttribute applies to the CURRENT device: once per device, not once per process (a process that
+// opens a ctx on a second device must opt its kernels in there too)
+bool g_attr_done[64] = {};
 int ensure_kernel_attrs(be_ctx* ctx) {
-    if (g_attr_done) return BE_OK;
+    const int slot = ctx->device >= 0 && ctx->device < 64 ? ctx->device : 0;
+    if (g_attr_done[slot]) return BE_OK;
     BE_CUDA(cudaFuncSetAttribute(k_chol_update, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
     BE_CUDA(cudaFuncSetAttribute(k_panel_scale, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
     BE_CUDA(cudaFuncSetAttribute(k_trtri_accum, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
@@ -140,7 +143,7 @@ int ensure_kernel_attrs(be_ctx* ctx) {
     BE_CUDA(cudaFuncSetAttribute(k_ksd_weights, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WEIGHT_STAGE_MAX_BYTES));
     BE_CUDA(cudaFuncSetAttribute(k_w2_collapse, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WEIGHT_STAGE_MAX_BYTES));
     BE_CUDA(cudaFuncSetAttribute(k_similarity_pointwise, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WEIGHT_STAGE_MAX_BYTES));
-    g_attr_done = true;
+    g_attr_done[slot] = true;
     return BE_OK;
 }
 

@@ -798,7 +798,8 @@ __global__ void __launch_bounds__(256) k_weights_time_mean(const double* __restr
 __device__ __forceinline__ void barycentre_iterate(double S_unit /* sum w s, or NaN */, bool use_unit,
                                                    const double* __restrict__ w, const double* __restrict__ var,
                                                    size_t stride, int M, double tol, double init_var, int max_iters,
-                                                   double& sigma, int& iters) {
+                                                   double& sigma, int& iters, bool have_first = false,
+                                                   double first_cand = 0.0) {
     double bv = init_var;
     int n_it = 0;
     while (true) {
@@ -806,11 +807,18 @@ __device__ __forceinline__ void barycentre_iterate(double S_unit /* sum w s, or 
         double sq = sqrt(bv);
         if (use_unit) {
             cand = sq * S_unit;
+        } else if (n_it == 0 && have_first) {
+            cand = first_cand;  // formed by the caller in the pass that also read the means
         } else {
             for (int m = 0; m < M; ++m) cand += w[m * stride] * sq * sqrt(var[m * stride]);
         }
         if (cand - bv < tol) {
             bv = cand;
+            break;
+        }
+        if (cand != cand) {  // NaN never satisfies the signed test and never leaves: the loop would only count to
+            bv = cand;       // max_iters + 1 ("not converged", the reference warns) -- same outputs, no spinning
+            n_it = max_iters + 1;
             break;
         }
         bv = cand;
@@ -829,11 +837,20 @@ __global__ void k_barycentre_1d(const double* __restrict__ means, const double* 
     if (gid >= (size_t)C * N) return;
     int c = (int)(gid / N), i = (int)(gid % N);
     size_t base = (size_t)c * M * N + i;
-    double m_acc = 0.0;
-    for (int m = 0; m < M; ++m) m_acc += weights[base + (size_t)m * N] * means[base + (size_t)m * N];
+    // one pass over the three arrays: the weighted mean (wasserstein.py:98) and the first candidate of the
+    // variance iteration (:85-86), which is also the last one whenever sum w sigma < init_var (quirk Q-BARY)
+    double m_acc = 0.0, cand0 = 0.0;
+    const double sq0 = sqrt(init_var);
+#pragma unroll 4
+    for (int m = 0; m < M; ++m) {
+        const double wm = weights[base + (size_t)m * N];
+        m_acc += wm * means[base + (size_t)m * N];
+        cand0 += wm * sq0 * sqrt(variances[base + (size_t)m * N]);
+    }
     double sg;
     int it;
-    barycentre_iterate(0.0, false, weights + base, variances + base, (size_t)N, M, tol, init_var, max_iters, sg, it);
+    barycentre_iterate(0.0, false, weights + base, variances + base, (size_t)N, M, tol, init_var, max_iters, sg, it, true,
+                       cand0);
     mu[gid] = m_acc;
     sigma[gid] = sg;
     if (iters) iters[gid] = it;

@@ -79,6 +79,8 @@ class Backend:
 
     def _in(self, t, shape=None, name="tensor"):
         if not isinstance(t, torch.Tensor):
+            if hasattr(t, "flags") and not t.flags.writeable:  # broadcast views etc.: torch wants a writable buffer
+                t = t.copy()
             t = torch.as_tensor(t, dtype=torch.float64)
         if t.dtype != torch.float64:
             t = t.to(torch.float64)

@@ -1,3 +1,3 @@
-"""ensembles/utils.py entry points kept by the mirror (checkpoint loading only; ``PerfectModelTest`` is
-orchestration and out of scope)."""
+"""ensembles/utils.py entry points kept by the mirror: checkpoint loading and ``PerfectModelTest``."""
 from .checkpoint import load_model_collection, load_reference_pickle  # noqa: F401
+from .perfect_model import PerfectModelTest  # noqa: F401

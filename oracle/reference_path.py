@@ -572,6 +572,24 @@ def inverse_square_weights(model_means, obs_mean):
         return w / w.sum(axis=0)
 
 
+def perfect_model_metrics(bary_mu, bary_scale, truth_mu, truth_cov, obs, forecast_realisations):
+    """The six metrics of ``PerfectModelTest._run_single_test`` (ensembles/utils.py:139-155).
+    ``bary_mu, bary_scale [T]``: the barycentre ``Distribution``'s loc and the value handed to
+    ``MultivariateNormalDiag`` as ``scale_diag`` (= sigma_bary**2, ensemble_scheme.py:75-78, Q-SCALE);
+    ``truth_mu, truth_cov``: the held-out model's fitted posterior; ``obs [Ro,T]`` its realisations;
+    ``forecast_realisations [sum R, T]`` (:148).  Returns (nll_bary, rmse_bary, w2_bary, nll_mmm, rmse_mmm, w2_mmm)."""
+    obs = np.asarray(obs, dtype=np.float64)
+    nll_bary = -np.mean(mvn_diag_log_prob(bary_mu, bary_scale, obs))                      # :139
+    rmse_bary = np.mean(np.sqrt(np.mean((bary_mu - obs) ** 2, axis=0)))                   # :141
+    w2_bary = gaussian_w2_distance(bary_mu, np.diag(bary_scale ** 2), truth_mu, truth_cov)  # :143-144 (full_cov=True)
+    mmm_mu = np.mean(forecast_realisations, axis=0)
+    mmm_scale = np.var(forecast_realisations, axis=0)                                     # :149 variance as scale
+    nll_mmm = -np.mean(normal_log_prob(mmm_mu, mmm_scale, obs))                           # :150
+    rmse_mmm = np.mean(np.sqrt(np.mean((mmm_mu - obs) ** 2, axis=0)))                     # :152
+    w2_mmm = w2_distance_diag(mmm_mu, mmm_scale ** 2, truth_mu, np.diag(truth_cov))       # :154 (full_cov=False)
+    return nll_bary, rmse_bary, w2_bary, nll_mmm, rmse_mmm, w2_mmm
+
+
 # --------------------------------------------------------------------------------------
 # the whole path for one grid cell (what bench.py's cpu_baseline times)
 # --------------------------------------------------------------------------------------

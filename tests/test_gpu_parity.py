@@ -831,3 +831,55 @@ def test_cfg5_properties_at_size(backend):
     assert int(pd.item()) == 0
     assert rel_err(roots[0].cpu().numpy(), rp.sqrtm_svd(covs[0])) < 1e-9
     assert rel_err(mu[0].cpu().numpy(), (w[:, None] * mus).sum(0)) < 1e-13
+
+
+# ------------------------------------------------------------------------------------ the integration-level caller
+def test_perfect_model_test_end_to_end(backend, tmp_path):
+    """PerfectModelTest (ensembles/utils.py:32-228) through the mirrored API: every held-out model's six metrics
+    against the oracle's composition of the same steps (DBA mean, fixed-theta posterior, LogLikelihoodWeight,
+    time-mean, Barycentre, NLL / RMSE / W2 of barycentre and multi-model mean)."""
+    import functools
+
+    import bayesian_ensembling_b200 as es
+    from bayesian_ensembling_b200 import utils
+    from bayesian_ensembling_b200.labelled import DataArray
+    from oracle import dba
+
+    M, R, Th, Tf = 4, 3, 30, 20
+    # members that differ by less than their internal variability, so that the un-shifted exp of Q-EXP stays finite
+    rng = np.random.default_rng(77)
+    tn = np.linspace(0.0, 1.0, Th + Tf)
+    reals = (1.5 * tn + tn ** 2)[None, None, :] + 0.03 * np.arange(M)[:, None, None] + synthetic._ar1(rng, (M, R, Th + Tf))
+    hind, fore = reals[:, :, :Th], reals[:, :, Th:]
+
+    def coll(block, t0):
+        time = 1900 + t0 + np.arange(block.shape[2])
+        return es.ModelCollection([es.ProcessModel(DataArray(block[m], ("realisation", "time"),
+                                                             {"realisation": np.arange(R), "time": time}), f"model{m}")
+                                   for m in range(M)])
+
+    pmt = utils.PerfectModelTest(coll(hind, 0), coll(fore, Th), functools.partial(es.GPDTW1D, hyperparameters=(0.5, 6.0)),
+                                 es.LogLikelihoodWeight, es.Barycentre, ssp="ssp-test", save_dir=str(tmp_path / "pmt"))
+    res = pmt.run(n_optim_nits=2)
+    assert res["columns"][0] == "model as psuedo obs" and len(res["rows"]) == M
+    assert (tmp_path / "pmt" / "csvs" / "prefect_model_test_results_LogLikelihoodWeight_ssp-test.csv").exists()
+
+    def dba_means(block):
+        return np.stack([dba.dba_subgradient(b, max_iter=50, tol=1e-3)[0] for b in block])
+
+    for i in range(M):
+        others = [m for m in range(M) if m != i]
+        oh = rp.cell_pipeline_L1(hind[others], hind[i], 0.5, 6.0, y_means=dba_means(hind[others]))
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            w_mean = np.nanmean(oh["weights"], axis=1)                                   # utils.py:112
+        of = rp.cell_pipeline_L1(fore[others], fore[i], 0.5, 6.0, y_means=dba_means(fore[others]))
+        var_f = np.asarray([np.diag(c) for c in of["cov"]])
+        bmu, bsd, _ = rp.barycentre_points(of["mu"], var_f, np.broadcast_to(w_mean[:, None], (M - 1, Tf)))  # :133-135
+        Xt, yt, st = rp.gpdtw1d_inputs(fore[i], dba.dba_subgradient(fore[i], max_iter=50, tol=1e-3)[0])
+        t_mu, t_cov = rp.gp_posterior_closed_form(Xt, yt, st, 0.5, 6.0)
+        want = rp.perfect_model_metrics(bmu, bsd ** 2, t_mu, t_cov, fore[i], np.vstack(list(fore[others])))
+        got = res["rows"][i]
+        assert got[0] == f"model{i}" and np.isfinite(want).all()
+        for name, g, w_ in zip(res["columns"][1:], got[1:], want):
+            assert abs(g - w_) <= 1e-6 * max(abs(w_), 1e-12), (i, name, g, w_)

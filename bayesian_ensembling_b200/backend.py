@@ -126,11 +126,11 @@ class Backend:
         return int(self.lib.be_gp_posterior_workspace_bytes(B, T, R))
 
     # ------------------------------------------------------------------ a1
-    def gpdtw1d_inputs(self, realisations):
-        """[B,R,T] -> X [B,T,R], y_mean [B,T], y_var [B,T]   (models.py:175-182)"""
+    def gpdtw1d_inputs(self, realisations, want_X=True):
+        """[B,R,T] -> X [B,T,R] (None unless want_X), y_mean [B,T], y_var [B,T]   (models.py:175-182)"""
         r = self._in(realisations)
         B, R, T = r.shape
-        X, ym, yv = self._new(B, T, R), self._new(B, T), self._new(B, T)
+        X, ym, yv = (self._new(B, T, R) if want_X else None), self._new(B, T), self._new(B, T)
         self._sync_stream()
         rc = self.lib.be_gpdtw1d_inputs(self.ctx, _ptr(r), B, R, T, _ptr(X), _ptr(ym), _ptr(yv))
         _lib.check(self.ctx, rc, "be_gpdtw1d_inputs")

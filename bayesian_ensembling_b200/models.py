@@ -73,3 +73,28 @@ class GPDTW1D:
                     mu=post.mu[k].cpu().numpy(), covariance=post.cov[k].cpu().numpy(), dim_array=blank_array,
                     dist_type=dists.MultivariateNormalFullCovariance, _prebuilt=dev)
         return out
+
+
+class MeanFieldApproximation:
+    """ensembles/models.py:75-131.  The reference initialises ``mean`` / ``variance`` as the mean and the
+    population variance over realisations (:104-105), runs ``n_optim_nits`` Adam steps on a copy of them
+    (:116-121) and then returns the INITIAL values (:126-128: the loop's ``params`` are never read back), as
+    ``Distribution(mu=mean, covariance=variance, dist_type=dx.Normal)`` -- the variance goes in as the scale
+    (quirk Q-SCALE).  The dead loop is not run here; the moments come from the device kernel of
+    models.py:175-182 (``be_gpdtw1d_inputs``) over the flattened trailing dimensions."""
+
+    def __init__(self, name="MeanFieldModel"):
+        self.name = name
+
+    def fit(self, model, optimiser=None, n_optim_nits: int = 500, compile_objective: bool = False):
+        if not optimiser:  # models.py:98-100
+            import warnings
+
+            warnings.warn("No optimiser specified, using Adam with learning rate 0.01")
+        be = Backend.get()
+        reals = np.asarray(model.model_data.values, dtype=np.float64).reshape(model.n_realisations, -1)  # :102-103
+        _, mean, variance = be.gpdtw1d_inputs(be._in(reals[None]), want_X=False)
+        blank_array = ones_like(model.model_data[0].drop_vars("realisation")) * np.nan
+        blank_array = blank_array.rename("blank")
+        return es_data.Distribution(mu=mean[0].cpu().numpy(), covariance=variance[0].cpu().numpy(),
+                                    dim_array=blank_array, dist_type=dists.Normal)

@@ -883,3 +883,23 @@ def test_perfect_model_test_end_to_end(backend, tmp_path):
         assert got[0] == f"model{i}" and np.isfinite(want).all()
         for name, g, w_ in zip(res["columns"][1:], got[1:], want):
             assert abs(g - w_) <= 1e-6 * max(abs(w_), 1e-12), (i, name, g, w_)
+
+
+def test_mean_field_approximation(backend):
+    """models.py:75-131: the returned Distribution holds the INITIAL moments (the Adam loop is dead code)."""
+    import bayesian_ensembling_b200 as es
+    from bayesian_ensembling_b200 import dists
+    from bayesian_ensembling_b200.labelled import DataArray
+
+    rng = np.random.default_rng(6)
+    data = rng.normal(size=(4, 12, 3, 5))  # realisation, time, lat, lon
+    pm = es.ProcessModel(DataArray(data, ("realisation", "time", "latitude", "longitude"),
+                                   {"realisation": np.arange(4), "time": np.arange(12), "latitude": np.arange(3.0),
+                                    "longitude": np.arange(5.0)}), "m")
+    with pytest.warns(UserWarning, match="No optimiser specified"):
+        d = es.MeanFieldApproximation().fit(pm, n_optim_nits=3)
+    assert isinstance(d._dist, dists.Normal)
+    flat = data.reshape(4, -1)
+    assert rel_err(d._dist.mean(), flat.mean(axis=0)) < 1e-15
+    assert rel_err(d._dist.stddev(), flat.var(axis=0)) < 1e-13       # the variance sits in the SCALE slot (Q-SCALE)
+    assert d.mean.shape == (12, 3, 5)

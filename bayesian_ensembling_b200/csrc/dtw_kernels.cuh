@@ -205,7 +205,10 @@ k_dtw_backtrack_w1(const double* __restrict__ X, int T, int R, int n_pairs, cons
             if (i == 0 && j == 0) { done = true; break; }
             const int t = j / W;
             const unsigned code = ((unsigned)wn[(i + t - s_lo) * 32 + t] >> (2 * (j - t * W))) & 3u;
-            const int ni = i - (code != 2u), nj = j - (code != 1u);
+            int ni = i - (code != 2u), nj = j - (code != 1u);
+            // a NaN table (NaN inputs) can record "diag" on a border; keep the walk inside the table
+            if (ni < 0) { ni = 0; nj = j - 1; }
+            if (nj < 0) { nj = 0; ni = i - 1; }
             if (ni != i) {
                 if (lane == 0) { vo[i] = cnt; wo[i] = acc; }
                 cnt = 0.0;
@@ -266,7 +269,10 @@ k_dtw_backtrack(const double* __restrict__ X, int T, int R, int n_pairs, const i
             const int t = j / W;
             const unsigned word = __shfl_sync(0xffffffffu, (t == t0) ? wA : wB, i0 - i);
             const unsigned code = (word >> (2 * (j - t * W))) & 3u;
-            const int ni = i - (code != 2u), nj = j - (code != 1u);
+            int ni = i - (code != 2u), nj = j - (code != 1u);
+            // a NaN table (NaN inputs) can record "diag" on a border; keep the walk inside the table
+            if (ni < 0) { ni = 0; nj = j - 1; }
+            if (nj < 0) { nj = 0; ni = i - 1; }
             if (ni != i) {
                 if (lane == 0) { vo[i] = cnt; wo[i] = acc; }
                 cnt = 0.0;

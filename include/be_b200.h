@@ -121,7 +121,8 @@ int be_vgp_fit(be_ctx* ctx, const double* X, const double* y_mean, const double*
  * cov^-1 = E'^-1 + G N^-1 G and det cov = det N det E' / det M with G = E E'^-1, N = K + diag(E D / E')
  * (Woodbury), so the statistics come from chol(M), its triangular inverse and chol(N): T^3 tensor flops per
  * problem instead of 4/3 T^3.  Agreement with be_gp_posterior: ~1e-12 relative (tests/test_gpu_parity.py).
- * info_dist reports chol(N). */
+ * info_dist reports chol(N).  N carries no jitter: where y_var is exactly 0 at every time step (a single
+ * realisation) N = K can be singular although cov is not -- info_dist != 0 says so; use be_gp_posterior there. */
 size_t be_gp_posterior_factored_workspace_bytes(int B, int T, int R);
 int be_gp_posterior_factored(be_ctx* ctx, const double* X, const double* y_mean, const double* y_var,
                              const double* variance, const double* lengthscale, double jitter,

@@ -80,7 +80,11 @@ static void backtrack(const uint8_t* dir, int T1, int T2, const double* x, doubl
         wx[i] += x[j];
         const int code = dir[(size_t)i * T2 + j];
         if (code == 3) break;
-        if (code == 0) { --i; --j; } else if (code == 1) { --i; } else { --j; }
+        int ni = i - (code != 2), nj = j - (code != 1);
+        /* a NaN table (NaN inputs) can record "diag" on a border; keep the walk inside the table */
+        if (ni < 0) { ni = 0; nj = j - 1; }
+        if (nj < 0) { nj = 0; ni = i - 1; }
+        i = ni; j = nj;
     }
 }
 
@@ -101,7 +105,10 @@ int be_oracle_dtw_path(const double* s, int T1, const double* t, int T2, int tie
         path_ij[2 * n] = i; path_ij[2 * n + 1] = j; ++n;
         const int code = dir[(size_t)i * T2 + j];
         if (code == 3) break;
-        if (code == 0) { --i; --j; } else if (code == 1) { --i; } else { --j; }
+        int ni = i - (code != 2), nj = j - (code != 1);
+        if (ni < 0) { ni = 0; nj = j - 1; }
+        if (nj < 0) { nj = 0; ni = i - 1; }
+        i = ni; j = nj;
     }
     for (int a = 0, b = n - 1; a < b; ++a, --b) {
         int t0 = path_ij[2 * a], t1 = path_ij[2 * a + 1];

@@ -219,3 +219,19 @@ def test_gpdtw1d_default_uses_dba_mean(backend):
         mu_m, _ = rp.gp_posterior_closed_form(X, y, s, 0.5, 6.0)
         assert rel_err(mc_mean[m].distribution.mean.values, mu_m) <= 1e-8
         assert rel_err(mu, mu_m) > 1e-4  # the two means really differ on warped inputs
+
+
+def test_dba_nan_inputs_do_not_leave_the_table(backend):
+    """NaN realisations poison their own problem only, and the path walk stays inside the table
+    (a NaN table records "diag" on the borders): same outputs as the oracle, NaN pattern included."""
+    rng = np.random.default_rng(21)
+    X = np.stack([_series(rng, 3, 70, "gmst") for _ in range(3)])
+    X[1, 0, 5] = np.nan
+    bary, n_iter, _ = backend.dtw_barycenter_averaging_subgradient(_t(backend, X), max_iter=4, tol=1e-3, want_info=True)
+    for b in range(3):
+        want, n, _ = dba.dba_subgradient(X[b], max_iter=4, tol=1e-3)
+        got = bary[b].cpu().numpy()
+        assert (np.isnan(got) == np.isnan(want)).all()
+        ok = ~np.isnan(want)
+        assert np.array_equal(got[ok], want[ok]) and int(n_iter[b]) == n
+    assert not np.isnan(bary[0].cpu().numpy()).any() and np.isnan(bary[1].cpu().numpy()).any()

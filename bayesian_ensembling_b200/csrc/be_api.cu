@@ -125,6 +125,7 @@ int ensure_kernel_attrs(be_ctx* ctx) {
     BE_CUDA(cudaFuncSetAttribute(k_trtri_accum, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
     BE_CUDA(cudaFuncSetAttribute(k_lauum_cov, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
     BE_CUDA(cudaFuncSetAttribute(k_diag_block, cudaFuncAttributeMaxDynamicSharedMemorySize, DIAG_SMEM_BYTES));
+    BE_CUDA(cudaFuncSetAttribute(k_diag_block2, cudaFuncAttributeMaxDynamicSharedMemorySize, DG2_SMEM_BYTES));
     BE_CUDA(cudaFuncSetAttribute(k_matern32<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     BE_CUDA(cudaFuncSetAttribute(k_matern32<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     BE_CUDA(cudaFuncSetAttribute(k_matern32<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
@@ -170,7 +171,13 @@ int potrf_padded(be_ctx* ctx, double* Mat, int Tp, int T, int B, double* Dinv, d
         }
         {
             Prof pr(ctx, F_DIAG, B * (2.0 / 3.0) * kw * kw * kw, B * 3.0 * kw * kw * 8);
-            k_diag_block<<<B, 256, DIAG_SMEM_BYTES, ctx->stream>>>(Mat, ld, Tp, T, kb, Dinv, nblk, V, info);
+            // two forms of the same kernel: with fewer problems than would fill every SM twice, one CTA per SM
+            // and the faster single-CTA form (170 KB of shared memory); beyond that the 100 KB form, two CTAs per
+            // SM covering each other's latencies (cfg4: 7.36 -> 5.78 ms per step; cfg2, 144 problems: 2.74 vs 3.22)
+            if (B < 2 * ctx->sm_count)
+                k_diag_block<<<B, 256, DIAG_SMEM_BYTES, ctx->stream>>>(Mat, ld, Tp, T, kb, Dinv, nblk, V, info);
+            else
+                k_diag_block2<<<B, 256, DG2_SMEM_BYTES, ctx->stream>>>(Mat, ld, Tp, T, kb, Dinv, nblk, V, info);
             BE_LAUNCHED();
         }
         if (t > 0) {

@@ -288,4 +288,269 @@ __global__ void __launch_bounds__(256, 1) k_diag_block(double* __restrict__ Mat,
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// k_diag_block2: the same algorithm in 100 KB of shared memory instead of 170 KB, so that TWO CTAs share an SM.
+// The one-CTA-per-SM version is latency-bound (ncu r01g: issue active 28 %, 12 % of the warp slots): nothing
+// covers its barrier waits, its dependent pivot chains or the latency of its global loads and stores.
+//   * Only the lower trapezoid is stored: rows 0..63 keep 64 columns (row stride 68), rows 64..127 keep 128
+//     (row stride 132); both strides are 4 mod 16, so every fragment load stays bank-conflict free.
+//   * The recursive-doubling inverse works IN PLACE, without the 64 x 68 scratch tile: T = B A^-1 is formed
+//     one 8-row strip per warp (the whole strip is accumulated in registers before it overwrites B's strip),
+//     and B <- -C^-1 T one 8-column block per warp (the block's operand fragments are loaded into registers
+//     before its first tile is overwritten).  Every level has exactly eight strips / blocks: one per warp.
+// ------------------------------------------------------------------------------------------------
+constexpr int DG2_LDT = 68;                  // rows 0..63
+constexpr int DG2_LDB = 132;                 // rows 64..127
+constexpr int DG2_TOP = 64 * DG2_LDT;
+constexpr int DG2_SMEM_DOUBLES = DG2_TOP + 64 * DG2_LDB;
+constexpr int DG2_SMEM_BYTES = DG2_SMEM_DOUBLES * 8;
+
+__device__ __forceinline__ int dg2_ld(int r) { return r < 64 ? DG2_LDT : DG2_LDB; }
+__device__ __forceinline__ int dg2_off(int r, int c) {
+    return r < 64 ? r * DG2_LDT + c : DG2_TOP + (r - 64) * DG2_LDB + c;
+}
+
+// T strip (8 rows x s columns) = B strip * Ainv, accumulated completely, then written over the B strip.
+template <int S_>
+__device__ __forceinline__ void dg2_strip_product(double* Bs, int ldb, const double* Ainv, int lda) {
+    constexpr int NF = S_ / 8;
+    const int lane = threadIdx.x & 31, g = lane >> 2, q = lane & 3;
+    double acc[NF][2];
+#pragma unroll
+    for (int f = 0; f < NF; ++f) acc[f][0] = acc[f][1] = 0.0;
+#pragma unroll 4
+    for (int k = 0; k < S_; k += 4) {
+        const double a = Bs[g * ldb + k + q];
+#pragma unroll
+        for (int f = 0; f < NF; ++f) dmma884(acc[f][0], acc[f][1], a, Ainv[(k + q) * lda + f * 8 + g]);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int f = 0; f < NF; ++f)
+        *reinterpret_cast<double2*>(Bs + g * ldb + f * 8 + 2 * q) = make_double2(acc[f][0], acc[f][1]);
+}
+
+// B block (s rows x 8 columns) <- -Cinv * (T block): T's fragments first, then tile by tile in place.
+template <int S_>
+__device__ __forceinline__ void dg2_block_product(double* Tb, int ldt, const double* Cinv, int ldc) {
+    constexpr int NK = S_ / 4;
+    const int lane = threadIdx.x & 31, g = lane >> 2, q = lane & 3;
+    double bf[NK];
+#pragma unroll
+    for (int k = 0; k < NK; ++k) bf[k] = Tb[(4 * k + q) * ldt + g];
+    __syncwarp();
+#pragma unroll 2
+    for (int fr = 0; fr < S_ / 8; ++fr) {
+        double c0 = 0.0, c1 = 0.0;
+#pragma unroll
+        for (int k = 0; k < NK; ++k) dmma884(c0, c1, Cinv[(fr * 8 + g) * ldc + 4 * k + q], bf[k]);
+        *reinterpret_cast<double2*>(Tb + (fr * 8 + g) * ldt + 2 * q) = make_double2(-c0, -c1);
+    }
+}
+
+template <int S_>
+__device__ __forceinline__ void dg2_level(double* S) {
+    // pairs [[A,0],[B,C]] of size 2 S_ along the diagonal; eight tasks per product, one per warp
+    const int warp = threadIdx.x >> 5;
+    constexpr int PER = S_ / 8;            // strips (or blocks) per pair
+    const int p = warp / PER, sub = warp % PER;
+    const int r0 = p * 2 * S_;             // first row / column of the pair
+    const int ld_b = dg2_ld(r0 + S_);      // B and C rows live in one region (2 S_ divides 64 or the pair is the whole block)
+    double* Bp = S + dg2_off(r0 + S_, r0);
+    const double* Ainv = S + dg2_off(r0, r0);
+    const double* Cinv = S + dg2_off(r0 + S_, r0 + S_);
+    dg2_strip_product<S_>(Bp + sub * 8 * ld_b, ld_b, Ainv, dg2_ld(r0));
+    __syncthreads();
+    dg2_block_product<S_>(Bp + sub * 8, ld_b, Cinv, ld_b);
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(256, 2) k_diag_block2(double* __restrict__ Mat, int ld, int Tp, int T, int kb,
+                                                        double* __restrict__ Dinv, int nblk, double* __restrict__ V,
+                                                        int* __restrict__ info) {
+    extern __shared__ double S[];
+    const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g = lane >> 2, q = lane & 3;
+    const int r0 = kb * 128;
+    const int n = min(128, Tp - r0);        // rows present (multiple of 16)
+    const int nr = max(0, min(n, T - r0));  // real (pivoting) columns
+    double* Mb = Mat + (size_t)b * Tp * ld;
+    // load the stored trapezoid (lower part, real columns; zero elsewhere)
+#pragma unroll 1
+    for (int e0 = tid; e0 < 128 * 128; e0 += 256 * 8) {
+        double v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            int e = e0 + u * 256, i = e >> 7, j = e & 127;
+            v[u] = (i < n && j < nr && j <= i) ? Mb[(size_t)(r0 + i) * ld + r0 + j] : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            int e = e0 + u * 256, i = e >> 7, j = e & 127;
+            if (i >= 64 || j < 64) S[dg2_off(i, j)] = v[u];
+        }
+    }
+    __shared__ int s_bad;
+    if (tid == 0) s_bad = 0;
+    __syncthreads();
+    const int nsteps = (nr + DG_W - 1) / DG_W;
+    int bad = 0;
+#pragma unroll 1
+    for (int st = 0; st < nsteps; ++st) {
+        const int c0 = st * DG_W;
+        const int w = min(DG_W, nr - c0);
+        const bool act = tid < 128 && tid >= c0 && tid < n;
+        double Lb[DG_W][DG_W];
+        double pv[DG_W];
+        if (act) {
+            const double* piv = S + dg2_off(c0, c0);
+            const int ldp = dg2_ld(c0);
+#pragma unroll
+            for (int i = 0; i < DG_W; ++i)
+#pragma unroll
+                for (int k = 0; k <= i; ++k) {
+                    double v = piv[i * ldp + k];
+                    Lb[i][k] = (i < w) ? v : (i == k ? 1.0 : 0.0);
+                }
+            const double* row = S + dg2_off(tid, c0);
+#pragma unroll
+            for (int k = 0; k < DG_W; k += 2) {
+                double2 t2 = *reinterpret_cast<const double2*>(row + k);
+                pv[k] = t2.x;
+                pv[k + 1] = t2.y;
+            }
+        }
+        __syncthreads();
+        if (act) {
+#pragma unroll
+            for (int j = 0; j < DG_W; ++j) {
+                const double piv = Lb[j][j];
+                bad = (bad == 0 && !(piv > 0.0)) ? r0 + c0 + j + 1 : bad;
+                const double rs = fast_rsqrt(piv);
+#pragma unroll
+                for (int i = j + 1; i < DG_W; ++i) Lb[i][j] *= rs;
+#pragma unroll
+                for (int k = j + 1; k < DG_W; ++k)
+#pragma unroll
+                    for (int i = k; i < DG_W; ++i) Lb[i][k] = fma(-Lb[i][j], Lb[k][j], Lb[i][k]);
+                pv[j] *= rs;
+#pragma unroll
+                for (int k = j + 1; k < DG_W; ++k) pv[k] = fma(-pv[j], Lb[k][j], pv[k]);
+            }
+            if (tid == c0 && bad != 0 && s_bad == 0) s_bad = bad;
+            double* row = S + dg2_off(tid, c0);
+#pragma unroll
+            for (int k = 0; k < DG_W; k += 2) {
+                double2 o;
+                o.x = (c0 + k <= tid) ? pv[k] : 0.0;
+                o.y = (c0 + k + 1 <= tid) ? pv[k + 1] : 0.0;
+                *reinterpret_cast<double2*>(row + k) = o;
+            }
+        }
+        __syncthreads();
+        // trailing real columns [p0, nr): S[r][c] -= P[r][0:8] . P[c][0:8], r >= c
+        const int p0 = c0 + DG_W;
+        const int ncs = (nr - p0 + 7) / 8;
+        const int nrs = (n - p0) / 8;
+        if (ncs > 0) {
+#pragma unroll 1
+            for (int fr = warp; fr < nrs; fr += 8) {
+                const int rr = p0 + fr * 8;      // first row of the strip (strips never straddle row 64)
+                const int ldr = dg2_ld(rr);
+                const double* Pr = S + dg2_off(rr, c0);
+                const double a0 = Pr[g * ldr + q], a1 = Pr[g * ldr + 4 + q];
+                const int fc_end = min(fr, ncs - 1);
+                const int r = rr + g;
+                double* Crow = S + dg2_off(r, 0);
+#pragma unroll 1
+                for (int fc0 = 0; fc0 <= fc_end; fc0 += 4) {
+                    double b0[4], b1[4];
+                    double2 cv[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int fc = min(fc0 + u, fc_end);
+                        const int rc = p0 + fc * 8;
+                        const int ldc = dg2_ld(rc);
+                        const double* Pc = S + dg2_off(rc, c0);
+                        b0[u] = Pc[g * ldc + q];
+                        b1[u] = Pc[g * ldc + 4 + q];
+                        cv[u] = *reinterpret_cast<const double2*>(Crow + p0 + fc * 8 + 2 * q);
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        double c[2] = {0.0, 0.0};
+                        dmma884(c[0], c[1], a0, b0[u]);
+                        dmma884(c[0], c[1], a1, b1[u]);
+                        const int fc = fc0 + u;
+                        const int cc = p0 + fc * 8 + 2 * q;
+                        if (fc <= fc_end) {
+                            double2 o;
+                            o.x = (cc < nr && cc <= r) ? cv[u].x - c[0] : cv[u].x;
+                            o.y = (cc + 1 < nr && cc + 1 <= r) ? cv[u].y - c[1] : cv[u].y;
+                            *reinterpret_cast<double2*>(Crow + cc) = o;
+                        }
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    if (tid == 0 && s_bad != 0 && info) {
+        if (info[b] == 0) info[b] = s_bad;
+    }
+    // the factor (lower, all n rows, real columns only)
+    for (int e = tid; e < 128 * 128; e += 256) {
+        int r = e >> 7, c = e & 127;
+        if (r < n && c <= r && c < nr) Mb[(size_t)(r0 + r) * ld + r0 + c] = S[dg2_off(r, c)];
+        if (r < nr && c > r && c < n) Mb[(size_t)(r0 + r) * ld + r0 + c] = 0.0;
+    }
+    __syncthreads();
+    // inverse of blockdiag(L11, I): rows >= nr become identity rows first
+    for (int e = tid; e < 128 * 128; e += 256) {
+        int r = e >> 7, c = e & 127;
+        if (r >= nr && c <= r) S[dg2_off(r, c)] = r == c ? 1.0 : 0.0;
+    }
+    __syncthreads();
+    {   // level 0: the sixteen 8 x 8 diagonal blocks; thread t < 128 owns column (t & 7) of block (t >> 3)
+        double x[DG_W];
+        const int blk = tid >> 3, cidx = tid & 7;
+        const int ldl = dg2_ld((blk & 15) * 8);
+        double* Lb = S + dg2_off((blk & 15) * 8, (blk & 15) * 8);
+        if (tid < 128) {
+#pragma unroll
+            for (int i = 0; i < DG_W; ++i) {
+                double sacc = (i == cidx) ? 1.0 : 0.0;
+#pragma unroll
+                for (int k = 0; k < i; ++k) sacc = fma(-Lb[i * ldl + k], (k >= cidx) ? x[k] : 0.0, sacc);
+                x[i] = (i >= cidx) ? sacc / Lb[i * ldl + i] : 0.0;
+            }
+        }
+        __syncthreads();
+        if (tid < 128) {
+#pragma unroll
+            for (int i = 0; i < DG_W; ++i)
+                if (i >= cidx) Lb[i * ldl + cidx] = x[i];
+        }
+        __syncthreads();
+    }
+    dg2_level<8>(S);
+    dg2_level<16>(S);
+    dg2_level<32>(S);
+    dg2_level<64>(S);
+    double* Db = Dinv + ((size_t)b * nblk + kb) * 128 * 128;
+    for (int e = tid; e < 128 * 128; e += 256) {
+        int r = e >> 7, c = e & 127;
+        Db[e] = c <= r ? S[dg2_off(r, c)] : 0.0;
+    }
+    if (V) {
+        double* Vb = V + (size_t)b * Tp * ld;
+        for (int e = tid; e < 128 * 128; e += 256) {
+            int r = e >> 7, c = e & 127;  // V tile entry (r, c) = Dinv[c][r]
+            if (r >= n || c >= n) continue;
+            Vb[(size_t)(r0 + r) * ld + r0 + c] = r <= c ? S[dg2_off(c, r)] : 0.0;
+        }
+    }
+}
+
 }  // namespace be

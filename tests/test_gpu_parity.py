@@ -82,6 +82,38 @@ def test_potrf_vs_lapack(backend, T):
         assert np.abs(np.triu(L[b], 1)).max() == 0.0
 
 
+@pytest.mark.parametrize("T", [16, 100, 128, 165, 251, 300])
+def test_potrf_many_problems_uses_the_two_cta_diag_kernel(backend, T):
+    """With >= 2 x (SM count) problems the diagonal-block kernel runs in its 100 KB form (trapezoidal
+    storage, in-place recursive-doubling inverse), two CTAs per SM: same factors, same inverse (through
+    the posterior), same non-PD reports."""
+    rng = np.random.default_rng(T + 7)
+    B = 320
+    A = rng.normal(size=(B, T, T + 3))
+    A = A @ A.transpose(0, 2, 1) / T + 0.5 * np.eye(T)
+    bad = 5
+    if T >= 16:
+        A[bad, 9, 9] = -1.0  # leading minor of order 10 is not positive definite
+    L, info = backend.potrf(_t(backend, A))
+    info = info.cpu().numpy()
+    assert info[bad] == 10 and np.count_nonzero(info) == 1
+    L = L.cpu().numpy()
+    ok = np.arange(B) != bad
+    assert rel_err(L[ok], np.linalg.cholesky(A[ok])) < 1e-12
+    assert np.abs(np.triu(L[ok], 1)).max() == 0.0
+    # the inverse of the diagonal blocks enters trtri / the posterior: a batch of B member posteriors
+    reals, _ = _cell(4, 3, T, 2, seed=T)
+    rb = np.tile(reals, (B // 4, 1, 1))
+    X, ym, yv = backend.gpdtw1d_inputs(_t(backend, rb))
+    post = backend.gp_posterior(X, ym, yv, np.full(B, 0.5), np.full(B, 6.0), want_scale_tri=False)
+    for m in range(4):
+        Xo, yo, so = rp.gpdtw1d_inputs(reals[m])
+        mu_o, cov_o = rp.gp_posterior_closed_form(Xo, yo, so, 0.5, 6.0)
+        for k in (m, B - 4 + m):
+            assert rel_err(post.mu[k].cpu().numpy(), mu_o) <= TOL_POSTERIOR
+            assert rel_err(post.cov[k].cpu().numpy(), cov_o) <= TOL_POSTERIOR
+
+
 def test_potrf_reports_non_pd_like_lapack(backend):
     T = 200
     rng = np.random.default_rng(0)

@@ -5,7 +5,7 @@ from .data import Distribution, ModelCollection, ProcessModel  # noqa: F401
 from .dtw import dtw_barycenter_averaging_subgradient, performDBA  # noqa: F401
 from .ensemble_scheme import Barycentre  # noqa: F401
 from .labelled import DataArray  # noqa: F401
-from .models import GPDTW1D, MeanFieldApproximation  # noqa: F401
+from .models import GPDTW1D, GPDTW3D, MeanFieldApproximation  # noqa: F401
 from .wasserstein import (gaussian_barycentre, gaussian_barycentre_fullcov, gaussian_w2_distance_distrax,  # noqa: F401
                           sqrtm, wasserstien_distance)
 from .weights import (CRPSWeight, InverseSquareWeight, KSDWeight, LogLikelihoodWeight, ModelSimilarityWeight,  # noqa: F401

@@ -98,3 +98,78 @@ class MeanFieldApproximation:
         blank_array = blank_array.rename("blank")
         return es_data.Distribution(mu=mean[0].cpu().numpy(), covariance=variance[0].cpu().numpy(),
                                     dim_array=blank_array, dist_type=dists.Normal)
+
+
+class GPDTW3D:
+    """ensembles/models.py:233-424, as far as it is deterministic.  The reference's 3-D model is (i) a DTW
+    barycentre average and a variance for EVERY (latitude, longitude) cell (``_dtw_to_xarray``, :238-268: a
+    Python double loop of tslearn calls), (ii) the design matrices of one sparse GP over all (t, lat, lon)
+    points (``_prep_data``, :270-322) and (iii) a stochastic-minibatch SVGP fit (:357-404: shuffled batches,
+    Adam on the kernel parameters AND the 400 inducing inputs).  (i) and (ii) are built -- (i) is ONE batched
+    device call, ``be_dtw_barycenter_averaging_subgradient`` with B = lat * lon -- and checked exactly; (iii) is
+    not (parity would be statistical only), so ``fit`` raises after validating its input
+    exactly as the reference does."""
+
+    def __init__(self, name: str = "GP3DRegressor") -> None:
+        import warnings
+
+        self.name = name
+        warnings.warn("GPDTW3D is experimental and only supports annual data. Use with care!")
+
+    @staticmethod
+    def _check(model):
+        if not model.model_data.ndim == 4:  # models.py:333-336
+            raise NotImplementedError(
+                "This method is only implemented for 4 dimensions (realisation, time, latitude, longitude")
+        assert "latitude" in model.model_data.coords, "There must be a latitude coordinate in the dataArray"
+        assert "longitude" in model.model_data.coords, "There must be a longitude coordinate in the dataArray"
+        if list(model.model_data.dims).index("latitude") != 2:  # :348-351
+            raise IndexError("Coordinate order should be realisation, time, latitude, longitude")
+
+    def _dtw_to_xarray(self, model):
+        """:238-268 -> (mean_array, var_array) with dims (time, latitude, longitude)."""
+        be = Backend.get()
+        data = np.asarray(model.model_data.values, dtype=np.float64)  # [R, T, lat, lon]
+        R, T, n_lat, n_lon = data.shape
+        cells = np.ascontiguousarray(data.transpose(2, 3, 0, 1)).reshape(n_lat * n_lon, R, T)
+        c_dev = be._in(cells)
+        y_mean = be.dtw_barycenter_averaging_subgradient(c_dev, max_iter=50, tol=1e-3)  # :250-252, all cells at once
+        _, _, y_var = be.gpdtw1d_inputs(c_dev, want_X=False)                              # :254
+        fitted_mean = y_mean.cpu().numpy().reshape(n_lat, n_lon, T).transpose(2, 0, 1)
+        fitted_var = y_var.cpu().numpy().reshape(n_lat, n_lon, T).transpose(2, 0, 1)
+        mean_array = model.model_data.isel(realisation=0).drop_vars("realisation").copy(deep=True)
+        mean_array.data = np.ascontiguousarray(fitted_mean)
+        var_array = model.model_data.isel(realisation=0).drop_vars("realisation").copy(deep=True)
+        var_array.data = np.ascontiguousarray(fitted_var)
+        return mean_array, var_array
+
+    def _prep_data(self, model_data, mean_array, var_array):
+        """:270-322 -> X [N, 4 + R] = (x, y, z, t_cont, realisations), Y [N, 2] = (DTW mean, variance),
+        N = T * lat * lon in (time, latitude, longitude) C order -- the row order of xarray's ``to_dataframe``."""
+        lat = np.asarray(mean_array.latitude.values if hasattr(mean_array.latitude, "values") else mean_array.latitude,
+                         dtype=np.float64)
+        lon = np.asarray(mean_array.longitude.values if hasattr(mean_array.longitude, "values") else mean_array.longitude,
+                         dtype=np.float64)
+        T = mean_array.shape[0]
+        lon_grid, lat_grid = np.meshgrid(lon, lat)
+        x = np.cos(lat_grid * np.pi / 180) * np.cos(lon_grid * np.pi / 180)
+        y = np.cos(lat_grid * np.pi / 180) * np.sin(lon_grid * np.pi / 180)
+        z = np.sin(lat * np.pi / 180)
+        t_cont = np.arange(T)
+        t_cont = 2 * t_cont / np.max(t_cont) - 1
+        shape = (T, lat.size, lon.size)
+        cols = [np.broadcast_to(x[None], shape), np.broadcast_to(y[None], shape),
+                np.broadcast_to(z[None, :, None], shape), np.broadcast_to(t_cont[:, None, None], shape)]
+        data = np.asarray(model_data.values, dtype=np.float64)
+        R = data.shape[0]
+        X = np.concatenate([np.stack([c.reshape(-1) for c in cols], axis=1), data.reshape(R, -1).T], axis=1)
+        Y = np.stack([np.asarray(mean_array.values, dtype=np.float64).reshape(-1),
+                      np.asarray(var_array.values, dtype=np.float64).reshape(-1)], axis=1)
+        return X.astype(np.float64), Y.astype(np.float64)
+
+    def fit(self, model, n_optim_nits: int = 500, n_inducing: int = 400, compile_objective: bool = False,
+            minibatch_size: int = 500, plot_loss: bool = False):
+        self._check(model)
+        raise NotImplementedError(
+            "GPDTW3D.fit: the stochastic-minibatch SVGP stage (models.py:357-404) is not built; "
+            "_dtw_to_xarray and _prep_data are (DESIGN.md section 8)")

@@ -235,3 +235,45 @@ def test_dba_nan_inputs_do_not_leave_the_table(backend):
         ok = ~np.isnan(want)
         assert np.array_equal(got[ok], want[ok]) and int(n_iter[b]) == n
     assert not np.isnan(bary[0].cpu().numpy()).any() and np.isnan(bary[1].cpu().numpy()).any()
+
+
+def test_gpdtw3d_dtw_to_xarray_and_prep_data(backend):
+    """GPDTW3D._dtw_to_xarray (models.py:238-268): the per-cell double loop of DBA calls as ONE batched device
+    call, bit-identical to the oracle cell by cell; _prep_data (:270-322): X / Y against a literal restatement of
+    the reference's coordinate arithmetic in to_dataframe row order."""
+    import bayesian_ensembling_b200 as es
+    from bayesian_ensembling_b200.labelled import DataArray
+
+    rng = np.random.default_rng(31)
+    R, T, n_lat, n_lon = 3, 25, 4, 5
+    data = np.stack([[_series(rng, R, T, "shifted") for _ in range(n_lon)] for _ in range(n_lat)])  # [lat,lon,R,T]
+    data = np.ascontiguousarray(data.transpose(2, 3, 0, 1))                                          # [R,T,lat,lon]
+    lat, lon = np.linspace(-60.0, 60.0, n_lat), np.linspace(0.0, 288.0, n_lon)
+    pm = es.ProcessModel(DataArray(data, ("realisation", "time", "latitude", "longitude"),
+                                   {"realisation": np.arange(R), "time": 1990 + np.arange(T), "latitude": lat,
+                                    "longitude": lon}, name="tas"), "m")
+    with pytest.warns(UserWarning, match="experimental"):
+        g3 = es.GPDTW3D()
+    mean_array, var_array = g3._dtw_to_xarray(pm)
+    assert mean_array.dims == ("time", "latitude", "longitude") and mean_array.shape == (T, n_lat, n_lon)
+    for i in range(n_lat):
+        for j in range(n_lon):
+            want = dba.dba_subgradient(data[:, :, i, j], max_iter=50, tol=1e-3)[0]
+            assert np.array_equal(mean_array.values[:, i, j], want), (i, j)
+            assert rel_err(var_array.values[:, i, j], np.var(data[:, :, i, j], axis=0)) < 1e-13
+    X, Y = g3._prep_data(pm.model_data, mean_array, var_array)
+    N = T * n_lat * n_lon
+    assert X.shape == (N, 4 + R) and Y.shape == (N, 2)
+    t_idx, la_idx, lo_idx = np.unravel_index(np.arange(N), (T, n_lat, n_lon))
+    assert np.allclose(X[:, 0], np.cos(lat[la_idx] * np.pi / 180) * np.cos(lon[lo_idx] * np.pi / 180), atol=0, rtol=1e-15)
+    assert np.allclose(X[:, 1], np.cos(lat[la_idx] * np.pi / 180) * np.sin(lon[lo_idx] * np.pi / 180), atol=0, rtol=1e-15)
+    assert np.array_equal(X[:, 2], np.sin(lat[la_idx] * np.pi / 180))
+    assert np.array_equal(X[:, 3], 2 * t_idx / (T - 1) - 1)
+    assert np.array_equal(X[:, 4:], data[:, t_idx, la_idx, lo_idx].T)
+    assert np.array_equal(Y[:, 0], mean_array.values[t_idx, la_idx, lo_idx])
+    assert np.array_equal(Y[:, 1], var_array.values[t_idx, la_idx, lo_idx])
+    with pytest.raises(NotImplementedError, match="SVGP"):
+        g3.fit(pm)
+    bad = es.ProcessModel(DataArray(data[:, :, 0, 0], ("realisation", "time")), "b")
+    with pytest.raises(NotImplementedError, match="4 dimensions"):
+        g3.fit(bad)

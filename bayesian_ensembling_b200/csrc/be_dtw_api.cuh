@@ -4,6 +4,8 @@
 
 namespace {
 
+constexpr int DTW_LANE_WALK_MIN_PAIRS = 8192;  // thread-per-pair path walk from this many pairs on (T <= 512)
+
 struct DtwShape {
     int W, NW;        // columns per thread, warps per pair
     int word_bytes;   // bytes of one direction word
@@ -106,7 +108,10 @@ int launch_dtw_backtrack_w(be_ctx* ctx, const double* X, int T, int R, int n_pai
                            size_t stride, double* v, double* wx) {
     typedef typename DtwWord<W>::type word_t;
     Prof p(ctx, F_DTW_BACK, 0.0, 40.0 * T * n_pairs);
-    if (NW == 1)
+    if (NW == 1 && n_pairs >= DTW_LANE_WALK_MIN_PAIRS)
+        k_dtw_backtrack_lane<W><<<(unsigned)((n_pairs + 127) / 128), 128, 0, ctx->stream>>>(
+            X, T, R, n_pairs, active, (const word_t*)dirs, stride, v, wx);
+    else if (NW == 1)
         k_dtw_backtrack_w1<W><<<(unsigned)((n_pairs + 3) / 4), 128, 0, ctx->stream>>>(X, T, R, n_pairs, active,
                                                                                      (const word_t*)dirs, stride, v, wx);
     else

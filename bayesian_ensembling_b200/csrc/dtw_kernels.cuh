@@ -225,6 +225,52 @@ k_dtw_backtrack_w1(const double* __restrict__ X, int T, int R, int n_pairs, cons
     }
 }
 
+// Path walk with ONE THREAD per pair, for launches with many pairs (>= 8192: a grid of cells).  The warp-per-
+// pair walks above and below are issue-bound with every lane repeating the same ~50 instructions per move;
+// here the 32 lanes walk 32 different paths, and what a move costs is one dependent 1-4 byte load of its
+// argmin word (an L2 / HBM round trip) -- paid once for thousands of walkers in flight.  x[j-1] is fetched
+// together with the word, so that the next cell's x never adds a second round trip.  Same accumulation order.
+template <int W>
+__global__ void __launch_bounds__(128)
+k_dtw_backtrack_lane(const double* __restrict__ X, int T, int R, int n_pairs, const int* __restrict__ active,
+                     const typename DtwWord<W>::type* __restrict__ dirs, size_t dirs_stride, double* __restrict__ v,
+                     double* __restrict__ wx) {
+    typedef typename DtwWord<W>::type word_t;
+    const int pair = blockIdx.x * 128 + threadIdx.x;
+    if (pair >= n_pairs) return;
+    if (active && !active[pair / R]) return;
+    const double* x = X + (size_t)pair * T;
+    const word_t* d = dirs + (size_t)pair * dirs_stride;
+    double* vo = v + (size_t)pair * T;
+    double* wo = wx + (size_t)pair * T;
+    int i = T - 1, j = T - 1;
+    double acc = 0.0, cnt = 0.0;
+    double xv = x[j];
+    for (;;) {
+        cnt += 1.0;
+        acc = __dadd_rn(acc, xv);
+        if (i == 0 && j == 0) break;
+        const int t = j / W;
+        const unsigned word = d[(size_t)(i + t) * 32 + t];
+        const double xm1 = x[j > 0 ? j - 1 : 0];
+        const unsigned code = (word >> (2 * (j - t * W))) & 3u;
+        int ni = i - (code != 2u), nj = j - (code != 1u);
+        if (ni < 0) { ni = 0; nj = j - 1; }
+        if (nj < 0) { nj = 0; ni = i - 1; }
+        if (nj != j) xv = xm1;
+        if (ni != i) {
+            vo[i] = cnt;
+            wo[i] = acc;
+            cnt = 0.0;
+            acc = 0.0;
+        }
+        i = ni;
+        j = nj;
+    }
+    vo[0] = cnt;
+    wo[0] = acc;
+}
+
 // Walks the optimal path of one pair back from (T-1, T-1) (tslearn _return_path; dtwa.py:131-139).
 // One warp per pair: the lanes fetch the direction words of 32 rows x 2 column strips around the
 // current cell in one coalesced-ish gather, then the warp walks inside that window with shuffles.

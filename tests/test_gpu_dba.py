@@ -277,3 +277,25 @@ def test_gpdtw3d_dtw_to_xarray_and_prep_data(backend):
     bad = es.ProcessModel(DataArray(data[:, :, 0, 0], ("realisation", "time")), "b")
     with pytest.raises(NotImplementedError, match="4 dimensions"):
         g3.fit(bad)
+
+
+@pytest.mark.parametrize("R,T,kind", [(12, 40, "shifted"), (9, 130, "gmst"), (10, 251, "ties")])
+def test_dba_many_pairs_uses_the_thread_per_pair_walk(backend, R, T, kind):
+    """From 8192 (problem, realisation) pairs on, the path walk runs one THREAD per pair: same barycentres,
+    iteration counts and costs, bit for bit (a sample of problems against the oracle, all against a
+    small-batch run of the warp-per-pair kernel)."""
+    rng = np.random.default_rng(R * 1000 + T)
+    B = 8192 // R + 8
+    base = np.stack([_series(rng, R, T, kind) for _ in range(16)])
+    X = np.tile(base, (B // 16 + 1, 1, 1))[:B] + 0.0
+    X[:, 0, :] += 1e-3 * np.arange(B)[:, None]  # every problem differs
+    Xd = _t(backend, X)
+    bary, n_iter, cost = backend.dtw_barycenter_averaging_subgradient(Xd, max_iter=6, tol=1e-3, want_info=True)
+    small, n_small, _ = backend.dtw_barycenter_averaging_subgradient(Xd[:64], max_iter=6, tol=1e-3, want_info=True)
+    import torch
+
+    assert torch.equal(bary[:64], small) and torch.equal(n_iter[:64], n_small)
+    for b in (0, 17, B - 1):
+        want, n, c = dba.dba_subgradient(X[b], max_iter=6, tol=1e-3)
+        assert int(n_iter[b]) == n and float(cost[b]) == c
+        assert np.array_equal(bary[b].cpu().numpy(), want)

@@ -202,10 +202,14 @@ int be_dtw_barycenter_averaging_subgradient(be_ctx* ctx, const double* X, int B,
             BE_LAUNCHED();
         }
         eta -= (initial_step_size - final_step_size) / (double)max_iter;
-        int n_active = 0;
-        BE_CUDA(cudaMemcpyAsync(&n_active, w.n_active, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-        BE_CUDA(cudaStreamSynchronize(ctx->stream));
-        if (n_active <= 0) break;
+        // every problem done?  Polled once per four iterations: an iteration over finished problems is three
+        // launches whose CTAs exit at once, cheaper than draining the launch queue every time
+        if ((it & 3) == 3) {
+            int n_active = 0;
+            BE_CUDA(cudaMemcpyAsync(&n_active, w.n_active, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+            BE_CUDA(cudaStreamSynchronize(ctx->stream));
+            if (n_active <= 0) break;
+        }
     }
     return BE_OK;
 }

@@ -376,19 +376,24 @@ __global__ void __launch_bounds__(256, 2) k_diag_block2(double* __restrict__ Mat
     const int n = min(128, Tp - r0);        // rows present (multiple of 16)
     const int nr = max(0, min(n, T - r0));  // real (pivoting) columns
     double* Mb = Mat + (size_t)b * Tp * ld;
-    // load the stored trapezoid (lower part, real columns; zero elsewhere)
-#pragma unroll 1
-    for (int e0 = tid; e0 < 128 * 128; e0 += 256 * 8) {
-        double v[8];
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-            int e = e0 + u * 256, i = e >> 7, j = e & 127;
-            v[u] = (i < n && j < nr && j <= i) ? Mb[(size_t)(r0 + i) * ld + r0 + j] : 0.0;
+    // load the stored trapezoid (lower part, real columns; zero elsewhere): a warp per row, four columns per lane
+#pragma unroll 4
+    for (int rr = 0; rr < 16; ++rr) {
+        const int i = warp + 8 * rr, j = lane * 4;
+        double2 lo = make_double2(0.0, 0.0), hi = lo;
+        if (i < n && j < n && j <= i) {  // n is a multiple of 16: the quad is inside the row
+            const double2* src = reinterpret_cast<const double2*>(Mb + (size_t)(r0 + i) * ld + r0 + j);
+            lo = src[0];
+            hi = src[1];
         }
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-            int e = e0 + u * 256, i = e >> 7, j = e & 127;
-            if (i >= 64 || j < 64) S[dg2_off(i, j)] = v[u];
+        lo.x = (j < nr && j <= i) ? lo.x : 0.0;
+        lo.y = (j + 1 < nr && j + 1 <= i) ? lo.y : 0.0;
+        hi.x = (j + 2 < nr && j + 2 <= i) ? hi.x : 0.0;
+        hi.y = (j + 3 < nr && j + 3 <= i) ? hi.y : 0.0;
+        if (i >= 64 || j < 64) {
+            double2* dst = reinterpret_cast<double2*>(S + dg2_off(i, j));
+            dst[0] = lo;
+            dst[1] = hi;
         }
     }
     __shared__ int s_bad;
@@ -499,18 +504,30 @@ __global__ void __launch_bounds__(256, 2) k_diag_block2(double* __restrict__ Mat
     if (tid == 0 && s_bad != 0 && info) {
         if (info[b] == 0) info[b] = s_bad;
     }
-    // the factor (lower, all n rows, real columns only)
-    for (int e = tid; e < 128 * 128; e += 256) {
-        int r = e >> 7, c = e & 127;
-        if (r < n && c <= r && c < nr) Mb[(size_t)(r0 + r) * ld + r0 + c] = S[dg2_off(r, c)];
-        if (r < nr && c > r && c < n) Mb[(size_t)(r0 + r) * ld + r0 + c] = 0.0;
+    // the factor (lower, all n rows, real columns only; the strict upper part of the real rows is cleaned)
+#pragma unroll 2
+    for (int rr = 0; rr < 16; ++rr) {
+        const int r = warp + 8 * rr, c = lane * 4;
+        if (r < n && c < n) {
+            double* dst = Mb + (size_t)(r0 + r) * ld + r0 + c;
+            if (c + 3 <= r && c + 3 < nr) {
+                const double2* src = reinterpret_cast<const double2*>(S + dg2_off(r, c));
+                reinterpret_cast<double2*>(dst)[0] = src[0];
+                reinterpret_cast<double2*>(dst)[1] = src[1];
+            } else {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int cc = c + u;
+                    if (cc <= r && cc < nr) dst[u] = S[dg2_off(r, cc)];
+                    else if (r < nr && cc > r) dst[u] = 0.0;
+                }
+            }
+        }
     }
     __syncthreads();
     // inverse of blockdiag(L11, I): rows >= nr become identity rows first
-    for (int e = tid; e < 128 * 128; e += 256) {
-        int r = e >> 7, c = e & 127;
-        if (r >= nr && c <= r) S[dg2_off(r, c)] = r == c ? 1.0 : 0.0;
-    }
+    for (int r = nr + warp; r < 128; r += 8)
+        for (int c = lane; c <= r; c += 32) S[dg2_off(r, c)] = r == c ? 1.0 : 0.0;
     __syncthreads();
     {   // level 0: the sixteen 8 x 8 diagonal blocks; thread t < 128 owns column (t & 7) of block (t >> 3)
         double x[DG_W];
@@ -539,16 +556,27 @@ __global__ void __launch_bounds__(256, 2) k_diag_block2(double* __restrict__ Mat
     dg2_level<32>(S);
     dg2_level<64>(S);
     double* Db = Dinv + ((size_t)b * nblk + kb) * 128 * 128;
-    for (int e = tid; e < 128 * 128; e += 256) {
-        int r = e >> 7, c = e & 127;
-        Db[e] = c <= r ? S[dg2_off(r, c)] : 0.0;
-    }
-    if (V) {
-        double* Vb = V + (size_t)b * Tp * ld;
-        for (int e = tid; e < 128 * 128; e += 256) {
-            int r = e >> 7, c = e & 127;  // V tile entry (r, c) = Dinv[c][r]
-            if (r >= n || c >= n) continue;
-            Vb[(size_t)(r0 + r) * ld + r0 + c] = r <= c ? S[dg2_off(c, r)] : 0.0;
+    double* Vb = V ? V + (size_t)b * Tp * ld : nullptr;
+#pragma unroll 2
+    for (int rr = 0; rr < 16; ++rr) {
+        const int r = warp + 8 * rr, c = lane * 4;
+        double2 lo, hi;
+        lo.x = c <= r ? S[dg2_off(r, c)] : 0.0;
+        lo.y = c + 1 <= r ? S[dg2_off(r, c + 1)] : 0.0;
+        hi.x = c + 2 <= r ? S[dg2_off(r, c + 2)] : 0.0;
+        hi.y = c + 3 <= r ? S[dg2_off(r, c + 3)] : 0.0;
+        double2* dst = reinterpret_cast<double2*>(Db + r * 128 + c);
+        dst[0] = lo;
+        dst[1] = hi;
+        if (Vb && r < n && c < n) {  // V tile entry (r, c) = Dinv[c][r], upper triangular
+            double2 vlo, vhi;
+            vlo.x = r <= c ? S[dg2_off(c, r)] : 0.0;
+            vlo.y = r <= c + 1 ? S[dg2_off(c + 1, r)] : 0.0;
+            vhi.x = r <= c + 2 ? S[dg2_off(c + 2, r)] : 0.0;
+            vhi.y = r <= c + 3 ? S[dg2_off(c + 3, r)] : 0.0;
+            double2* vd = reinterpret_cast<double2*>(Vb + (size_t)(r0 + r) * ld + r0 + c);
+            vd[0] = vlo;
+            vd[1] = vhi;
         }
     }
 }

@@ -260,7 +260,7 @@ int be_similarity_weights_pointwise(be_ctx* ctx, const double* mean, const doubl
  *   (= the mean over realisations, tslearn's _init_avg); barycenter [B,T] out; n_iter [B] (device,
  *   may be NULL) iterations run per problem; cost [B] (device, may be NULL) last cost evaluated.
  *   weights = None, barycenter_size = None, metric_params = None (the reference passes none).
- *   T <= 4096 (BE_ERR_UNSUPPORTED above).  Synchronises the ctx stream once per iteration.
+ *   T <= 4096 (BE_ERR_UNSUPPORTED above).  Synchronises the ctx stream once per four iterations.
  * be_perform_dba: the reference's own NumPy DBA, ensembles/dtwa.py:6-20 (medoid initialisation
  *   :23-37, n_iterations of DBA_update :84-141), R <= 50 series of equal length; center [B,T] out,
  *   medoid [B] (device int, may be NULL).

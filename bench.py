@@ -442,6 +442,22 @@ def run_ours(args, cfg):
               "cells_per_sec_at_2000_iterations": 1e3 / (t_it[0] - ms_iter + 2000 * ms_iter),
               "note": "be_vgp_fit on one cell (24 members batched): natural-gradient step + Adam step per iteration, "
                       "CUDA-graph replay; 2000 iterations is what experiments/full_experiment_script.py:87-113 uses"}
+        if rank == 0 and world == 1 and not args.no_cpu_baseline:
+            # the same iteration in the oracle (NumPy/SciPy, all host BLAS threads): ONE member, (fit with one
+            # iteration) - (fit with none), scaled to the cell's members
+            from oracle import reference_path as rp
+
+            _use_all_host_threads()
+            threads, _ = _blas_threads()
+            t0 = time.perf_counter()
+            rp.gpdtw1d_fit(reals[0, 0], n_optim_nits=0)
+            t1 = time.perf_counter()
+            rp.gpdtw1d_fit(reals[0, 0], n_optim_nits=1)
+            t2 = time.perf_counter()
+            cpu_it = max((t2 - t1) - (t1 - t0), 1e-9)
+            l2["cpu"] = {"seconds_per_iteration_per_cell": cpu_it * Bm, "cores": threads, "kind": "port",
+                         "sample": f"1 of {Bm} members, one iteration: {cpu_it:.1f} s, scaled x{Bm}",
+                         "gpu_over_cpu": cpu_it * Bm / (ms_iter * 1e-3)}
 
     # ---- memory-bound stages on their own, at a size >> L2 and with FINITE weights ----------------
     # (inside the cfg2 step they see 6 x 3012 points -- launch-latency sized -- and, at T=3012, NaN weights)

@@ -23,6 +23,18 @@ from .backend import Backend, DEFAULT_JITTER
 from .labelled import ones_like
 
 
+def _to_host(t: torch.Tensor) -> np.ndarray:
+    """Device tensor -> NumPy array through a pinned staging buffer (falls back to a pageable copy if pinning
+    fails, e.g. under a locked-memory limit)."""
+    try:
+        buf = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+        buf.copy_(t, non_blocking=True)
+        torch.cuda.current_stream(t.device).synchronize()
+        return buf.numpy()
+    except RuntimeError:
+        return t.cpu().numpy()
+
+
 class GPDTW1D:
     def __init__(self, name: str = "GPRegressor", hyperparameters=None, y_mean_fn=None, y_mean: str = "dba") -> None:
         if y_mean not in ("dba", "mean"):
@@ -62,6 +74,10 @@ class GPDTW1D:
                 post = be.gp_posterior(X, y_mean, y_var, var, ls, DEFAULT_JITTER)
             else:
                 post, _var, _ls = be.vgp_fit(X, y_mean, y_var, n_optim_nits)  # models.py:185-220
+            # ONE device-to-host copy of the group's means and covariances through pinned memory (a copy per
+            # member from pageable memory costs more than the fixed-theta fit itself at T = 3012)
+            mu_h = _to_host(post.mu)
+            cov_h = _to_host(post.cov)
             for k, i in enumerate(idxs):
                 pm = models[i]
                 blank_array = ones_like(pm.model_data[0].drop_vars("realisation")) * np.nan
@@ -70,7 +86,7 @@ class GPDTW1D:
                     _device_state=(post.mu[k], post.cov[k], post.scale_tri[k], post.var_diag[k], post.mvn_stats[k],
                                    post.info_dist[k]))
                 out[i] = es_data.Distribution(
-                    mu=post.mu[k].cpu().numpy(), covariance=post.cov[k].cpu().numpy(), dim_array=blank_array,
+                    mu=mu_h[k], covariance=cov_h[k], dim_array=blank_array,
                     dist_type=dists.MultivariateNormalFullCovariance, _prebuilt=dev)
         return out
 

@@ -1,0 +1,307 @@
+// Prototype for DESIGN.md section 10, item 1: an fp64-equivalent GEMM  C = A B^T  on the INTEGER tensor cores of
+// sm_100a (tcgen05.mma kind::i8, int32 accumulators in TMEM) by the Ozaki scheme.  Stand-alone (own main): NOT part of
+// the product library yet -- it exists to show that the scheme reaches fp64 accuracy on this hardware and to measure
+// what a single-CTA-per-tile, no-multicast pipeline delivers.
+//
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o tools/ozaki_dgemm tools/ozaki_dgemm.cu
+//   tools/ozaki_dgemm [M=2048] [N=4096] [K=3072]
+//
+// Scheme (S = 8 slices of 7 bits, exact in every step but the final fp64 sums):
+//   row i of A:  a = 2^(E_i+1) x,  |x| < 1/2;   q_s = rint(128 x), x <- 128 x - q_s  (s = 1..S),  |q_s| <= 64 (int8)
+//   A B^T = 2^(E_i+1) 2^(F_j+1) sum_{p=2}^{S+1} 128^-p I_p,     I_p = sum_{s+t=p} Q_s Q_t^T   (exact in int32)
+// terms with s + t > S + 1 are dropped (relative size K 2^-55 of the row/column scale, the order of fp64 rounding).
+// One CTA of six warps owns a 128 x 256 tile: warp 4 (one thread) streams slice blocks with cp.async.bulk into a
+// two-stage ring, warp 5 (one thread) issues the MMAs, warps 0-3 are the epilogue; mbarriers only, no CTA barrier
+// inside the loops.  TMEM holds two 128 x 256 int32 accumulators, so the eight p are taken two at a
+// time (p = 9,8 | 7,6 | 5,4 | 3,2): four sweeps over K; the sweep for (p_hi, p_lo) needs slices 1 .. p_hi - 1 of both
+// operands.  Slices live in global memory in the slab order [slice][tile][k/16][row][16 B], so that the 32-byte K
+// block of a slice tile is contiguous and lands in shared memory directly in the canonical K-major no-swizzle UMMA
+// layout.  After a sweep the two accumulators are combined exactly in int64 (J = 128 I_lo + I_hi) and added to the
+// fp64 partial sum of the tile in global memory (L2-resident); the last sweep applies the power-of-two scales.
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#define CK(x)                                                                                   \
+    do {                                                                                        \
+        cudaError_t e_ = (x);                                                                   \
+        if (e_ != cudaSuccess) {                                                                \
+            fprintf(stderr, "%s:%d %s: %s\n", __FILE__, __LINE__, #x, cudaGetErrorString(e_)); \
+            exit(1);                                                                            \
+        }                                                                                       \
+    } while (0)
+
+constexpr int S = 8;            // slices
+constexpr int TM = 128, TN = 256;
+constexpr int A_SLICE_BYTES = 2 * TM * 16;  // one 32-byte K block of one slice: two 16-byte slabs x 128 rows
+constexpr int B_SLICE_BYTES = 2 * TN * 16;
+constexpr int STAGE_BYTES = S * (A_SLICE_BYTES + B_SLICE_BYTES);  // 96 KB
+constexpr int NSTAGE = 2;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return (uint64_t)((saddr >> 4) & 0x3fff) | ((uint64_t)((lbo_bytes >> 4) & 0x3fff) << 16) |
+           ((uint64_t)((sbo_bytes >> 4) & 0x3fff) << 32) | ((uint64_t)1 << 46);
+}
+__host__ __device__ constexpr uint32_t umma_idesc_i8(int M, int N) {
+    return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}\n"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    }
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+
+// Asl [S][MT][K/16][128][16], Bsl [S][NT][K/16][256][16]; EA [M], FB [N] = exponents (scale 2^(E+1)); C [M][N] (zeroed)
+__global__ void __launch_bounds__(192, 1)
+k_ozaki_dgemm(const int8_t* __restrict__ Asl, const int8_t* __restrict__ Bsl, const int* __restrict__ EA,
+              const int* __restrict__ FB, double* __restrict__ C, int M, int N, int K) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ __align__(8) uint64_t bar_full[NSTAGE];   // "the bulk copies of this stage have landed"
+    __shared__ __align__(8) uint64_t bar_stage[NSTAGE];  // "the MMAs that read this stage are done"
+    __shared__ __align__(8) uint64_t bar_acc;            // "both accumulators of this sweep are complete"
+    __shared__ __align__(8) uint64_t bar_drained;        // "the 128 epilogue threads have read the accumulators"
+    __shared__ uint32_t tmem_base_s;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int MT = M / TM, NT = N / TN, nslab = K / 16, nkb = K / 32;
+    const int mt = blockIdx.x % MT, nt = blockIdx.x / MT;
+    if (tid == 0) {
+        for (int s = 0; s < NSTAGE; ++s) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar_full[s])));
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar_stage[s])));
+        }
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar_acc)));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 128;" ::"r"(smem_u32(&bar_drained)));
+        asm volatile("fence.mbarrier_init.release.cluster;");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(512u));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;");
+    const uint32_t tmem = tmem_base_s;
+    const uint32_t idesc = umma_idesc_i8(TM, TN);
+    const uint32_t smem0 = smem_u32(smem);
+
+    if (warp == 4) {
+        // ===== PRODUCER (one warp): lane s copies slice s + 1 of A and of B; bytes are counted on bar_full =====
+        int it = 0;
+        for (int g = 0; g < 4; ++g) {
+            const int ns = S - 2 * g;
+            for (int kb = 0; kb < nkb; ++kb, ++it) {
+                const int st = it % NSTAGE, use = it / NSTAGE;
+                if (use > 0) mbar_wait(&bar_stage[st], (use - 1) & 1);  // the MMAs that read this stage are done
+                const uint32_t sA = smem0 + st * STAGE_BYTES, sB = sA + S * A_SLICE_BYTES;
+                const uint32_t fb = smem_u32(&bar_full[st]);
+                if (lane == 0)
+                    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(fb),
+                                 "r"((uint32_t)(ns * (A_SLICE_BYTES + B_SLICE_BYTES))) : "memory");
+                __syncwarp();
+                if (lane < ns) {
+                    const int s = lane;
+                    const int8_t* srcA = Asl + (((size_t)s * MT + mt) * nslab + 2 * kb) * (TM * 16);
+                    const int8_t* srcB = Bsl + (((size_t)s * NT + nt) * nslab + 2 * kb) * (TN * 16);
+                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                                     sA + s * A_SLICE_BYTES),
+                                 "l"(srcA), "r"((uint32_t)A_SLICE_BYTES), "r"(fb)
+                                 : "memory");
+                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                                     sB + s * B_SLICE_BYTES),
+                                 "l"(srcB), "r"((uint32_t)B_SLICE_BYTES), "r"(fb)
+                                 : "memory");
+                }
+            }
+        }
+    } else if (warp == 5) {
+        // ===== MMA ISSUER (one thread) =====
+        if (lane == 0) {
+            int it = 0;
+            for (int g = 0; g < 4; ++g) {
+                const int p_hi = S + 1 - 2 * g, p_lo = p_hi - 1, ns = p_hi - 1;
+                if (g > 0) mbar_wait(&bar_drained, (g - 1) & 1);  // the epilogue has read the previous accumulators
+                asm volatile("tcgen05.fence::after_thread_sync;");
+                for (int kb = 0; kb < nkb; ++kb, ++it) {
+                    const int st = it % NSTAGE, use = it / NSTAGE;
+                    mbar_wait(&bar_full[st], use & 1);
+                    asm volatile("tcgen05.fence::after_thread_sync;");
+                    const uint32_t sA = smem0 + st * STAGE_BYTES, sB = sA + S * A_SLICE_BYTES;
+                    bool first_hi = kb == 0, first_lo = kb == 0;
+                    for (int s = 1; s <= ns; ++s) {
+                        const uint64_t ad = umma_desc(sA + (s - 1) * A_SLICE_BYTES, TM * 16, 128);
+                        for (int pp = 0; pp < 2; ++pp) {
+                            const int t = (pp == 0 ? p_hi : p_lo) - s;
+                            if (t < 1 || t > ns) continue;
+                            const uint64_t bd = umma_desc(sB + (t - 1) * B_SLICE_BYTES, TN * 16, 128);
+                            bool& first = pp == 0 ? first_hi : first_lo;
+                            const uint32_t accumulate = first ? 0u : 1u;
+                            first = false;
+                            asm volatile(
+                                "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                                "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t}\n" ::"r"(
+                                    tmem + (pp == 0 ? 0u : 256u)),
+                                "l"(ad), "l"(bd), "r"(idesc), "r"(accumulate), "r"(0u));
+                        }
+                    }
+                    umma_commit(&bar_stage[st]);
+                    if (kb == nkb - 1) umma_commit(&bar_acc);
+                }
+            }
+        }
+    } else {
+        // ===== EPILOGUE (warps 0-3, one TMEM lane quarter each): J = 128 I_lo + I_hi (exact), U += 2^(-7 p_hi) J =====
+        for (int g = 0; g < 4; ++g) {
+            const int p_hi = S + 1 - 2 * g;
+            mbar_wait(&bar_acc, g & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;");
+            const int row = warp * 32 + lane;
+            const int gi = mt * TM + row;
+            double* crow = C + (size_t)gi * N + (size_t)nt * TN;
+            const double w = ldexp(1.0, -7 * p_hi);
+            const int ea = EA[gi];
+            for (int c0 = 0; c0 < TN; c0 += 8) {
+                uint32_t hi[8], lo[8];
+                const uint32_t ta = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0;
+                asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                             : "=r"(hi[0]), "=r"(hi[1]), "=r"(hi[2]), "=r"(hi[3]), "=r"(hi[4]), "=r"(hi[5]), "=r"(hi[6]), "=r"(hi[7])
+                             : "r"(ta));
+                asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                             : "=r"(lo[0]), "=r"(lo[1]), "=r"(lo[2]), "=r"(lo[3]), "=r"(lo[4]), "=r"(lo[5]), "=r"(lo[6]), "=r"(lo[7])
+                             : "r"(ta + 256u));
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (c0 == TN - 8) {  // everything this thread needs has left TMEM: let the next sweep start
+                    asm volatile("tcgen05.fence::before_thread_sync;");
+                    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&bar_drained)) : "memory");
+                }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const long long J = 128LL * (long long)(int32_t)lo[u] + (long long)(int32_t)hi[u];
+                    double v = (g == 0 ? 0.0 : crow[c0 + u]) + w * (double)J;
+                    if (g == 3) v = ldexp(v, ea + FB[nt * TN + c0 + u] + 2);
+                    crow[c0 + u] = v;
+                }
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u));
+}
+
+// host: slice a row-major [R][K] fp64 matrix into S int8 arrays in slab order, tile height TR
+static void slice_matrix(const std::vector<double>& X, int R, int K, int TR, std::vector<int8_t>& out, std::vector<int>& E) {
+    const int RT = R / TR, nslab = K / 16;
+    out.assign((size_t)S * R * K, 0);
+    E.assign(R, 0);
+    for (int i = 0; i < R; ++i) {
+        double mx = 0.0;
+        for (int k = 0; k < K; ++k) mx = fmax(mx, fabs(X[(size_t)i * K + k]));
+        const int e = mx > 0.0 ? ilogb(mx) + 1 : 0;  // max < 2^e
+        E[i] = e;
+        const int rt = i / TR, r = i % TR;
+        for (int k = 0; k < K; ++k) {
+            double x = ldexp(X[(size_t)i * K + k], -(e + 1));  // |x| < 1/2
+            for (int s = 0; s < S; ++s) {
+                const double y = x * 128.0;
+                const double q = nearbyint(y);
+                x = y - q;
+                out[((((size_t)s * RT + rt) * nslab + k / 16) * TR + r) * 16 + k % 16] = (int8_t)q;
+            }
+        }
+    }
+}
+
+int main(int argc, char** argv) {
+    const int M = argc > 1 ? atoi(argv[1]) : 2048, N = argc > 2 ? atoi(argv[2]) : 4096, K = argc > 3 ? atoi(argv[3]) : 3072;
+    if (M % TM || N % TN || K % 32) {
+        fprintf(stderr, "M %% 128, N %% 256, K %% 32 must be 0\n");
+        return 2;
+    }
+    std::vector<double> A((size_t)M * K), B((size_t)N * K);
+    srand(7);
+    auto rnd = []() { return (double)rand() / RAND_MAX - 0.5; };
+    // rows with very different scales and entries spanning orders of magnitude inside a row
+    for (int i = 0; i < M; ++i) {
+        const double rs = ldexp(1.0, (i * 7) % 40 - 20);
+        for (int k = 0; k < K; ++k) A[(size_t)i * K + k] = rs * rnd() * exp(4.0 * rnd());
+    }
+    for (int j = 0; j < N; ++j) {
+        const double rs = ldexp(1.0, (j * 5) % 30 - 15);
+        for (int k = 0; k < K; ++k) B[(size_t)j * K + k] = rs * rnd() * exp(4.0 * rnd());
+    }
+    std::vector<int8_t> hAs, hBs;
+    std::vector<int> EA, FB;
+    slice_matrix(A, M, K, TM, hAs, EA);
+    slice_matrix(B, N, K, TN, hBs, FB);
+    int8_t *dA, *dB;
+    int *dEA, *dFB;
+    double* dC;
+    CK(cudaMalloc(&dA, hAs.size()));
+    CK(cudaMalloc(&dB, hBs.size()));
+    CK(cudaMalloc(&dEA, sizeof(int) * M));
+    CK(cudaMalloc(&dFB, sizeof(int) * N));
+    CK(cudaMalloc(&dC, sizeof(double) * (size_t)M * N));
+    CK(cudaMemcpy(dA, hAs.data(), hAs.size(), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dB, hBs.data(), hBs.size(), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dEA, EA.data(), sizeof(int) * M, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dFB, FB.data(), sizeof(int) * N, cudaMemcpyHostToDevice));
+    const size_t smem = (size_t)NSTAGE * STAGE_BYTES + 1024;
+    CK(cudaFuncSetAttribute(k_ozaki_dgemm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int grid = (M / TM) * (N / TN);
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    float best = 1e30f;
+    for (int rep = 0; rep < 3; ++rep) {
+        CK(cudaMemset(dC, 0xff, sizeof(double) * (size_t)M * N));  // NaN: the first sweep must not read C
+        CK(cudaEventRecord(e0));
+        k_ozaki_dgemm<<<grid, 192, smem>>>(dA, dB, dEA, dFB, dC, M, N, K);
+        CK(cudaEventRecord(e1));
+        CK(cudaDeviceSynchronize());
+        float ms;
+        CK(cudaEventElapsedTime(&ms, e0, e1));
+        best = fminf(best, ms);
+    }
+    std::vector<double> C((size_t)M * N);
+    CK(cudaMemcpy(C.data(), dC, sizeof(double) * C.size(), cudaMemcpyDeviceToHost));
+    // accuracy on a sample: error relative to sum |a||b| (the scale of an fp64 dot product's own rounding bound)
+    double worst = 0.0, worst_plain = 0.0;
+    for (int smp = 0; smp < 4000; ++smp) {
+        const int i = rand() % M, j = rand() % N;
+        long double ref = 0.0L, mag = 0.0L;
+        double plain = 0.0;
+        for (int k = 0; k < K; ++k) {
+            const long double t = (long double)A[(size_t)i * K + k] * (long double)B[(size_t)j * K + k];
+            ref += t;
+            mag += fabsl(t);
+            plain += A[(size_t)i * K + k] * B[(size_t)j * K + k];
+        }
+        worst = fmax(worst, (double)(fabsl((long double)C[(size_t)i * N + j] - ref) / mag));
+        worst_plain = fmax(worst_plain, (double)(fabsl((long double)plain - ref) / mag));
+    }
+    const double flops = 2.0 * M * N * (double)K;
+    printf("{\"M\": %d, \"N\": %d, \"K\": %d, \"slices\": %d, \"int8_mmas_per_fp64_mma\": 36, \"ms\": %.3f, "
+           "\"fp64_equivalent_tflops\": %.1f, \"int8_tops\": %.0f, \"max_err_over_sum_abs\": %.3e, "
+           "\"plain_fp64_loop_err_over_sum_abs\": %.3e}\n",
+           M, N, K, S, best, flops / (best * 1e-3) / 1e12, 36.0 * flops / (best * 1e-3) / 1e12, worst, worst_plain);
+    return worst < 1e-14 ? 0 : 1;
+}

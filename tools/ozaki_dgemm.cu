@@ -39,8 +39,11 @@ constexpr int S = 8;            // slices
 constexpr int TM = 128, TN = 256;
 constexpr int A_SLICE_BYTES = 2 * TM * 16;  // one 32-byte K block of one slice: two 16-byte slabs x 128 rows
 constexpr int B_SLICE_BYTES = 2 * TN * 16;
-constexpr int STAGE_BYTES = S * (A_SLICE_BYTES + B_SLICE_BYTES);  // 96 KB
-constexpr int NSTAGE = 2;
+constexpr int SLICE_PAIR_BYTES = A_SLICE_BYTES + B_SLICE_BYTES;  // 12 KB: one slice of A and of B for a 32-byte K block
+constexpr int RING_BYTES = 216 * 1024;
+constexpr int MAXSTAGE = 8;
+// stages of the ring in sweep g (ns = 8, 6, 4, 2 slices per operand): as many as fit -- 2, 3, 4, 8
+__host__ __device__ constexpr int n_stages(int ns) { return RING_BYTES / (ns * SLICE_PAIR_BYTES) > MAXSTAGE ? MAXSTAGE : RING_BYTES / (ns * SLICE_PAIR_BYTES); }
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -66,17 +69,27 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+// 32 lanes x 32 consecutive 32-bit columns of TMEM -> 32 registers per thread (no wait: see tcgen05.wait::ld)
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
 }
 
 // Asl [S][MT][K/16][128][16], Bsl [S][NT][K/16][256][16]; EA [M], FB [N] = exponents (scale 2^(E+1)); C [M][N] (zeroed)
 __global__ void __launch_bounds__(192, 1)
 k_ozaki_dgemm(const int8_t* __restrict__ Asl, const int8_t* __restrict__ Bsl, const int* __restrict__ EA,
-              const int* __restrict__ FB, double* __restrict__ C, int M, int N, int K) {
+              const int* __restrict__ FB, double* __restrict__ C, double* __restrict__ U, int M, int N, int K,
+              long long* __restrict__ TS) {
     extern __shared__ __align__(1024) uint8_t smem[];
-    __shared__ __align__(8) uint64_t bar_full[NSTAGE];   // "the bulk copies of this stage have landed"
-    __shared__ __align__(8) uint64_t bar_stage[NSTAGE];  // "the MMAs that read this stage are done"
+    __shared__ __align__(8) uint64_t bar_full[MAXSTAGE];   // "the bulk copies of this stage have landed"
+    __shared__ __align__(8) uint64_t bar_stage[MAXSTAGE];  // "the MMAs that read this stage are done"
     __shared__ __align__(8) uint64_t bar_acc;            // "both accumulators of this sweep are complete"
     __shared__ __align__(8) uint64_t bar_drained;        // "the 128 epilogue threads have read the accumulators"
     __shared__ uint32_t tmem_base_s;
@@ -84,7 +97,7 @@ k_ozaki_dgemm(const int8_t* __restrict__ Asl, const int8_t* __restrict__ Bsl, co
     const int MT = M / TM, NT = N / TN, nslab = K / 16, nkb = K / 32;
     const int mt = blockIdx.x % MT, nt = blockIdx.x / MT;
     if (tid == 0) {
-        for (int s = 0; s < NSTAGE; ++s) {
+        for (int s = 0; s < MAXSTAGE; ++s) {
             asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar_full[s])));
             asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar_stage[s])));
         }
@@ -100,22 +113,26 @@ k_ozaki_dgemm(const int8_t* __restrict__ Asl, const int8_t* __restrict__ Bsl, co
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;");
     const uint32_t tmem = tmem_base_s;
+    if (TS && blockIdx.x == 0 && tid == 0) TS[0] = clock64();
     const uint32_t idesc = umma_idesc_i8(TM, TN);
     const uint32_t smem0 = smem_u32(smem);
+    // (taking the sweeps in an order rotated per CTA, to spread the read-modify-write epilogues in time, measured 10 %
+    // SLOWER: CTAs that share an operand tile stop reading the same slices at the same time and lose their L2 hits)
+    constexpr int rot = 0;
 
     if (warp == 4) {
         // ===== PRODUCER (one warp): lane s copies slice s + 1 of A and of B; bytes are counted on bar_full =====
-        int it = 0;
+        uint32_t uses[MAXSTAGE] = {0, 0, 0, 0, 0, 0, 0, 0};  // times each stage has been filled (barrier phase = uses & 1)
         for (int g = 0; g < 4; ++g) {
-            const int ns = S - 2 * g;
-            for (int kb = 0; kb < nkb; ++kb, ++it) {
-                const int st = it % NSTAGE, use = it / NSTAGE;
-                if (use > 0) mbar_wait(&bar_stage[st], (use - 1) & 1);  // the MMAs that read this stage are done
-                const uint32_t sA = smem0 + st * STAGE_BYTES, sB = sA + S * A_SLICE_BYTES;
+            const int ns = S - 2 * ((g + rot) & 3), nst = n_stages(ns), stage_bytes = ns * SLICE_PAIR_BYTES;
+            if (g > 0) mbar_wait(&bar_acc, (g - 1) & 1);  // the ring is re-partitioned: every MMA of the last sweep is done
+            for (int kb = 0; kb < nkb; ++kb) {
+                const int st = kb % nst;
+                if (kb >= nst) mbar_wait(&bar_stage[st], (uses[st] - 1) & 1);  // the MMAs that read this stage are done
+                const uint32_t sA = smem0 + st * stage_bytes, sB = sA + ns * A_SLICE_BYTES;
                 const uint32_t fb = smem_u32(&bar_full[st]);
                 if (lane == 0)
-                    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(fb),
-                                 "r"((uint32_t)(ns * (A_SLICE_BYTES + B_SLICE_BYTES))) : "memory");
+                    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(fb), "r"((uint32_t)stage_bytes) : "memory");
                 __syncwarp();
                 if (lane < ns) {
                     const int s = lane;
@@ -130,21 +147,24 @@ k_ozaki_dgemm(const int8_t* __restrict__ Asl, const int8_t* __restrict__ Bsl, co
                                  "l"(srcB), "r"((uint32_t)B_SLICE_BYTES), "r"(fb)
                                  : "memory");
                 }
+                uses[st] += 1;
             }
         }
     } else if (warp == 5) {
         // ===== MMA ISSUER (one thread) =====
         if (lane == 0) {
-            int it = 0;
+            uint32_t fulls[MAXSTAGE] = {0, 0, 0, 0, 0, 0, 0, 0};  // times each stage has been consumed
             for (int g = 0; g < 4; ++g) {
-                const int p_hi = S + 1 - 2 * g, p_lo = p_hi - 1, ns = p_hi - 1;
+                const int p_hi = S + 1 - 2 * ((g + rot) & 3), p_lo = p_hi - 1, ns = p_hi - 1;
+                const int nst = n_stages(ns), stage_bytes = ns * SLICE_PAIR_BYTES;
                 if (g > 0) mbar_wait(&bar_drained, (g - 1) & 1);  // the epilogue has read the previous accumulators
                 asm volatile("tcgen05.fence::after_thread_sync;");
-                for (int kb = 0; kb < nkb; ++kb, ++it) {
-                    const int st = it % NSTAGE, use = it / NSTAGE;
-                    mbar_wait(&bar_full[st], use & 1);
+                for (int kb = 0; kb < nkb; ++kb) {
+                    const int st = kb % nst;
+                    mbar_wait(&bar_full[st], fulls[st] & 1);
+                    fulls[st] += 1;
                     asm volatile("tcgen05.fence::after_thread_sync;");
-                    const uint32_t sA = smem0 + st * STAGE_BYTES, sB = sA + S * A_SLICE_BYTES;
+                    const uint32_t sA = smem0 + st * stage_bytes, sB = sA + ns * A_SLICE_BYTES;
                     bool first_hi = kb == 0, first_lo = kb == 0;
                     for (int s = 1; s <= ns; ++s) {
                         const uint64_t ad = umma_desc(sA + (s - 1) * A_SLICE_BYTES, TM * 16, 128);
@@ -170,36 +190,55 @@ k_ozaki_dgemm(const int8_t* __restrict__ Asl, const int8_t* __restrict__ Bsl, co
     } else {
         // ===== EPILOGUE (warps 0-3, one TMEM lane quarter each): J = 128 I_lo + I_hi (exact), U += 2^(-7 p_hi) J =====
         for (int g = 0; g < 4; ++g) {
-            const int p_hi = S + 1 - 2 * g;
+            const int p_hi = S + 1 - 2 * ((g + rot) & 3);
             mbar_wait(&bar_acc, g & 1);
             asm volatile("tcgen05.fence::after_thread_sync;");
+            if (TS && blockIdx.x == 0 && tid == 0) TS[1 + 2 * g] = clock64();
             const int row = warp * 32 + lane;
             const int gi = mt * TM + row;
             double* crow = C + (size_t)gi * N + (size_t)nt * TN;
             const double w = ldexp(1.0, -7 * p_hi);
             const int ea = EA[gi];
-            for (int c0 = 0; c0 < TN; c0 += 8) {
-                uint32_t hi[8], lo[8];
+            for (int c0 = 0; c0 < TN; c0 += 32) {
+                uint32_t hi[32], lo[32];
                 const uint32_t ta = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0;
-                asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-                             : "=r"(hi[0]), "=r"(hi[1]), "=r"(hi[2]), "=r"(hi[3]), "=r"(hi[4]), "=r"(hi[5]), "=r"(hi[6]), "=r"(hi[7])
-                             : "r"(ta));
-                asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-                             : "=r"(lo[0]), "=r"(lo[1]), "=r"(lo[2]), "=r"(lo[3]), "=r"(lo[4]), "=r"(lo[5]), "=r"(lo[6]), "=r"(lo[7])
-                             : "r"(ta + 256u));
+                tmem_ld32(ta, hi);
+                tmem_ld32(ta + 256u, lo);
+                // the partial sums of the tile live in a scratch buffer laid out [tile][32-column block][row][32], so
+                // that the 128 threads (= rows) of a step touch 32 KB of contiguous memory (the row-major C would put
+                // them 8 N bytes apart); their loads are in flight together with the TMEM loads
+                double* up = U + (((size_t)blockIdx.x * (TN / 32) + c0 / 32) * TM + row) * 32;
+                double v[32];
+                if (g > 0) {
+#pragma unroll
+                    for (int u = 0; u < 32; u += 4) {
+                        const double4 q4 = *reinterpret_cast<const double4*>(up + u);
+                        v[u] = q4.x; v[u + 1] = q4.y; v[u + 2] = q4.z; v[u + 3] = q4.w;
+                    }
+                }
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                if (c0 == TN - 8) {  // everything this thread needs has left TMEM: let the next sweep start
+                if (c0 == TN - 32) {  // everything this thread needs has left TMEM: let the next sweep start
                     asm volatile("tcgen05.fence::before_thread_sync;");
                     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&bar_drained)) : "memory");
                 }
 #pragma unroll
-                for (int u = 0; u < 8; ++u) {
+                for (int u = 0; u < 32; ++u) {
                     const long long J = 128LL * (long long)(int32_t)lo[u] + (long long)(int32_t)hi[u];
-                    double v = (g == 0 ? 0.0 : crow[c0 + u]) + w * (double)J;
-                    if (g == 3) v = ldexp(v, ea + FB[nt * TN + c0 + u] + 2);
-                    crow[c0 + u] = v;
+                    v[u] = (g == 0 ? 0.0 : v[u]) + w * (double)J;
+                }
+                if (g < 3) {
+#pragma unroll
+                    for (int u = 0; u < 32; u += 4) *reinterpret_cast<double4*>(up + u) = make_double4(v[u], v[u + 1], v[u + 2], v[u + 3]);
+                } else {
+#pragma unroll
+                    for (int u = 0; u < 32; u += 2) {
+                        const int2 f2 = *reinterpret_cast<const int2*>(FB + nt * TN + c0 + u);
+                        *reinterpret_cast<double2*>(crow + c0 + u) =
+                            make_double2(ldexp(v[u], ea + f2.x + 2), ldexp(v[u + 1], ea + f2.y + 2));
+                    }
                 }
             }
+            if (TS && blockIdx.x == 0 && tid == 0) TS[2 + 2 * g] = clock64();
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;");
@@ -260,11 +299,16 @@ int main(int argc, char** argv) {
     CK(cudaMalloc(&dEA, sizeof(int) * M));
     CK(cudaMalloc(&dFB, sizeof(int) * N));
     CK(cudaMalloc(&dC, sizeof(double) * (size_t)M * N));
+    double* dU;
+    long long* dTS;
+    CK(cudaMalloc(&dTS, sizeof(long long) * 32));
+    CK(cudaMemset(dTS, 0, sizeof(long long) * 32));
+    CK(cudaMalloc(&dU, sizeof(double) * (size_t)M * N));
     CK(cudaMemcpy(dA, hAs.data(), hAs.size(), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(dB, hBs.data(), hBs.size(), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(dEA, EA.data(), sizeof(int) * M, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(dFB, FB.data(), sizeof(int) * N, cudaMemcpyHostToDevice));
-    const size_t smem = (size_t)NSTAGE * STAGE_BYTES + 1024;
+    const size_t smem = (size_t)RING_BYTES + 1024;
     CK(cudaFuncSetAttribute(k_ozaki_dgemm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int grid = (M / TM) * (N / TN);
     cudaEvent_t e0, e1;
@@ -274,7 +318,7 @@ int main(int argc, char** argv) {
     for (int rep = 0; rep < 3; ++rep) {
         CK(cudaMemset(dC, 0xff, sizeof(double) * (size_t)M * N));  // NaN: the first sweep must not read C
         CK(cudaEventRecord(e0));
-        k_ozaki_dgemm<<<grid, 192, smem>>>(dA, dB, dEA, dFB, dC, M, N, K);
+        k_ozaki_dgemm<<<grid, 192, smem>>>(dA, dB, dEA, dFB, dC, dU, M, N, K, (argc > 4 && atoi(argv[4]) == 0) ? nullptr : dTS);
         CK(cudaEventRecord(e1));
         CK(cudaDeviceSynchronize());
         float ms;
@@ -298,6 +342,11 @@ int main(int argc, char** argv) {
         worst = fmax(worst, (double)(fabsl((long double)C[(size_t)i * N + j] - ref) / mag));
         worst_plain = fmax(worst_plain, (double)(fabsl((long double)plain - ref) / mag));
     }
+    long long hTS[32];
+    CK(cudaMemcpy(hTS, dTS, sizeof(hTS), cudaMemcpyDeviceToHost));
+    fprintf(stderr, "CTA 0 timeline (cycles from start):");
+    for (int q = 1; q <= 8; ++q) fprintf(stderr, " %lld", hTS[q] - hTS[0]);
+    fprintf(stderr, "\n");
     const double flops = 2.0 * M * N * (double)K;
     printf("{\"M\": %d, \"N\": %d, \"K\": %d, \"slices\": %d, \"int8_mmas_per_fp64_mma\": 36, \"ms\": %.3f, "
            "\"fp64_equivalent_tflops\": %.1f, \"int8_tops\": %.0f, \"max_err_over_sum_abs\": %.3e, "

@@ -12,6 +12,7 @@
 #include "sqrtm_kernels.cuh"
 #include "weights_next_kernels.cuh"
 #include "dtw_kernels.cuh"
+#include "ozaki_gemm.cuh"
 
 using namespace be;
 

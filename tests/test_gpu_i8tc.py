@@ -4,7 +4,7 @@ fp64 dot product's own rounding bound -- with C_ref from NumPy's longdouble (80-
 import numpy as np
 import pytest
 
-pytestmark = pytest.mark.gpu
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(180)]  # mbarrier pipelines: a regression must fail, not hang
 
 
 def _t(backend, a):

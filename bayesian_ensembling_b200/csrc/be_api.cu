@@ -140,6 +140,8 @@ int ensure_kernel_attrs(be_ctx* ctx) {
     BE_CUDA(cudaFuncSetAttribute(k_gemm_nt<EpiSym>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
     BE_CUDA(cudaFuncSetAttribute(k_gemm_nt<EpiPlain>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
     BE_CUDA(cudaFuncSetAttribute(k_loglik_weights_mvn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WEIGHT_STAGE_MAX_BYTES + 16384));
+    BE_CUDA(cudaFuncSetAttribute(k_loglik_weights_mvn_tab<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WEIGHT_STAGE_MAX_BYTES + 16384 + 128));
+    BE_CUDA(cudaFuncSetAttribute(k_loglik_weights_mvn_tab<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WEIGHT_STAGE_MAX_BYTES + 16384 + 128));
     BE_CUDA(cudaFuncSetAttribute(k_loglik_weights_normal, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WEIGHT_STAGE_MAX_BYTES));
     BE_CUDA(cudaFuncSetAttribute(k_crps_weights, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WEIGHT_STAGE_MAX_BYTES));
     BE_CUDA(cudaFuncSetAttribute(k_ksd_weights, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WEIGHT_STAGE_MAX_BYTES));
@@ -746,9 +748,21 @@ int be_loglik_weights_mvn(be_ctx* ctx, const double* mvn_stats, const double* ob
     const int wb = weight_stage_block(M);
     const size_t wsm = weight_stage_bytes(M);
     const size_t ssm = weight_stats_bytes(M) <= 16384 ? weight_stats_bytes(M) : 0;
-    k_loglik_weights_mvn<<<grid1d((size_t)C * T, wb), wb, wsm + ssm, ctx->stream>>>(
-        mvn_stats, obs, C, M, Ro, T, standardisation_constant, weights, lls_exp, lls_mean,
-        (wsm > 0 ? 1 : 0) | (ssm > 0 ? 2 : 0));
+    // opt-in until its GPU tests have run (tests/test_gpu_parity.py::test_weights_exponential_whole_range)
+    static const bool use_tab = getenv("BE_WEIGHTS_TAB") != nullptr;
+    if (wsm > 0 && ssm > 0 && use_tab) {
+        const size_t sm = wsm + ssm + 16 * sizeof(double);
+        if (lls_exp || lls_mean)
+            k_loglik_weights_mvn_tab<true><<<grid1d((size_t)C * T, wb), wb, sm, ctx->stream>>>(
+                mvn_stats, obs, C, M, Ro, T, standardisation_constant, weights, lls_exp, lls_mean);
+        else
+            k_loglik_weights_mvn_tab<false><<<grid1d((size_t)C * T, wb), wb, sm, ctx->stream>>>(
+                mvn_stats, obs, C, M, Ro, T, standardisation_constant, weights, nullptr, nullptr);
+    } else {
+        k_loglik_weights_mvn<<<grid1d((size_t)C * T, wb), wb, wsm + ssm, ctx->stream>>>(
+            mvn_stats, obs, C, M, Ro, T, standardisation_constant, weights, lls_exp, lls_mean,
+            (wsm > 0 ? 1 : 0) | (ssm > 0 ? 2 : 0));
+    }
     BE_LAUNCHED();
     return BE_OK;
 }

@@ -710,6 +710,140 @@ __global__ void k_loglik_weights_mvn(const double* __restrict__ stats, const dou
     for (int m = 0; m < M; ++m) wp[(size_t)m * T] = st[m] / total;
 }
 
+// exp by a 16-entry table of 2^(j/16) and a degree-7 polynomial on |r| <= ln2/32 (truncation 1.2e-18, total
+// error ~1.5 ulp): 13 FP64 instructions instead of the library's ~34 FP64 out of 67.  The table is 128 bytes
+// of shared memory = each entry on its own pair of banks, so any index pattern is conflict-free.  Arguments
+// outside |x| < 700 (overflow, gradual underflow, NaN) take the library's exp.
+__constant__ double EXP2_16TH[16] = {
+    0x1.0000000000000p+0, 0x1.0b5586cf9890fp+0, 0x1.172b83c7d517bp+0, 0x1.2387a6e756238p+0,
+    0x1.306fe0a31b715p+0, 0x1.3dea64c123422p+0, 0x1.4bfdad5362a27p+0, 0x1.5ab07dd485429p+0,
+    0x1.6a09e667f3bcdp+0, 0x1.7a11473eb0187p+0, 0x1.8ace5422aa0dbp+0, 0x1.9c49182a3f090p+0,
+    0x1.ae89f995ad3adp+0, 0x1.c199bdd85529cp+0, 0x1.d5818dcfba487p+0, 0x1.ea4afa2a490dap+0};
+
+// Constants whose low word is not zero are read as constant-bank operands of the DFMAs (as 64-bit literals
+// they cost two moves each per use); ln2/16 is split so that its high part has a zero low word (an immediate).
+struct ExpTabConsts {
+    double inv, lo, c7, c6, c5, c4, c3;
+};
+__constant__ ExpTabConsts EXPC = {0x1.71547652b82fep+4,   0x1.fdf473de6af28p-26, 0x1.a01a01a01a01ap-13, 0x1.6c16c16c16c17p-10,
+                                  0x1.1111111111111p-7,   0x1.5555555555555p-5,  0x1.5555555555555p-3};
+
+// exp_tab16_core is branch-free (any input, garbage outside |x| < 700, never a trap or an out-of-range table
+// index) so that the chains of neighbouring members interleave; exp_tab16_fix repairs the rare outliers.
+__device__ __forceinline__ double exp_tab16_core(double x, const double* __restrict__ tab) {
+    const double v = fma(x, EXPC.inv, 6755399441055744.0);  // k = rint(16 x / ln2) in the low word
+    const int k = __double2loint(v);
+    const double kd = v - 6755399441055744.0;
+    double r = fma(kd, -0x1.62e4200000000p-5, x);
+    r = fma(kd, -EXPC.lo, r);
+    double q = fma(EXPC.c7, r, EXPC.c6);
+    q = fma(q, r, EXPC.c5);
+    q = fma(q, r, EXPC.c4);
+    q = fma(q, r, EXPC.c3);
+    q = fma(q, r, 0.5);
+    const double p = fma(q * r, r, r);
+    const double t = tab[k & 15];
+    const double e = fma(t, p, t);
+    return __hiloint2double(__double2hiint(e) + ((k >> 4) << 20), __double2loint(e));
+}
+__device__ __forceinline__ bool exp_tab16_ok(double x) { return fabs(x) < 700.0; }
+__device__ __noinline__ double exp_tab16_fix(double x, double e) { return exp_tab16_ok(x) ? e : exp(x); }
+
+// The form of k_loglik_weights_mvn the library launches when the staging area and the statistics both fit
+// shared memory (smem layout: [M][blockDim] staging | [2][M][4] statistics | 16 table entries).  Same
+// arithmetic up to the exponential; the exponential is exp_tab16 and the M divisions by the normaliser are
+// one reciprocal and M products when the normaliser is an ordinary number (2^-1000 < total < 2^1000: the
+// product is then within 1.5 ulp of the quotient); zero, subnormal, huge, infinite and NaN normalisers take
+// the divisions, so 0/0, x/inf and NaN come out as in the reference (weights.py:122-123).
+// 100 -> ~40 instructions per (point, member): the kernel was issue-bound (ncu r01n: 88 instructions per
+// member executed, issue slots 68 % busy, DRAM at 35 %).
+template <bool LLS>
+__global__ void __launch_bounds__(128, 8)
+    k_loglik_weights_mvn_tab(const double* __restrict__ stats, const double* __restrict__ obs, int C, int M, int Ro,
+                             int T, double cst, double* __restrict__ w, double* __restrict__ lls_exp,
+                             double* __restrict__ lls_mean) {
+    extern __shared__ double wstage[];
+    const size_t gid0 = (size_t)blockIdx.x * blockDim.x;
+    const size_t gid = gid0 + threadIdx.x;
+    const size_t n_pts = (size_t)C * T;
+    const int c0 = (int)(gid0 / T);
+    const int c_last = (int)((min(gid0 + blockDim.x, n_pts) - 1) / T);
+    double* sst = wstage + (size_t)M * blockDim.x;
+    double* tab = sst + (size_t)2 * M * 4;
+    const bool stats_in_smem = c_last - c0 <= 1;
+    if (stats_in_smem) {
+        const int n = (c_last - c0 + 1) * M * 4;
+        for (int e = threadIdx.x; e < n; e += blockDim.x) sst[e] = stats[(size_t)c0 * M * 4 + e];
+    }
+    if (threadIdx.x < 16) tab[threadIdx.x] = EXP2_16TH[threadIdx.x];
+    __syncthreads();
+    if (gid >= n_pts) return;
+    const int c = (int)(gid / T), i = (int)(gid - (size_t)c * T);
+    double* stg = wstage + threadIdx.x;
+    const int bs = blockDim.x;
+    const double* ob = obs + (size_t)c * Ro * T + i;
+    double m1 = 0.0, m2 = 0.0;
+#pragma unroll 5
+    for (int r = 0; r < Ro; ++r) {
+        double o = ob[(size_t)r * T];
+        m1 += o;
+        m2 = fma(o, o, m2);
+    }
+    m1 /= Ro;
+    m2 /= Ro;
+    const double base = -0.5 * (double)T * LOG_2PI;
+    const double m1x2 = 2.0 * m1;
+    double total = 0.0;
+    const double2* sp = stats_in_smem ? reinterpret_cast<const double2*>(sst + (size_t)(c - c0) * M * 4)
+                                      : reinterpret_cast<const double2*>(stats + (size_t)c * M * 4);
+    double* wp = w + (size_t)c * M * T + i;
+    // members four at a time: the four exponential chains are independent and branch-free
+    auto member = [&](int m, double& x, double& mean) {
+        const double2 s01 = sp[2 * m], s23 = sp[2 * m + 1];
+        double maha = (m2 * s01.x - m1x2 * s01.y) + s23.x;
+        mean = (-0.5 * maha + base) - s23.y;
+        x = cst * mean;
+    };
+    auto emit = [&](int m, double mean, double e) {
+        if (LLS) {
+            size_t o = ((size_t)c * M + m) * T + i;
+            if (lls_mean) lls_mean[o] = mean;
+            if (lls_exp) lls_exp[o] = e;
+        }
+        stg[m * bs] = e;
+        total += e;
+    };
+    int m = 0;
+    for (; m + 4 <= M; m += 4) {
+        double x[4], mean[4], e[4];
+        bool ok = true;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            member(m + j, x[j], mean[j]);
+            e[j] = exp_tab16_core(x[j], tab);
+            ok = ok && exp_tab16_ok(x[j]);
+        }
+        if (!ok) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) e[j] = exp_tab16_fix(x[j], e[j]);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) emit(m + j, mean[j], e[j]);
+    }
+    for (; m < M; ++m) {
+        double x, mean;
+        member(m, x, mean);
+        emit(m, mean, exp_tab16_fix(x, exp_tab16_core(x, tab)));
+    }
+    if (total > 0x1p-1000 && total < 0x1p1000) {
+        const double inv = 1.0 / total;
+#pragma unroll 4
+        for (int m = 0; m < M; ++m) wp[(size_t)m * T] = stg[m * bs] * inv;
+    } else {
+        for (int m = 0; m < M; ++m) wp[(size_t)m * T] = stg[m * bs] / total;
+    }
+}
+
 __global__ void k_normal_logprob(const double* __restrict__ loc, const double* __restrict__ scale,
                                  const double* __restrict__ x, size_t n, double* __restrict__ ll) {
     size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;

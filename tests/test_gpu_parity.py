@@ -251,6 +251,56 @@ def test_weights_reference_test_shapes(backend, M, Ro):
     assert np.allclose(w[:, ok].sum(axis=0), 1.0, atol=1e-6)
 
 
+def _stats_for_exponent(backend, x, T):
+    """mvn statistics (|a|^2, a.b, |b|^2, sum log diag L) under which a zero observation's mean log-density is x"""
+    import torch
+
+    st = torch.zeros(len(x), 4, dtype=torch.float64, device=backend.device)
+    st[:, 3] = -torch.as_tensor(x, dtype=torch.float64, device=backend.device) - 0.5 * T * np.log(2 * np.pi)
+    return st
+
+
+def test_weights_exponential_whole_range(backend):
+    """exp_tab16 of k_loglik_weights_mvn_tab (be_kernels.cuh) against the oracle's np.exp over the exponent
+    range of the fast path and beyond it (overflow, gradual underflow), for M % 4 != 0 as well."""
+    import torch
+
+    rng = np.random.default_rng(11)
+    for M in (24, 7):
+        C, T = 16, 96
+        x = rng.uniform(-760.0, 720.0, size=C * M)
+        x[:6] = [0.0, 709.7, -745.0, 699.999999, -700.0, 1e-9]
+        obs = torch.zeros(C, 2, T, dtype=torch.float64, device=backend.device)
+        w, le, lm = backend.loglik_weights_mvn(_stats_for_exponent(backend, x, T), obs, M, want_lls=True)
+        lm, le, w = lm.cpu().numpy(), le.cpu().numpy(), w.cpu().numpy()
+        with np.errstate(over="ignore", under="ignore", invalid="ignore"):
+            want = np.exp(lm)
+            pos = np.isfinite(want) & (want > 0)
+            assert (np.abs(le - want)[pos] <= 4e-16 * want[pos] + 1e-323).all()
+            assert np.array_equal(le[~pos], want[~pos])  # overflow -> inf, underflow -> 0
+            w_o = le / le.sum(axis=1, keepdims=True)
+        _nan_equal_close(w, w_o, 1e-14, "weights")
+
+
+@pytest.mark.parametrize("x", [-800.0, -740.0, -700.0, 690.0, 720.0, float("nan")])
+def test_weights_normaliser_special_cases(backend, x):
+    """weights.py:122-123 divides by the sum over models: 0/0 (every member underflows), a subnormal sum, a
+    sum near the overflow threshold, inf/inf and NaN must come out as the division gives them."""
+    import torch
+
+    M, T = 10, 40
+    xs = np.full(M, x)
+    xs[0] = x - 3.0
+    obs = torch.zeros(1, 3, T, dtype=torch.float64, device=backend.device)
+    st = _stats_for_exponent(backend, xs, T)
+    w, le, _ = backend.loglik_weights_mvn(st, obs, M, want_lls=True)
+    assert torch.equal(w.nan_to_num(nan=-1.0), backend.loglik_weights_mvn(st, obs, M).nan_to_num(nan=-1.0))
+    w, le = w.cpu().numpy(), le.cpu().numpy()
+    with np.errstate(over="ignore", under="ignore", invalid="ignore"):
+        w_o = le / le.sum(axis=1, keepdims=True)
+    _nan_equal_close(w, w_o, 1e-13, "weights")
+
+
 def test_normal_branch(backend):
     rng = np.random.default_rng(5)
     C, M, Ro, N = 2, 4, 3, 77

@@ -748,9 +748,9 @@ int be_loglik_weights_mvn(be_ctx* ctx, const double* mvn_stats, const double* ob
     const int wb = weight_stage_block(M);
     const size_t wsm = weight_stage_bytes(M);
     const size_t ssm = weight_stats_bytes(M) <= 16384 ? weight_stats_bytes(M) : 0;
-    // opt-in until its GPU tests have run (tests/test_gpu_parity.py::test_weights_exponential_whole_range)
-    static const bool use_tab = getenv("BE_WEIGHTS_TAB") != nullptr;
-    if (wsm > 0 && ssm > 0 && use_tab) {
+    // BE_WEIGHTS_LIBEXP: the library-exp kernel for every M (the A/B switch of tools/prof_weights_ab.py)
+    static const bool lib_exp = getenv("BE_WEIGHTS_LIBEXP") != nullptr;
+    if (wsm > 0 && ssm > 0 && !lib_exp) {
         const size_t sm = wsm + ssm + 16 * sizeof(double);
         if (lls_exp || lls_mean)
             k_loglik_weights_mvn_tab<true><<<grid1d((size_t)C * T, wb), wb, sm, ctx->stream>>>(

@@ -649,16 +649,12 @@ __host__ inline size_t weight_stats_bytes(int M) { return (size_t)2 * M * 4 * si
 // (same terms as summing the Ro log-densities, one rounding pattern apart: ~1e-13 on the weights).
 // That takes the kernel from M*Ro to M density evaluations per point (15% -> 42% of the HBM peak at 4M
 // points, bench.py hbm_stages); the per-realisation values stay available from k_mvn_constvec_logprob.
-// (Variants that interleave four fast-exp chains, or keep the un-normalised weights in registers instead of
-// re-reading them, measured SLOWER at 4M points -- 0.44 / 0.52 ms against 0.40 ms: the kernel is latency-bound
-// at the occupancy those variants allow, not ALU- or traffic-bound.)
 // The (|a|^2, a.b, |b|^2, sum log diag L) statistics of the one or two cells a CTA's points belong to are
 // copied to shared memory first (read per member from global memory they are a dependent L2 round trip per
-// loop trip: the staging buffer leaves almost no L1).  exp and the division are the library's: variants with
-// a branch-free exp core and a shared-reciprocal division, four members interleaved, measured SLOWER
-// (0.42 against 0.36 ms at 4 M points, 24 members: more registers, fewer resident warps); so did a form with
-// four lanes per point (each lane a quarter of the members, normaliser by xor-shuffles, full occupancy):
-// 0.58 ms -- the 64-byte row segments it loads and stores quadruple the memory requests.
+// loop trip: the staging buffer leaves almost no L1).
+// This form (library exp, M divisions) is ISSUE-bound: ~100 instructions per (point, member), 48 % of the HBM
+// peak at 4 M points x 24 members.  It is what the library launches only when the staging area does not fit
+// shared memory; otherwise k_loglik_weights_mvn_tab below (69 %).
 __global__ void k_loglik_weights_mvn(const double* __restrict__ stats, const double* __restrict__ obs, int C, int M,
                                      int Ro, int T, double cst, double* __restrict__ w, double* __restrict__ lls_exp,
                                      double* __restrict__ lls_mean, int smem_ok) {

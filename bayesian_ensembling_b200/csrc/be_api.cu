@@ -754,10 +754,10 @@ int be_loglik_weights_mvn(be_ctx* ctx, const double* mvn_stats, const double* ob
         const size_t sm = wsm + ssm + 16 * sizeof(double);
         if (lls_exp || lls_mean)
             k_loglik_weights_mvn_tab<true><<<grid1d((size_t)C * T, wb), wb, sm, ctx->stream>>>(
-                mvn_stats, obs, C, M, Ro, T, standardisation_constant, weights, lls_exp, lls_mean);
+                mvn_stats, obs, C, M, Ro, T, standardisation_constant, 1.0 / Ro, weights, lls_exp, lls_mean);
         else
             k_loglik_weights_mvn_tab<false><<<grid1d((size_t)C * T, wb), wb, sm, ctx->stream>>>(
-                mvn_stats, obs, C, M, Ro, T, standardisation_constant, weights, nullptr, nullptr);
+                mvn_stats, obs, C, M, Ro, T, standardisation_constant, 1.0 / Ro, weights, nullptr, nullptr);
     } else {
         k_loglik_weights_mvn<<<grid1d((size_t)C * T, wb), wb, wsm + ssm, ctx->stream>>>(
             mvn_stats, obs, C, M, Ro, T, standardisation_constant, weights, lls_exp, lls_mean,

@@ -756,25 +756,39 @@ __device__ __noinline__ double exp_tab16_fix(double x, double e) { return exp_ta
 template <bool LLS>
 __global__ void __launch_bounds__(128, 8)
     k_loglik_weights_mvn_tab(const double* __restrict__ stats, const double* __restrict__ obs, int C, int M, int Ro,
-                             int T, double cst, double* __restrict__ w, double* __restrict__ lls_exp,
+                             int T, double cst, double inv_ro, double* __restrict__ w, double* __restrict__ lls_exp,
                              double* __restrict__ lls_mean) {
     extern __shared__ double wstage[];
+    // One 64-bit division per CTA-uniform quantity (gid0 / T); everything per thread is 32-bit and, when a row
+    // is at least as long as the CTA (the usual case), division-free: the prologue was ~300 of the ~1400
+    // instructions a warp executes at M = 24.
     const size_t gid0 = (size_t)blockIdx.x * blockDim.x;
-    const size_t gid = gid0 + threadIdx.x;
     const size_t n_pts = (size_t)C * T;
-    const int c0 = (int)(gid0 / T);
-    const int c_last = (int)((min(gid0 + blockDim.x, n_pts) - 1) / T);
+    const unsigned uT = (unsigned)T;
+    const int c0 = (int)(gid0 / uT);
+    const unsigned i0 = (unsigned)(gid0 - (size_t)c0 * uT);
+    const unsigned nvalid = (unsigned)min((size_t)blockDim.x, n_pts - gid0);
+    const unsigned loc = i0 + threadIdx.x;
+    unsigned spans, dc;
+    if (uT >= blockDim.x) {  // the CTA's points lie in at most two cells
+        spans = i0 + nvalid - 1 >= uT;
+        dc = loc >= uT;
+    } else {
+        spans = (i0 + nvalid - 1) / uT;
+        dc = loc / uT;
+    }
     double* sst = wstage + (size_t)M * blockDim.x;
     double* tab = sst + (size_t)2 * M * 4;
-    const bool stats_in_smem = c_last - c0 <= 1;
+    const bool stats_in_smem = spans <= 1;
     if (stats_in_smem) {
-        const int n = (c_last - c0 + 1) * M * 4;
-        for (int e = threadIdx.x; e < n; e += blockDim.x) sst[e] = stats[(size_t)c0 * M * 4 + e];
+        const int n = (int)(spans + 1) * M * 4;
+        const double* src = stats + (size_t)c0 * M * 4;
+        for (int e = threadIdx.x; e < n; e += blockDim.x) sst[e] = src[e];
     }
     if (threadIdx.x < 16) tab[threadIdx.x] = EXP2_16TH[threadIdx.x];
     __syncthreads();
-    if (gid >= n_pts) return;
-    const int c = (int)(gid / T), i = (int)(gid - (size_t)c * T);
+    if (threadIdx.x >= nvalid) return;
+    const int c = c0 + (int)dc, i = (int)(loc - dc * uT);
     double* stg = wstage + threadIdx.x;
     const int bs = blockDim.x;
     const double* ob = obs + (size_t)c * Ro * T + i;
@@ -785,12 +799,12 @@ __global__ void __launch_bounds__(128, 8)
         m1 += o;
         m2 = fma(o, o, m2);
     }
-    m1 /= Ro;
-    m2 /= Ro;
+    m1 *= inv_ro;  // 1 / Ro from the host: within an ulp of the quotient the library-exp form takes
+    m2 *= inv_ro;
     const double base = -0.5 * (double)T * LOG_2PI;
     const double m1x2 = 2.0 * m1;
     double total = 0.0;
-    const double2* sp = stats_in_smem ? reinterpret_cast<const double2*>(sst + (size_t)(c - c0) * M * 4)
+    const double2* sp = stats_in_smem ? reinterpret_cast<const double2*>(sst + (size_t)dc * M * 4)
                                       : reinterpret_cast<const double2*>(stats + (size_t)c * M * 4);
     double* wp = w + (size_t)c * M * T + i;
     // members four at a time: the four exponential chains are independent and branch-free

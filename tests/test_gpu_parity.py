@@ -266,8 +266,10 @@ def test_weights_exponential_whole_range(backend):
     import torch
 
     rng = np.random.default_rng(11)
-    for M in (24, 7):
-        C, T = 16, 96
+    # (M, T): rows shorter and longer than the CTA (128 threads to M = 32, 64 beyond), M % 4 != 0, and an M whose
+    # staging does not fit shared memory (the library-exp kernel with the output array as staging)
+    for M, T in ((24, 96), (7, 96), (40, 300), (33, 50), (24, 129), (200, 70)):
+        C = 16
         x = rng.uniform(-760.0, 720.0, size=C * M)
         x[:6] = [0.0, 709.7, -745.0, 699.999999, -700.0, 1e-9]
         obs = torch.zeros(C, 2, T, dtype=torch.float64, device=backend.device)

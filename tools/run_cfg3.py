@@ -2,7 +2,7 @@
 monthly (T = 1980), 24 models x 5 realisations, per-cell GP posterior + LogLikelihoodWeight + Barycentre, cells
 sharded across the ranks of one box with no data-path collective.  One JSON line from rank 0.
 
-    python tools/run_cfg3.py [--cells 2592] [--wave 24] [--posterior dense|factored] [--y-mean mean|dba]
+    python tools/run_cfg3.py [--workload cfg3|cfg4] [--cells 2592] [--wave 24] [--posterior dense|factored] [--y-mean mean|dba]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 tools/run_cfg3.py
 
 Inputs are generated on the host per wave (seeded per cell, so any sharding reproduces the same numbers) and
@@ -27,8 +27,10 @@ from bayesian_ensembling_b200.backend import Backend  # noqa: E402
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--cells", type=int, default=2592)
-    ap.add_argument("--wave", type=int, default=24, help="cells per device wave")
+    ap.add_argument("--workload", default="cfg3", choices=["cfg3", "cfg4"],
+                    help="cfg4: 1 x 1 degree grid (64 800 cells) x 251 years annual, 40 models x 10 realisations")
+    ap.add_argument("--cells", type=int, default=0, help="0: the whole grid (2592 / 64 800)")
+    ap.add_argument("--wave", type=int, default=0, help="cells per device wave (0: 24 / 128)")
     ap.add_argument("--posterior", default="dense", choices=["dense", "factored"])
     ap.add_argument("--y-mean", default="mean", choices=["mean", "dba"])
     args = ap.parse_args()
@@ -43,7 +45,9 @@ def main():
 
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     be = Backend.get()
-    cfg = synthetic.CONFIGS["cfg3"]
+    cfg = synthetic.CONFIGS[args.workload]
+    args.cells = args.cells or (2592 if args.workload == "cfg3" else 64800)
+    args.wave = args.wave or (24 if args.workload == "cfg3" else 128)
     lo, hi = grid.shard_range(args.cells, rank, world)
     var, ls = synthetic.L1_VARIANCE, synthetic.L1_LENGTHSCALE
     dev_ms, n_nan_cols, n_cols, worst_sum, bad_info = 0.0, 0, 0, 0.0, 0
@@ -92,7 +96,9 @@ def main():
         mx = sm = mn = stats
     if rank == 0:
         line = {
-            "config": "cfg3 full size: %d cells x 24 members x 5 realisations x 1980 months" % args.cells,
+            "config": "%s%s: %d cells x %d members x %d realisations x %d time steps" % (
+                args.workload, " full size" if args.cells in (2592, 64800) else " (part of the grid)", args.cells,
+                cfg.members, cfg.realisations, cfg.steps),
             "n_gpus": world, "cells": args.cells, "cells_per_wave": args.wave, "posterior": args.posterior,
             "y_mean": args.y_mean,
             "device_seconds_max_over_ranks": float(mx[0]) / 1e3,

@@ -216,8 +216,9 @@ def measure_hbm_stages(be, cfg, n_points, hbm_peak, reps=5):
     res["k_barycentre"] = (ms, N * (24.0 * M + 16.0 + 4.0))
     # SURVEY 8f rows 2-3 (CRPSWeight is the weight the published experiment uses): same [C, M, N] layout.  Their
     # HBM bytes are as small as the log-likelihood kernel's, but the reference arithmetic asks for M * Ro erfc + exp
-    # (CRPS), M * Ro^2 kernel evaluations (KSD) and M^2 square roots (similarity) per point: FP64-pipe work, so
-    # the fraction of the HBM peak is reported for what it is, next to the evaluations per second.
+    # (CRPS), M * Ro^2 kernel evaluations (KSD; the kernel's factored form does Ro (Ro - 1) / 2 per point, the
+    # figure below counts the reference's M * Ro^2) and M^2 square roots (similarity) per point: FP64-pipe work,
+    # so the fraction of the HBM peak is reported for what it is, next to the evaluations per second.
     sd = variances.sqrt()
     ms, wc = timed(lambda: be.crps_weights(means, sd, obs))
     assert bool(torch.isfinite(wc).all())

@@ -754,6 +754,15 @@ def test_ksd_weights_vs_oracle(backend):
         assert rel_err(k[c].cpu().numpy(), ko) < 1e-12
         assert rel_err(w[c].cpu().numpy(), wo) < 1e-12
         assert np.abs(w[c].cpu().numpy().sum(axis=0) - 1.0).max() < 1e-12
+    # tightly clustered samples with the model mean inside the cluster: the regime where the kernel's factored
+    # form (moments of the pair kernel about the sample mean, weights_next_kernels.cuh) cancels the most
+    obs_c = 0.8 + 1e-3 * rng.normal(size=(C, 10, N))
+    loc_c = 0.8 + 1e-3 * rng.normal(size=(C, M, N))
+    w, k = backend.ksd_weights(_t(backend, loc_c), _t(backend, var), _t(backend, obs_c), want_ksd=True)
+    for c in range(C):
+        wo, ko = rp.ksd_weights(loc_c[c], var[c], obs_c[c])
+        assert np.abs(k[c].cpu().numpy() / ko - 1.0).max() < 1e-11
+        assert rel_err(w[c].cpu().numpy(), wo) < 1e-11
     # a single observation realisation: k0(a, a) = g^2 + 1
     w1, k1 = backend.ksd_weights(_t(backend, loc), _t(backend, var), _t(backend, obs[:, :1]), want_ksd=True)
     g = -(obs[:, :1] - loc) / var ** 2

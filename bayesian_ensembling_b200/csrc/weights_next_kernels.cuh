@@ -8,12 +8,21 @@ namespace be {
 constexpr double INV_SQRT_PI = 0.5641895835477563;
 constexpr double INV_SQRT_2PI = 0.3989422804014327;
 
-// properscoring.crps_gaussian: sig (z (2 Phi(z) - 1) + 2 phi(z) - 1/sqrt(pi)),  z = (x - mu) / sig
-__device__ __forceinline__ double crps_gaussian_d(double x, double mu, double sig) {
-    double z = (x - mu) / sig;
-    double pdf = exp(-0.5 * z * z) * INV_SQRT_2PI;
-    double cdf = normcdf(z);
-    return sig * (z * (2.0 * cdf - 1.0) + 2.0 * pdf - INV_SQRT_PI);
+// properscoring.crps_gaussian: sig (z (2 Phi(z) - 1) + 2 phi(z) - 1/sqrt(pi)),  z = (x - mu) / sig.
+// 2 Phi(z) - 1 is erf(z / sqrt 2) (no cancellation at small z, and half the cost of normcdf, which is an erfc
+// with its own exponential and division); the exponential is exp_tab16 (be_kernels.cuh); the division by sig is
+// a product with 1 / sig, formed once per model, when sig is an ordinary number (2^-500 < |sig| < 2^500;
+// zero, subnormal, infinite and NaN scales keep the division and with it the reference's inf / NaN results).
+__device__ __forceinline__ double crps_gaussian_d(double x, double mu, double sig, double inv_sig, bool ordinary,
+                                                  const double* __restrict__ tab) {
+    const double d = x - mu;
+    const double z = ordinary ? d * inv_sig : d / sig;
+    const double a = -0.5 * z * z;
+    double e = exp_tab16_core(a, tab);
+    if (!exp_tab16_ok(a)) e = exp(a);
+    const double pdf = e * INV_SQRT_2PI;
+    const double two_cdf_m1 = erf(z * 0.70710678118654752440);
+    return sig * (z * two_cdf_m1 + 2.0 * pdf - INV_SQRT_PI);
 }
 
 // one thread per (cell, point): weights.py:469-471 (mean over obs realisations), :507 (inverse),
@@ -23,6 +32,9 @@ __global__ void k_crps_weights(const double* __restrict__ loc, const double* __r
                                const double* __restrict__ obs, int C, int M, int Ro, int N, double* __restrict__ w,
                                double* __restrict__ crps_mean, int smem_ok) {
     extern __shared__ double wstage[];
+    __shared__ double tab[16];
+    if (threadIdx.x < 16) tab[threadIdx.x] = EXP2_16TH[threadIdx.x];
+    __syncthreads();
     size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (gid >= (size_t)C * N) return;
     int c = (int)(gid / N), i = (int)(gid % N);
@@ -31,9 +43,12 @@ __global__ void k_crps_weights(const double* __restrict__ loc, const double* __r
     double total = 0.0;
     for (int m = 0; m < M; ++m) {
         size_t o = ((size_t)c * M + m) * N + i;
-        double l = loc[o], sc = scale[o];
+        const double l = loc[o], sc = scale[o];
+        const bool ordinary = fabs(sc) > 0x1p-500 && fabs(sc) < 0x1p500;
+        const double inv_sc = 1.0 / sc;
         double s = 0.0;
-        for (int r = 0; r < Ro; ++r) s += crps_gaussian_d(ob[(size_t)r * N], l, sc);
+#pragma unroll 2
+        for (int r = 0; r < Ro; ++r) s += crps_gaussian_d(ob[(size_t)r * N], l, sc, inv_sc, ordinary, tab);
         double mean = s / Ro;
         if (crps_mean) crps_mean[o] = mean;
         double inv = 1.0 / mean;

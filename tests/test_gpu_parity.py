@@ -741,6 +741,26 @@ def test_crps_weights_vs_oracle(backend):
         assert np.abs(w[c].cpu().numpy().sum(axis=0) - 1.0).max() < 1e-12
 
 
+def test_crps_special_scales_and_far_observations(backend):
+    """Scales that are zero, subnormal, infinite or NaN keep the reference's division (inf / NaN results equal
+    to the oracle's); observations hundreds of scales away take the library exp; many realisations."""
+    rng = np.random.default_rng(8)
+    C, M, Ro, N = 1, 8, 10, 64
+    loc = rng.normal(size=(C, M, N))
+    scale = rng.uniform(0.002, 2.0, size=(C, M, N))
+    scale[0, 0, :4] = [0.0, 1e-320, np.inf, np.nan]
+    scale[0, 1, 4:8] = [1e-200, 1e200, 1e-3, 50.0]
+    obs = rng.normal(size=(C, Ro, N))
+    _, cm = backend.crps_weights(_t(backend, loc), _t(backend, scale), _t(backend, obs), want_crps=True)
+    with np.errstate(all="ignore"):
+        _, co = rp.crps_weights(loc[0], scale[0], obs[0])
+    got = cm[0].cpu().numpy()
+    assert np.array_equal(np.isnan(got), np.isnan(co))
+    assert np.array_equal(np.isinf(got), np.isinf(co)) and np.array_equal(got[np.isinf(co)], co[np.isinf(co)])
+    fin = np.isfinite(co)
+    assert np.abs(got[fin] / co[fin] - 1.0).max() < 1e-13
+
+
 def test_ksd_weights_vs_oracle(backend):
     """KSDWeight (weights.py:336-441): IMQ kernel Stein discrepancy per model and point."""
     rng = np.random.default_rng(4)

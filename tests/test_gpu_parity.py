@@ -805,6 +805,26 @@ def test_similarity_weights_vs_oracle(backend):
     wto, w2to = rp.model_similarity_weights_temporal(mus, var)
     assert np.abs(w2t[0].cpu().numpy() - w2to).max() < 1e-13
     assert rel_err(wt[0].cpu().numpy(), wto) < 1e-12
+    # without the pair distances the kernel takes its M-square-roots form wherever the point is clean; a NaN mean,
+    # a negative variance or an infinite one at a point sends that point through the NaN-skipping pair loop
+    wt_fast = backend.similarity_weights_pointwise(_t(backend, mus[None]), _t(backend, (var * var)[None]))
+    assert rel_err(wt_fast[0].cpu().numpy(), wto) < 1e-12
+    rng = np.random.default_rng(23)
+    Mb, Nb = 24, 200
+    mu_b, v_b = rng.normal(size=(Mb, Nb)), rng.uniform(0.05, 0.5, size=(Mb, Nb))
+    mu_b[3, 5] = np.nan
+    v_b[7, 9] = -0.1
+    v_b[2, 11] = np.inf
+    got = backend.similarity_weights_pointwise(_t(backend, mu_b[None]), _t(backend, (v_b * np.abs(v_b))[None]))[0].cpu().numpy()
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        with np.errstate(all="ignore"):
+            r = np.sqrt(v_b * np.abs(v_b))
+            dist = np.abs(mu_b[:, None] - mu_b[None]) + ((v_b * np.abs(v_b))[:, None] + (v_b * np.abs(v_b))[None]
+                                                         - 2.0 * np.sqrt(r[:, None] * (v_b * np.abs(v_b))[None] * r[:, None]))
+            mean_d = np.nanmean(dist, axis=1)
+            want = mean_d / mean_d.sum(axis=0)
+    _nan_equal_close(got, want, 1e-12, "temporal similarity weights")
     # NaN distances are skipped by the nanmean
     d = np.arange(1.0, 1.0 + M * M * 3).reshape(1, M, M, 3)
     d[0, 1, 2, 0] = np.nan

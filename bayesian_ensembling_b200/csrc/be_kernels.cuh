@@ -862,28 +862,57 @@ __global__ void k_normal_logprob(const double* __restrict__ loc, const double* _
     ll[gid] = -0.5 * z * z - 0.5 * LOG_2PI - log(scale[gid]);
 }
 
+// Normal branch (weights.py:95-96: elementwise Normal log-pdf with scale = covariance, mean over the observation
+// realisations, exp, normalise).  The log-density is quadratic in the observation, so its mean needs only the
+// sample mean and the centred second moment of the point's Ro observations:
+//   mean_r ll = -1/2 (var_o + (mean_o - loc)^2) / scale^2 - 1/2 log 2pi - log scale,   var_o = mean_r (o_r - mean_o)^2
+// (centred, so nothing cancels when loc is close to the observations; the residual of the rounded mean is carried) -- one division and one log per model
+// instead of Ro divisions; scales that are not ordinary numbers (zero, subnormal, huge, infinite, NaN) keep
+// the per-realisation form and with it the reference's inf / NaN results.
 __global__ void k_loglik_weights_normal(const double* __restrict__ loc, const double* __restrict__ scale,
                                         const double* __restrict__ obs, int C, int M, int Ro, int N, double cst,
                                         double* __restrict__ w, double* __restrict__ lls_exp,
                                         double* __restrict__ lls_mean, int smem_ok) {
     extern __shared__ double wstage[];
+    __shared__ double tab[16];
+    if (threadIdx.x < 16) tab[threadIdx.x] = EXP2_16TH[threadIdx.x];
+    __syncthreads();
     size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (gid >= (size_t)C * N) return;
     int c = (int)(gid / N), i = (int)(gid % N);
     WeightStage st(wstage, smem_ok, w + (size_t)c * M * N + i, (size_t)N);
     const double* ob = obs + (size_t)c * Ro * N + i;
+    double mean_o = 0.0;
+    for (int r = 0; r < Ro; ++r) mean_o += ob[(size_t)r * N];
+    mean_o /= Ro;
+    double var_o = 0.0, mean_d = 0.0;  // mean_d: what the rounded pivot mean_o leaves of mean_r (o_r - mean_o)
+    for (int r = 0; r < Ro; ++r) {
+        const double d = ob[(size_t)r * N] - mean_o;
+        var_o = fma(d, d, var_o);
+        mean_d += d;
+    }
+    var_o /= Ro;
+    mean_d /= Ro;
     double total = 0.0;
     for (int m = 0; m < M; ++m) {
         size_t o = ((size_t)c * M + m) * N + i;
         double l = loc[o], sc = scale[o];
         double lsc = log(sc);
-        double s = 0.0;
-        for (int r = 0; r < Ro; ++r) {
-            double z = (ob[(size_t)r * N] - l) / sc;
-            s += -0.5 * z * z - 0.5 * LOG_2PI - lsc;
+        double mean;
+        if (sc > 0x1p-500 && sc < 0x1p500) {
+            const double dl = mean_o - l;  // (o_r - loc) = d_r + dl exactly, for any pivot
+            mean = (-0.5 * (fma(dl, 2.0 * mean_d + dl, var_o) / (sc * sc)) - 0.5 * LOG_2PI) - lsc;
+        } else {
+            double s = 0.0;
+            for (int r = 0; r < Ro; ++r) {
+                double z = (ob[(size_t)r * N] - l) / sc;
+                s += -0.5 * z * z - 0.5 * LOG_2PI - lsc;
+            }
+            mean = s / Ro;
         }
-        double mean = s / Ro;
-        double e = exp(cst * mean);
+        const double x = cst * mean;
+        double e = exp_tab16_core(x, tab);
+        if (!exp_tab16_ok(x)) e = exp(x);
         if (lls_mean) lls_mean[o] = mean;
         if (lls_exp) lls_exp[o] = e;
         st[m] = e;

@@ -225,6 +225,10 @@ def measure_hbm_stages(be, cfg, n_points, hbm_peak, reps=5):
     res["k_crps_weights"] = (ms, N * 8.0 * (Ro + 3.0 * M))
     ms, _ = timed(lambda: be.ksd_weights(means, sd, obs))
     res["k_ksd_weights"] = (ms, N * 8.0 * (Ro + 3.0 * M))
+    loc_n, scale_n = (obs.mean(dim=1, keepdim=True) + 0.1 * (means - 0.5)).contiguous(), 0.3 + sd
+    ms, wn = timed(lambda: be.loglik_weights_normal(loc_n, scale_n, obs))
+    assert bool(torch.isfinite(wn).all())
+    res["k_loglik_weights_normal"] = (ms, N * 8.0 * (Ro + 3.0 * M))
     ms, _ = timed(lambda: be.similarity_weights_pointwise(means, variances))
     res["k_similarity_pointwise"] = (ms, N * 8.0 * 3.0 * M)
     evals = {"k_crps_weights": float(N) * M * Ro, "k_ksd_weights": float(N) * M * Ro * Ro,

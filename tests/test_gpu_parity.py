@@ -251,6 +251,28 @@ def test_weights_reference_test_shapes(backend, M, Ro):
     assert np.allclose(w[:, ok].sum(axis=0), 1.0, atol=1e-6)
 
 
+def test_normal_branch_moment_form_and_special_scales(backend):
+    """k_loglik_weights_normal takes the mean log-density from the observations' mean and centred second moment;
+    zero / negative / subnormal / infinite / NaN scales keep the per-realisation form: all against the oracle,
+    including observations tightly clustered far from zero with the model mean inside the cluster."""
+    rng = np.random.default_rng(15)
+    C, M, Ro, N = 1, 9, 10, 80
+    loc = 288.0 + 1e-3 * rng.normal(size=(C, M, N))
+    obs = 288.0 + 1e-3 * rng.normal(size=(C, Ro, N))
+    scale = rng.uniform(5e-4, 5e-3, size=(C, M, N))
+    scale[0, 0, :6] = [0.0, -0.2, 1e-320, np.inf, np.nan, 1e-200]
+    w, le, lm = backend.loglik_weights_normal(_t(backend, loc), _t(backend, scale), _t(backend, obs), want_lls=True)
+    with np.errstate(all="ignore"):
+        wo, eo, lo = rp.loglik_weights_normal(loc[0], scale[0], obs[0])
+    got = lm[0].cpu().numpy()
+    assert np.array_equal(np.isnan(got), np.isnan(lo))
+    inf = np.isinf(lo)
+    assert np.array_equal(np.isinf(got), inf) and np.array_equal(got[inf], lo[inf])
+    fin = np.isfinite(lo)
+    assert np.abs(got[fin] - lo[fin]).max() <= 1e-12 * np.abs(lo[fin]).max()
+    _nan_equal_close(w[0].cpu().numpy(), wo, 1e-9, "weights")  # exp amplifies the 1e-12 of exponents up to ~1e3
+
+
 def _stats_for_exponent(backend, x, T):
     """mvn statistics (|a|^2, a.b, |b|^2, sum log diag L) under which a zero observation's mean log-density is x"""
     import torch

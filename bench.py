@@ -147,7 +147,7 @@ def run_reference(args, cfg):
         return
     _use_all_host_threads()
     threads, blas = _blas_threads()
-    m = args.cpu_members
+    m = min(cfg.members, args.cpu_members or (6 if cfg.steps >= 1000 else cfg.members))
     for _ in range(args.warmup):
         cpu_sample_seconds(cfg, m)
     t0 = time.perf_counter()
@@ -523,7 +523,7 @@ def run_ours(args, cfg):
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         _use_all_host_threads()
         threads, blas = _blas_threads()
-        m = args.cpu_members
+        m = min(cfg.members, args.cpu_members or (6 if cfg.steps >= 1000 else cfg.members))
         dt = cpu_sample_seconds(cfg, m)
         cpu_baseline = {
             "value": 1.0 / (dt * cfg.members / m), "unit": UNIT, "cores": threads, "kind": "port",
@@ -579,7 +579,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg2")
     ap.add_argument("--cells-per-step", type=int, default=6)
-    ap.add_argument("--cpu-members", type=int, default=2, help="members of one cell the CPU arm times per step")
+    ap.add_argument("--cpu-members", type=int, default=0,
+                    help="members of one cell the CPU arm times per step (0: 6 for T >= 1000 -- about 12 s of CPU work "
+                         "at cfg2 on 16 threads -- else every member of the cell)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--hbm-points", type=int, default=4_000_000,
                     help="(cell, time) points of the stand-alone memory-bound stage measurements (0: skip)")

@@ -141,23 +141,59 @@ def cpu_sample_seconds(cfg, members, repeats=1):
     return best
 
 
+def _one_cell_single_thread(cfg_name, cell):
+    """Worker of cpu_small_t_cell_seconds: one whole cell through the oracle with one BLAS thread."""
+    from threadpoolctl import threadpool_limits
+
+    from bayesian_ensembling_b200 import synthetic
+    from oracle import reference_path as rp
+
+    cfg = synthetic.CONFIGS[cfg_name]
+    reals, obs = synthetic.make_cells(cfg, n_cells=1, cell_offset=cell)
+    with threadpool_limits(limits=1, user_api="blas"):
+        t0 = time.perf_counter()
+        rp.cell_pipeline_L1(reals[0], obs[0], synthetic.L1_VARIANCE, synthetic.L1_LENGTHSCALE)
+        return time.perf_counter() - t0
+
+
+def cpu_small_t_cell_seconds(cfg, rounds=2):
+    """Small T (cfg1 / cfg4 shapes): threaded BLAS does not pay on 251 x 251 matrices, so the host cores are used
+    the way SURVEY 8d asks -- one process per core, one BLAS thread each, every process a whole cell (all its
+    members).  Returns (seconds per cell at full occupancy of the host, processes, description)."""
+    from joblib import Parallel, delayed
+
+    procs = os.cpu_count() or 1
+    with Parallel(n_jobs=procs, backend="loky") as par:
+        par(delayed(_one_cell_single_thread)(cfg.name, c) for c in range(procs))  # worker start-up and imports
+        t0 = time.perf_counter()
+        par(delayed(_one_cell_single_thread)(cfg.name, c) for c in range(procs * rounds))
+        wall = time.perf_counter() - t0
+    return wall / (procs * rounds), procs, (
+        f"{procs * rounds} whole {cfg.name} cells (T={cfg.steps}, {cfg.members} members, Ro={cfg.obs_realisations}) on "
+        f"{procs} processes with one BLAS thread each: {wall:.1f} s")
+
+
 def run_reference(args, cfg):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     _use_all_host_threads()
     threads, blas = _blas_threads()
-    m = min(cfg.members, args.cpu_members or (6 if cfg.steps >= 1000 else cfg.members))
-    for _ in range(args.warmup):
-        cpu_sample_seconds(cfg, m)
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        cpu_sample_seconds(cfg, m)
-    dt = (time.perf_counter() - t0) / args.steps
-    cell_s = dt * cfg.members / m
+    if cfg.steps < 1000 and not args.cpu_members:
+        cell_s, threads, sample = cpu_small_t_cell_seconds(cfg, rounds=max(1, args.steps))
+        dt, blas = cell_s, blas + ", 1 thread per process"
+    else:
+        m = min(cfg.members, args.cpu_members or 6)
+        for _ in range(args.warmup):
+            cpu_sample_seconds(cfg, m)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            cpu_sample_seconds(cfg, m)
+        dt = (time.perf_counter() - t0) / args.steps
+        cell_s = dt * cfg.members / m
+        sample = (f"{m} of {cfg.members} members of one {cfg.name} cell per step (T={cfg.steps}, "
+                  f"Ro={cfg.obs_realisations}), scaled x{cfg.members / m:.0f} to a cell")
     value = 1.0 / cell_s
-    sample = (f"{m} of {cfg.members} members of one {cfg.name} cell per step (T={cfg.steps}, Ro={cfg.obs_realisations}), "
-              f"scaled x{cfg.members / m:.0f} to a cell")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
@@ -523,13 +559,18 @@ def run_ours(args, cfg):
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         _use_all_host_threads()
         threads, blas = _blas_threads()
-        m = min(cfg.members, args.cpu_members or (6 if cfg.steps >= 1000 else cfg.members))
-        dt = cpu_sample_seconds(cfg, m)
-        cpu_baseline = {
-            "value": 1.0 / (dt * cfg.members / m), "unit": UNIT, "cores": threads, "kind": "port",
-            "sample": f"{m} of {cfg.members} members of one {cfg.name} cell (T={cfg.steps}, Ro={cfg.obs_realisations}): "
-                      f"{dt:.1f} s, scaled x{cfg.members / m:.0f} to a cell",
-            "blas": blas, "host_cpus": os.cpu_count()}
+        if cfg.steps < 1000 and not args.cpu_members:
+            cell_s, procs, sample = cpu_small_t_cell_seconds(cfg, rounds=4)
+            cpu_baseline = {"value": 1.0 / cell_s, "unit": UNIT, "cores": procs, "kind": "port", "sample": sample,
+                            "blas": blas + ", 1 thread per process", "host_cpus": os.cpu_count()}
+        else:
+            m = min(cfg.members, args.cpu_members or 6)
+            dt = cpu_sample_seconds(cfg, m)
+            cpu_baseline = {
+                "value": 1.0 / (dt * cfg.members / m), "unit": UNIT, "cores": threads, "kind": "port",
+                "sample": f"{m} of {cfg.members} members of one {cfg.name} cell (T={cfg.steps}, "
+                          f"Ro={cfg.obs_realisations}): {dt:.1f} s, scaled x{cfg.members / m:.0f} to a cell",
+                "blas": blas, "host_cpus": os.cpu_count()}
 
     if rank == 0:
         line = {
@@ -580,8 +621,8 @@ def main():
     ap.add_argument("--workload", default="cfg2")
     ap.add_argument("--cells-per-step", type=int, default=6)
     ap.add_argument("--cpu-members", type=int, default=0,
-                    help="members of one cell the CPU arm times per step (0: 6 for T >= 1000 -- about 12 s of CPU work "
-                         "at cfg2 on 16 threads -- else every member of the cell)")
+                    help="members of one cell the CPU arm times per step with threaded BLAS (0: 6 for T >= 1000 -- about "
+                         "12 s of CPU work at cfg2 on 16 threads; for T < 1000 whole cells on one process per core)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--hbm-points", type=int, default=4_000_000,
                     help="(cell, time) points of the stand-alone memory-bound stage measurements (0: skip)")

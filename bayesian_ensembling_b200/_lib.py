@@ -53,6 +53,7 @@ SIGNATURES = {
     "be_mvn_from_cov": (_I, [_P, _P, _P, _I, _I, _P, _P, _P, _P, _P, _Z]),
     "be_loglik_weights_mvn": (_I, [_P, _P, _P, _I, _I, _I, _I, _D, _P, _P, _P]),
     "be_mvn_constvec_logprob": (_I, [_P, _P, _P, _I, _I, _I, _I, _P]),
+    "be_mvn_log_prob": (_I, [_P, _P, _P, _P, _I, _I, _D, _P]),
     "be_normal_logprob": (_I, [_P, _P, _P, _P, _Z, _P]),
     "be_loglik_weights_normal": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _D, _P, _P, _P]),
     "be_weights_time_mean": (_I, [_P, _P, _I, _I, _I, _P]),

@@ -269,6 +269,21 @@ class Backend:
         _lib.check(self.ctx, rc, "be_mvn_constvec_logprob")
         return ll
 
+    def mvn_log_prob(self, mu, scale_tri, x, sum_log_diag):
+        """mu [T], scale_tri [T,T] (dense lower factor), x [N,T] -> log N(x_n | mu, L L^T) [N]: one forward
+        substitution per vector against the stored factor (distrax MultivariateNormalTri.log_prob)."""
+        mu = self._in(mu)
+        T = mu.shape[0]
+        L = self._in(scale_tri, (T, T), "scale_tri")
+        x = self._in(x)
+        N = x.shape[0]
+        x = self._in(x, (N, T), "x")
+        ll = self._new(N)
+        self._sync_stream()
+        rc = self.lib.be_mvn_log_prob(self.ctx, _ptr(mu), _ptr(L), _ptr(x), T, N, float(sum_log_diag), _ptr(ll))
+        _lib.check(self.ctx, rc, "be_mvn_log_prob")
+        return ll
+
     def normal_logprob(self, loc, scale, x):
         x = self._in(x)
         loc = self._in(loc).expand_as(x).contiguous()

@@ -6,6 +6,8 @@
 #include <new>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include "../../include/be_b200.h"
 #include "be_kernels.cuh"
 #include "vgp_kernels.cuh"
@@ -113,6 +115,18 @@ struct Prof {
     }
 };
 
+// NVTX range per stage of the path (tracing hook); header-only nvtx3, a no-op without a profiler attached
+struct NvtxRange {
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+};
+
+// rows / columns of block kb that are REAL (index < T): flops are booked on T, not on the padded Tp
+inline double real_width(int T, int kb) {
+    int w = T - kb * NB;
+    return (double)(w < 0 ? 0 : (w > NB ? NB : w));
+}
+
 inline unsigned grid1d(size_t n, int block) { return (unsigned)((n + block - 1) / block); }
 
 // cudaFuncSetAttribute applies to the CURRENT device: once per device, not once per process (a process that
@@ -143,6 +157,7 @@ int ensure_kernel_attrs(be_ctx* ctx) {
     BE_CUDA(cudaFuncSetAttribute(k_loglik_weights_mvn_tab<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WEIGHT_STAGE_MAX_BYTES + 16384 + 128));
     BE_CUDA(cudaFuncSetAttribute(k_loglik_weights_mvn_tab<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WEIGHT_STAGE_MAX_BYTES + 16384 + 128));
     BE_CUDA(cudaFuncSetAttribute(k_loglik_weights_normal, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WEIGHT_STAGE_MAX_BYTES));
+    BE_CUDA(cudaFuncSetAttribute(k_mvn_logprob_vectors, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     BE_CUDA(cudaFuncSetAttribute(k_crps_weights, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WEIGHT_STAGE_MAX_BYTES));
     BE_CUDA(cudaFuncSetAttribute(k_ksd_weights, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WEIGHT_STAGE_MAX_BYTES));
     BE_CUDA(cudaFuncSetAttribute(k_w2_collapse, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WEIGHT_STAGE_MAX_BYTES));
@@ -159,10 +174,12 @@ inline size_t matern_smem(int R) { return ((size_t)2 * NB * R + 2 * NB) * sizeof
 int potrf_padded(be_ctx* ctx, double* Mat, int Tp, int T, int B, double* Dinv, double* Pbuf, double* V, int* info) {
     const int ld = Tp, nblk = num_blocks(Tp);
     // left-looking: column update (one long-K tensor-core GEMM per tile) -> diagonal block -> panel
+    NvtxRange nvtx("be:potrf_padded");
     for (int kb = 0; kb < nblk; ++kb) {
-        const double kw = (double)(Tp - kb * NB < NB ? Tp - kb * NB : NB);
-        const double nrem = (double)Tp - kb * NB - kw;  // rows below the diagonal block
-        const double kdone = (double)kb * NB;           // columns already factorised
+        // algorithmic sizes on the REAL dimension T (the padding and the two right-hand-side rows are not booked)
+        const double kw = real_width(T, kb);
+        const double nrem = (double)T - kb * NB - kw > 0 ? (double)T - kb * NB - kw : 0.0;  // rows below the diagonal block
+        const double kdone = kw > 0 ? (double)kb * NB : 0.0;                              // columns already factorised
         int t = nblk - kb - 1;
         {
             // algorithmic: (nrem x kw) gemm + (kw x kw) syrk, K = kdone (kb == 0: moves the panel to Pbuf)
@@ -194,11 +211,12 @@ int potrf_padded(be_ctx* ctx, double* Mat, int Tp, int T, int B, double* Dinv, d
 }
 
 // V = C^-T (upper, row-major); diagonal tiles already written by potrf_padded.
-int trtri_padded(be_ctx* ctx, double* V, const double* Cm, int Tp, int B, const double* Dinv, double* Pbuf) {
+int trtri_padded(be_ctx* ctx, double* V, const double* Cm, int Tp, int T, int B, const double* Dinv, double* Pbuf) {
     const int ld = Tp, nblk = num_blocks(Tp);
+    NvtxRange nvtx("be:trtri_padded");
     for (int i = 1; i < nblk; ++i) {
-        const double kw = (double)(Tp - i * NB < NB ? Tp - i * NB : NB);
-        const double above = (double)i * NB;  // rows of V above block i
+        const double kw = real_width(T, i);                // booked on T, not Tp
+        const double above = kw > 0 ? (double)i * NB : 0;  // rows of V above block i
         {
             // algorithmic: triangular (above x above, upper) times (above x kw): above^2 * kw flops
             Prof pr(ctx, F_TRTRI, B * above * above * kw, B * (0.5 * above * above + 2.0 * above * kw) * 8);
@@ -226,15 +244,24 @@ size_t pbuf_doubles(int B, int T) { return (size_t)B * pad_dim(T) * NB; }
 template <class Epi>
 int launch_gemm(be_ctx* ctx, const GemmArgs& g, const Epi& epi) {
     const unsigned grid = (unsigned)((size_t)gemm_tiles(g.nblk, g.shape) * 2 * g.B);
-    // executed flops (the contraction ranges already skip structural zeros at block level)
-    double kavg = g.klo == KLO_ZERO && g.khi == KHI_END ? (double)g.Tp : 0.5 * g.Tp;
-    Prof pr(ctx, F_GEMM, 2.0 * g.B * (double)gemm_tiles(g.nblk, g.shape) * NB * NB * kavg, 0.0);
+    // flops of the contraction ranges at block granularity (structural zeros skipped per 128-block), clipped to the
+    // real dimension T: the padding is not booked
+    double macs = 0.0;
+    for (int tA = 0; tA < g.nblk; ++tA)
+        for (int tB = 0; tB < g.nblk; ++tB) {
+            if ((g.shape == SHAPE_LOWER && tA < tB) || (g.shape == SHAPE_UPPER && tA > tB)) continue;
+            int k0 = g.klo == KLO_ZERO ? 0 : (g.klo == KLO_TA ? tA : (tA > tB ? tA : tB)) * NB;
+            int k1 = g.khi == KHI_END ? g.Tp : ((g.khi == KHI_TB ? tB : tA) + 1) * NB;
+            if (k1 > g.T) k1 = g.T;
+            if (k1 > k0) macs += real_width(g.T, tA) * real_width(g.T, tB) * (double)(k1 - k0);
+        }
+    Prof pr(ctx, F_GEMM, 2.0 * g.B * macs, 0.0);
     k_gemm_nt<Epi><<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, ctx->stream>>>(g, epi);
     BE_LAUNCHED();
     return BE_OK;
 }
 
-inline GemmArgs gemm_args(const double* A, const double* Bm, int Tp, int B, int shape, int klo, int khi) {
+inline GemmArgs gemm_args(const double* A, const double* Bm, int Tp, int B, int shape, int klo, int khi, int T = -1) {
     GemmArgs g;
     g.A = A;
     g.Bm = Bm;
@@ -242,6 +269,7 @@ inline GemmArgs gemm_args(const double* A, const double* Bm, int Tp, int B, int 
     g.strideA = g.strideB = (size_t)Tp * Tp;
     g.divA = g.divB = 1;
     g.Tp = Tp;
+    g.T = T > 0 ? T : Tp;  // real dimension, for the flop booking only
     g.nblk = num_blocks(Tp);
     g.B = B;
     g.shape = shape;
@@ -283,15 +311,15 @@ int vgp_iteration(be_ctx* ctx, const VgpBuffers& w, const double* X, const doubl
     {
         EpiNatP e;
         e.P = w.P; e.work = w.M2; e.ld = ld; e.Tp = Tp; e.T = T; e.gamma = gamma;
-        if ((rc = launch_gemm(ctx, gemm_args(w.Wt, w.Ut, Tp, B, SHAPE_LOWER, KLO_TA, KHI_END), e)) != BE_OK) return rc;
+        if ((rc = launch_gemm(ctx, gemm_args(w.Wt, w.Ut, Tp, B, SHAPE_LOWER, KLO_TA, KHI_END, T), e)) != BE_OK) return rc;
     }
     // S = P^-1 (potrf, trtri, lauum), q_mu = S theta_1
     if ((rc = potrf_padded(ctx, w.M2, Tp, T, B, w.DinvP, w.Pbuf, w.VP, w.info_tmp)) != BE_OK) return rc;
-    if ((rc = trtri_padded(ctx, w.VP, w.M2, Tp, B, w.DinvP, w.Pbuf)) != BE_OK) return rc;
+    if ((rc = trtri_padded(ctx, w.VP, w.M2, Tp, T, B, w.DinvP, w.Pbuf)) != BE_OK) return rc;
     {
         EpiStore e;
         e.out = w.S; e.sub = nullptr; e.ld = ld; e.Tp = Tp; e.T = T; e.pad_diag = 1.0; e.mirror = 1;
-        if ((rc = launch_gemm(ctx, gemm_args(w.VP, w.VP, Tp, B, SHAPE_LOWER, KLO_TA, KHI_END), e)) != BE_OK) return rc;
+        if ((rc = launch_gemm(ctx, gemm_args(w.VP, w.VP, Tp, B, SHAPE_LOWER, KLO_TA, KHI_END, T), e)) != BE_OK) return rc;
     }
     k_rowdot<<<rows_grid, 256, 0, ctx->stream>>>(w.S, ld, Tp, T, 0, 0, w.n1, nullptr, nullptr, 0.0, w.qmu, B);
     BE_LAUNCHED();
@@ -303,21 +331,21 @@ int vgp_iteration(be_ctx* ctx, const VgpBuffers& w, const double* X, const doubl
     {
         EpiLbarT e;
         e.out = w.Zt; e.q_mu = w.qmu; e.r = w.r; e.y_var = y_var; e.ld = ld; e.Tp = Tp; e.T = T;
-        if ((rc = launch_gemm(ctx, gemm_args(w.S, w.Mk, Tp, B, SHAPE_FULL, KLO_ZERO, KHI_TB), e)) != BE_OK) return rc;
+        if ((rc = launch_gemm(ctx, gemm_args(w.S, w.Mk, Tp, B, SHAPE_FULL, KLO_ZERO, KHI_TB, T), e)) != BE_OK) return rc;
     }
     // Phi = tril(L^T Lbar), halved diagonal  (M2 is free again)
     {
         EpiPhi e;
         e.out = w.M2; e.ld = ld; e.Tp = Tp; e.T = T;
-        if ((rc = launch_gemm(ctx, gemm_args(w.Ut, w.Zt, Tp, B, SHAPE_LOWER, KLO_TA, KHI_END), e)) != BE_OK) return rc;
+        if ((rc = launch_gemm(ctx, gemm_args(w.Ut, w.Zt, Tp, B, SHAPE_LOWER, KLO_TA, KHI_END, T), e)) != BE_OK) return rc;
     }
     // VL = L^-T
-    if ((rc = trtri_padded(ctx, w.VL, w.Mk, Tp, B, w.DinvL, w.Pbuf)) != BE_OK) return rc;
+    if ((rc = trtri_padded(ctx, w.VL, w.Mk, Tp, T, B, w.DinvL, w.Pbuf)) != BE_OK) return rc;
     // YT = VL Phi^T  (block upper), into Wt
     {
         EpiStore e;
         e.out = w.Wt; e.sub = nullptr; e.ld = ld; e.Tp = Tp; e.T = T; e.pad_diag = 0.0; e.mirror = 0;
-        if ((rc = launch_gemm(ctx, gemm_args(w.VL, w.M2, Tp, B, SHAPE_UPPER, KLO_TA, KHI_TB), e)) != BE_OK) return rc;
+        if ((rc = launch_gemm(ctx, gemm_args(w.VL, w.M2, Tp, B, SHAPE_UPPER, KLO_TA, KHI_TB, T), e)) != BE_OK) return rc;
     }
     // g = sum Kbar_u .* dK/dtheta with Kbar_u = VL YT^T
     const int ctas = nblk * nblk * 2;
@@ -326,7 +354,7 @@ int vgp_iteration(be_ctx* ctx, const VgpBuffers& w, const double* X, const doubl
         EpiKbarGrad e;
         e.X = X; e.variance = variance; e.lengthscale = lengthscale; e.partial = w.partial; e.T = T; e.R = R;
         e.ctas_per_problem = ctas; e.g0 = 0.0; e.g1 = 0.0;
-        if ((rc = launch_gemm(ctx, gemm_args(w.VL, w.Wt, Tp, B, SHAPE_FULL, KLO_MAX, KHI_END), e)) != BE_OK) return rc;
+        if ((rc = launch_gemm(ctx, gemm_args(w.VL, w.Wt, Tp, B, SHAPE_FULL, KLO_MAX, KHI_END, T), e)) != BE_OK) return rc;
     }
     k_vgp_adam<<<grid1d(B, 128), 128, 0, ctx->stream>>>(w.partial, ctas, B, lr, 0.9, 0.999, 1e-7, w.u, w.am, w.av, w.step,
                                                        variance, lengthscale);
@@ -445,6 +473,7 @@ long long be_ctx_launch_count(be_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
 int be_gpdtw1d_inputs(be_ctx* ctx, const double* realisations, int B, int R, int T, double* X, double* y_mean,
                       double* y_var) {
+    NvtxRange nvtx_fn("be_gpdtw1d_inputs");
     if (!ctx) return -1;
     if (!realisations) return -2;
     if (B <= 0) return -3;
@@ -458,6 +487,7 @@ int be_gpdtw1d_inputs(be_ctx* ctx, const double* realisations, int B, int R, int
 
 int be_matern32_gram(be_ctx* ctx, const double* X, int B, int T, int R, const double* variance,
                      const double* lengthscale, double* K) {
+    NvtxRange nvtx_fn("be_matern32_gram");
     if (!ctx) return -1;
     if (!X) return -2;
     if (B <= 0) return -3;
@@ -481,6 +511,7 @@ size_t be_potrf_workspace_bytes(int B, int T) {
 
 int be_potrf_batched(be_ctx* ctx, const double* A, int B, int T, double* L, int* info, void* workspace,
                      size_t workspace_bytes) {
+    NvtxRange nvtx_fn("be_potrf_batched");
     if (!ctx) return -1;
     if (!A) return -2;
     if (B <= 0) return -3;
@@ -515,6 +546,7 @@ int be_gp_posterior(be_ctx* ctx, const double* X, const double* y_mean, const do
                     const double* lengthscale, double jitter, int B, int T, int R, double* mu, double* var_diag,
                     double* cov, double* scale_tri, double* mvn_stats, int* info_fit, int* info_dist, void* workspace,
                     size_t workspace_bytes) {
+    NvtxRange nvtx_fn("be_gp_posterior");
     if (!ctx) return -1;
     if (!X) return -2;
     if (!y_mean) return -3;
@@ -561,7 +593,7 @@ int be_gp_posterior(be_ctx* ctx, const double* X, const double* y_mean, const do
         BE_LAUNCHED();
     }
     // 3. V = C^-T
-    rc = trtri_padded(ctx, Vw, Mw, Tp, B, Dinv, Pbuf);
+    rc = trtri_padded(ctx, Vw, Mw, Tp, T, B, Dinv, Pbuf);
     if (rc != BE_OK) return rc;
     // 4. mean = y - E V u
     {
@@ -605,6 +637,7 @@ int be_gp_posterior_factored(be_ctx* ctx, const double* X, const double* y_mean,
                              const double* variance, const double* lengthscale, double jitter, int B, int T, int R,
                              double* mu, double* var_diag, double* mvn_stats, int* info_fit, int* info_dist,
                              void* workspace, size_t workspace_bytes) {
+    NvtxRange nvtx_fn("be_gp_posterior_factored");
     if (!ctx) return -1;
     if (!X) return -2;
     if (!y_mean) return -3;
@@ -659,7 +692,7 @@ int be_gp_posterior_factored(be_ctx* ctx, const double* X, const double* y_mean,
         BE_LAUNCHED();
     }
     // 3-4. V = C^-T; mean = y - E V u and var_diag = D + E - E^2 diag(V V^T) in one pass over V
-    rc = trtri_padded(ctx, Vw, Mw, Tp, B, Dinv, Pbuf);
+    rc = trtri_padded(ctx, Vw, Mw, Tp, T, B, Dinv, Pbuf);
     if (rc != BE_OK) return rc;
     {
         Prof pr(ctx, F_MEAN, 2.0 * dB * dT * dT, dB * (0.5 * dT * dT + 5.0 * dT) * 8);
@@ -700,6 +733,7 @@ size_t be_mvn_from_cov_workspace_bytes(int B, int T) { return be_potrf_workspace
 
 int be_mvn_from_cov(be_ctx* ctx, const double* mu, const double* cov, int B, int T, double* scale_tri,
                     double* var_diag, double* mvn_stats, int* info, void* workspace, size_t workspace_bytes) {
+    NvtxRange nvtx_fn("be_mvn_from_cov");
     if (!ctx) return -1;
     if (!mu) return -2;
     if (!cov) return -3;
@@ -734,6 +768,7 @@ int be_mvn_from_cov(be_ctx* ctx, const double* mu, const double* cov, int B, int
 
 int be_loglik_weights_mvn(be_ctx* ctx, const double* mvn_stats, const double* obs, int C, int M, int Ro, int T,
                           double standardisation_constant, double* weights, double* lls_exp, double* lls_mean) {
+    NvtxRange nvtx_fn("be_loglik_weights_mvn");
     if (!ctx) return -1;
     if (!mvn_stats) return -2;
     if (!obs) return -3;
@@ -783,6 +818,20 @@ int be_mvn_constvec_logprob(be_ctx* ctx, const double* mvn_stats, const double* 
     return BE_OK;
 }
 
+int be_mvn_log_prob(be_ctx* ctx, const double* mu, const double* scale_tri, const double* x, int T, int N,
+                    double sum_log_diag, double* ll) {
+    if (!ctx) return -1;
+    if (!mu) return -2;
+    if (!scale_tri) return -3;
+    if (!x) return -4;
+    if (T <= 0 || (size_t)T * sizeof(double) > 200 * 1024) return -5;
+    if (N <= 0) return -6;
+    if (!ll) return -8;
+    k_mvn_logprob_vectors<<<N, 256, (size_t)T * sizeof(double), ctx->stream>>>(mu, scale_tri, x, T, N, sum_log_diag, ll);
+    BE_LAUNCHED();
+    return BE_OK;
+}
+
 int be_normal_logprob(be_ctx* ctx, const double* loc, const double* scale, const double* x, size_t n, double* ll) {
     if (!ctx) return -1;
     if (!loc) return -2;
@@ -798,6 +847,7 @@ int be_normal_logprob(be_ctx* ctx, const double* loc, const double* scale, const
 int be_loglik_weights_normal(be_ctx* ctx, const double* loc, const double* scale, const double* obs, int C, int M,
                              int Ro, int N, double standardisation_constant, double* weights, double* lls_exp,
                              double* lls_mean) {
+    NvtxRange nvtx_fn("be_loglik_weights_normal");
     if (!ctx) return -1;
     if (!loc) return -2;
     if (!scale) return -3;
@@ -816,6 +866,7 @@ int be_loglik_weights_normal(be_ctx* ctx, const double* loc, const double* scale
 }
 
 int be_weights_time_mean(be_ctx* ctx, const double* weights, int C, int M, int T, double* w_bar) {
+    NvtxRange nvtx_fn("be_weights_time_mean");
     if (!ctx) return -1;
     if (!weights) return -2;
     if (C <= 0) return -3;
@@ -842,6 +893,7 @@ int be_weights_normalise(be_ctx* ctx, const double* lls_exp, const double* total
 
 int be_barycentre_1d(be_ctx* ctx, const double* means, const double* variances, const double* weights, int C, int M,
                      int N, double tolerance, double init_var, int max_iters, double* mu, double* sigma, int* iters) {
+    NvtxRange nvtx_fn("be_barycentre_1d");
     if (!ctx) return -1;
     if (!means) return -2;
     if (!variances) return -3;
@@ -904,6 +956,7 @@ int be_vgp_fit(be_ctx* ctx, const double* X, const double* y_mean, const double*
                int n_iters, double gamma, double lr, int train_hypers, double jitter, double* variance,
                double* lengthscale, double* mu, double* var_diag, double* cov, double* scale_tri, double* mvn_stats,
                int* info_fit, int* info_dist, void* workspace, size_t workspace_bytes) {
+    NvtxRange nvtx_fn("be_vgp_fit");
     if (!ctx) return -1;
     if (!X) return -2;
     if (!y_mean) return -3;
@@ -1009,7 +1062,7 @@ int be_vgp_fit(be_ctx* ctx, const double* X, const double* y_mean, const double*
                                                                                    ld, ntl);
     BE_LAUNCHED();
     if ((rc = potrf_padded(ctx, w.Mk, Tp, T, B, w.DinvL, w.Pbuf, w.VL, info_fit)) != BE_OK) return rc;
-    if ((rc = trtri_padded(ctx, w.VL, w.Mk, Tp, B, w.DinvL, w.Pbuf)) != BE_OK) return rc;
+    if ((rc = trtri_padded(ctx, w.VL, w.Mk, Tp, T, B, w.DinvL, w.Pbuf)) != BE_OK) return rc;
     k_matern32<2><<<(unsigned)((size_t)nblk * nblk * B), 256, matern_smem(R), ctx->stream>>>(
         X, B, T, R, variance, lengthscale, nullptr, nullptr, 0.0, w.Ut, Tp, ld, nblk * nblk);  // Ut := K (no jitter)
     BE_LAUNCHED();
@@ -1019,19 +1072,19 @@ int be_vgp_fit(be_ctx* ctx, const double* X, const double* y_mean, const double*
     {   // AT = K Lm^-T  (= A^T, A = Lm^-1 K)
         EpiStore e;
         e.out = w.Zt; e.sub = nullptr; e.ld = ld; e.Tp = Tp; e.T = T; e.pad_diag = 0.0; e.mirror = 0;
-        if ((rc = launch_gemm(ctx, gemm_args(w.Ut, w.Wt, Tp, B, SHAPE_FULL, KLO_ZERO, KHI_TB), e)) != BE_OK) return rc;
+        if ((rc = launch_gemm(ctx, gemm_args(w.Ut, w.Wt, Tp, B, SHAPE_FULL, KLO_ZERO, KHI_TB, T), e)) != BE_OK) return rc;
     }
     k_rowdot<<<grid1d((size_t)B * T, 8), 256, 0, ctx->stream>>>(w.Zt, ld, Tp, T, 0, 0, w.qmu, nullptr, nullptr, 0.0, mu, B);
     BE_LAUNCHED();
     {   // M2 = AT S - AT
         EpiStore e;
         e.out = w.M2; e.sub = w.Zt; e.ld = ld; e.Tp = Tp; e.T = T; e.pad_diag = 0.0; e.mirror = 0;
-        if ((rc = launch_gemm(ctx, gemm_args(w.Zt, w.S, Tp, B, SHAPE_FULL, KLO_ZERO, KHI_END), e)) != BE_OK) return rc;
+        if ((rc = launch_gemm(ctx, gemm_args(w.Zt, w.S, Tp, B, SHAPE_FULL, KLO_ZERO, KHI_END, T), e)) != BE_OK) return rc;
     }
     {   // cov = K + (AT (S - I)) AT^T + D
         EpiCov e;
         e.K = w.Ut; e.y_var = y_var; e.cov = cov; e.var_diag = var_diag; e.ld = ld; e.Tp = Tp; e.T = T;
-        if ((rc = launch_gemm(ctx, gemm_args(w.M2, w.Zt, Tp, B, SHAPE_LOWER, KLO_ZERO, KHI_END), e)) != BE_OK) return rc;
+        if ((rc = launch_gemm(ctx, gemm_args(w.M2, w.Zt, Tp, B, SHAPE_LOWER, KLO_ZERO, KHI_END, T), e)) != BE_OK) return rc;
     }
     // Distribution(mu, cov, MultivariateNormalFullCovariance): data.py:38-39
     k_pad_from_dense<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(cov, mu, B, T, Tp, Tp, w.P, 1);

@@ -160,6 +160,7 @@ int be_dtw_barycenter_averaging_subgradient(be_ctx* ctx, const double* X, int B,
                                             double initial_step_size, double final_step_size, double tol,
                                             const double* init_barycenter, double* barycenter, int* n_iter,
                                             double* cost, void* workspace, size_t workspace_bytes) {
+    NvtxRange nvtx_fn("be_dtw_barycenter_averaging_subgradient");
     if (!ctx) return -1;
     if (!X) return -2;
     if (B <= 0) return -3;
@@ -216,6 +217,7 @@ int be_dtw_barycenter_averaging_subgradient(be_ctx* ctx, const double* X, int B,
 
 int be_perform_dba(be_ctx* ctx, const double* X, int B, int R, int T, int n_iterations, double* center, int* medoid,
                    void* workspace, size_t workspace_bytes) {
+    NvtxRange nvtx_fn("be_perform_dba");
     if (!ctx) return -1;
     if (!X) return -2;
     if (B <= 0) return -3;

@@ -618,6 +618,54 @@ __global__ void k_mvn_constvec_logprob(const double* __restrict__ stats, const d
     ll[gid] = constvec_ll(stats + ((size_t)c * M + m) * 4, obs[((size_t)c * Ro + r) * T + i], T);
 }
 
+// distrax MultivariateNormalTri.log_prob for GENERAL vectors (dists.py; the NLL of utils.py:139): one CTA per
+// vector x, z = L^-1 (x - mu) by blocked forward substitution against the STORED dense factor scale_tri [T,T]
+// (32 columns at a time: warp 0 solves the 32 x 32 diagonal block with shuffles, then every thread takes the rows
+// below it), ll = -1/2 |z|^2 - T/2 log 2pi - sum log diag L.  O(T^2) per vector, L is read once per vector.
+__global__ void __launch_bounds__(256) k_mvn_logprob_vectors(const double* __restrict__ mu, const double* __restrict__ L,
+                                                              const double* __restrict__ x, int T, int N,
+                                                              double sum_log_diag, double* __restrict__ ll) {
+    extern __shared__ double zsh[];  // [T] running right-hand side, then the solution
+    __shared__ double red[8];
+    const int v = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int i = tid; i < T; i += 256) zsh[i] = x[(size_t)v * T + i] - mu[i];
+    __syncthreads();
+    for (int j0 = 0; j0 < T; j0 += 32) {
+        const int w = min(32, T - j0);
+        if (warp == 0) {
+            // lane l owns row j0 + l of the diagonal block
+            double r = lane < w ? zsh[j0 + lane] : 0.0;
+            const double* row = L + (size_t)(j0 + min(lane, w - 1)) * T + j0;
+            for (int k = 0; k < w; ++k) {
+                if (lane == k) r = r / row[k];  // z_k is final
+                const double zk = __shfl_sync(0xffffffffu, r, k);
+                if (lane > k && lane < w) r = fma(-row[k], zk, r);
+            }
+            if (lane < w) zsh[j0 + lane] = r;
+        }
+        __syncthreads();
+        for (int i = j0 + 32 + tid; i < T; i += 256) {
+            const double* row = L + (size_t)i * T + j0;
+            double acc = 0.0;
+#pragma unroll 8
+            for (int k = 0; k < 32; ++k) acc = fma(row[k], zsh[j0 + k], acc);
+            zsh[i] -= acc;
+        }
+        __syncthreads();
+    }
+    double q = 0.0;
+    for (int i = tid; i < T; i += 256) q = fma(zsh[i], zsh[i], q);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+    if (lane == 0) red[warp] = q;
+    __syncthreads();
+    if (tid == 0) {
+        double s = 0.0;
+        for (int k = 0; k < 8; ++k) s += red[k];
+        ll[v] = -0.5 * s - 0.5 * (double)T * LOG_2PI - sum_log_diag;
+    }
+}
+
 // Un-normalised weights of one point are staged in SHARED memory (one column per thread, [M][blockDim.x],
 // conflict-free) between the pass that forms them and the pass that divides by their sum, so that the
 // weights cross HBM once (the first version wrote them, re-read them and wrote them again: 2.4x the
@@ -700,7 +748,7 @@ __global__ void k_loglik_weights_mvn(const double* __restrict__ stats, const dou
         if (lls_mean) lls_mean[o] = mean;
         if (lls_exp) lls_exp[o] = e;
         st[m] = e;
-        total += e;
+        if (e == e) total += e;  // xarray .sum('model') skips NaN (weights.py:122)
     }
 #pragma unroll 4
     for (int m = 0; m < M; ++m) wp[(size_t)m * T] = st[m] / total;
@@ -821,7 +869,7 @@ __global__ void __launch_bounds__(128, 8)
             if (lls_exp) lls_exp[o] = e;
         }
         stg[m * bs] = e;
-        total += e;
+        if (e == e) total += e;  // xarray .sum('model') skips NaN (weights.py:122)
     };
     int m = 0;
     for (; m + 4 <= M; m += 4) {
@@ -916,7 +964,7 @@ __global__ void k_loglik_weights_normal(const double* __restrict__ loc, const do
         if (lls_mean) lls_mean[o] = mean;
         if (lls_exp) lls_exp[o] = e;
         st[m] = e;
-        total += e;
+        if (e == e) total += e;  // xarray .sum('model') skips NaN (weights.py:122)
     }
     for (int m = 0; m < M; ++m) w[((size_t)c * M + m) * N + i] = st[m] / total;
 }
@@ -1040,7 +1088,7 @@ __global__ void k_barycentre_partial(const double* __restrict__ means, const dou
     double s0 = 0, s1 = 0, s2 = 0;
     for (int m = 0; m < M; ++m) {
         double w = lls_exp[base + (size_t)m * N];
-        s0 += w;
+        if (w == w) s0 += w;  // the normaliser skips NaN members (xarray .sum('model')); the barycentre sums do not
         s1 += w * means[base + (size_t)m * N];
         s2 += w * sqrt(variances[base + (size_t)m * N]);
     }

@@ -58,12 +58,12 @@ int sqrtm_padded(be_ctx* ctx, const SqrtmBuffers& w, int B, int T, double tol, i
         if ((rc = potrf_padded(ctx, w.WY, Tp, T, B, w.Dinv, w.Pbuf, w.VY, info)) != BE_OK) return rc;
         k_diag_reduce<1><<<B, 256, 0, ctx->stream>>>(w.WY, ld, Tp, T, w.hldY, 0);
         BE_LAUNCHED();
-        if ((rc = trtri_padded(ctx, w.VY, w.WY, Tp, B, w.Dinv, w.Pbuf)) != BE_OK) return rc;
+        if ((rc = trtri_padded(ctx, w.VY, w.WY, Tp, T, B, w.Dinv, w.Pbuf)) != BE_OK) return rc;
         if (it > 0) {  // Z^-1 = VZ VZ^T  (Z0 = I needs no factorisation)
             if ((rc = potrf_padded(ctx, w.WZ, Tp, T, B, w.Dinv, w.Pbuf, w.VZ, info)) != BE_OK) return rc;
             k_diag_reduce<1><<<B, 256, 0, ctx->stream>>>(w.WZ, ld, Tp, T, w.hldZ, 0);
             BE_LAUNCHED();
-            if ((rc = trtri_padded(ctx, w.VZ, w.WZ, Tp, B, w.Dinv, w.Pbuf)) != BE_OK) return rc;
+            if ((rc = trtri_padded(ctx, w.VZ, w.WZ, Tp, T, B, w.Dinv, w.Pbuf)) != BE_OK) return rc;
         }
         k_db_mu<<<grid1d(B, 128), 128, 0, ctx->stream>>>(w.hldY, w.hldZ, w.delta, DB_SCALING_OFF, T, B, w.mu);
         BE_LAUNCHED();
@@ -74,33 +74,39 @@ int sqrtm_padded(be_ctx* ctx, const SqrtmBuffers& w, int B, int T, double tol, i
             EpiDB e;
             e.cur = w.Y; e.work = w.WY; e.mu = w.mu; e.partial = w.partialY; e.ld = ld; e.Tp = Tp; e.T = T;
             e.ctas_per_problem = ctas; e.d2 = 0.0; e.n2 = 0.0;
-            if ((rc = launch_gemm(ctx, gemm_args(w.VZ, w.VZ, Tp, B, SHAPE_LOWER, KLO_TA, KHI_END), e)) != BE_OK) return rc;
+            if ((rc = launch_gemm(ctx, gemm_args(w.VZ, w.VZ, Tp, B, SHAPE_LOWER, KLO_TA, KHI_END, T), e)) != BE_OK) return rc;
         }
         {
             EpiDB e;
             e.cur = w.Z; e.work = w.WZ; e.mu = w.mu; e.partial = w.partialZ; e.ld = ld; e.Tp = Tp; e.T = T;
             e.ctas_per_problem = ctas; e.d2 = 0.0; e.n2 = 0.0;
-            if ((rc = launch_gemm(ctx, gemm_args(w.VY, w.VY, Tp, B, SHAPE_LOWER, KLO_TA, KHI_END), e)) != BE_OK) return rc;
+            if ((rc = launch_gemm(ctx, gemm_args(w.VY, w.VY, Tp, B, SHAPE_LOWER, KLO_TA, KHI_END, T), e)) != BE_OK) return rc;
         }
         k_db_delta<<<grid1d(B, 128), 128, 0, ctx->stream>>>(w.partialY, ctas, B, w.delta);
         BE_LAUNCHED();
         BE_CUDA(cudaMemcpyAsync(delta_h.data(), w.delta, sizeof(double) * B, cudaMemcpyDeviceToHost, ctx->stream));
         BE_CUDA(cudaStreamSynchronize(ctx->stream));
         ++it;
+        // A problem whose delta is NaN / inf is not SPD (its info says where): it is left out of the convergence
+        // measure and stays NaN, while the other problems of the batch keep iterating until THEY converge.
         double worst = 0.0;
-        bool bad = false;
+        int good = 0;
         for (int b = 0; b < B; ++b) {
-            if (!(delta_h[b] == delta_h[b]) || delta_h[b] == INFINITY) bad = true;  // NaN / inf: not SPD, see info
-            else if (delta_h[b] > worst) worst = delta_h[b];
+            if (!(delta_h[b] == delta_h[b]) || delta_h[b] == INFINITY) continue;
+            ++good;
+            if (delta_h[b] > worst) worst = delta_h[b];
         }
-        if (bad || worst < tol) break;
+        if (good == 0 || worst < tol) break;
     }
+    // problems that end above the tolerance (max_iters reached, or NaN) and carry no Cholesky report get their own code
+    k_mark_unconverged<<<grid1d(B, 128), 128, 0, ctx->stream>>>(w.delta, tol, B, info);
+    BE_LAUNCHED();
     if (iters_host) *iters_host = it;
     return BE_OK;
 }
 
-inline GemmArgs gemm_args_div(const double* A, int divA, const double* Bm, int divB, int Tp, int B, int shape) {
-    GemmArgs g = gemm_args(A, Bm, Tp, B, shape, KLO_ZERO, KHI_END);
+inline GemmArgs gemm_args_div(const double* A, int divA, const double* Bm, int divB, int Tp, int B, int shape, int T = -1) {
+    GemmArgs g = gemm_args(A, Bm, Tp, B, shape, KLO_ZERO, KHI_END, T);
     g.divA = divA;
     g.divB = divB;
     return g;
@@ -114,6 +120,7 @@ size_t be_sqrtm_psd_workspace_bytes(int B, int T) { return sqrtm_core_bytes(B, T
 
 int be_sqrtm_psd(be_ctx* ctx, const double* A, int B, int T, double tol, int max_iters, double* sqrt_out,
                  double* inv_sqrt_out, int* iters_host, int* info, void* workspace, size_t workspace_bytes) {
+    NvtxRange nvtx_fn("be_sqrtm_psd");
     if (!ctx) return -1;
     if (!A) return -2;
     if (B <= 0) return -3;
@@ -148,6 +155,7 @@ size_t be_w2_distance_workspace_bytes(int P, int T) {
 
 int be_w2_distance(be_ctx* ctx, const double* mu1, const double* sigma1, const double* mu2, const double* sigma2, int P,
                    int T, double tol, int max_iters, double* w2, int* info, void* workspace, size_t workspace_bytes) {
+    NvtxRange nvtx_fn("be_w2_distance");
     if (!ctx) return -1;
     if (!mu1) return -2;
     if (!sigma1) return -3;
@@ -188,12 +196,12 @@ int be_w2_distance(be_ctx* ctx, const double* mu1, const double* sigma1, const d
     {
         EpiPlain e;
         e.out = G; e.ld = ld; e.Tp = Tp; e.T = T;
-        if ((rc = launch_gemm(ctx, gemm_args_div(w.Y, 1, S2, 1, Tp, P, SHAPE_FULL), e)) != BE_OK) return rc;  // G = R1 S2
+        if ((rc = launch_gemm(ctx, gemm_args_div(w.Y, 1, S2, 1, Tp, P, SHAPE_FULL, T), e)) != BE_OK) return rc;  // G = R1 S2
     }
     {
         EpiSym e;
         e.out = S2; e.work = w.WY; e.ld = ld; e.Tp = Tp; e.T = T;
-        if ((rc = launch_gemm(ctx, gemm_args_div(w.Y, 1, G, 1, Tp, P, SHAPE_LOWER), e)) != BE_OK) return rc;  // R1 S2 R1
+        if ((rc = launch_gemm(ctx, gemm_args_div(w.Y, 1, G, 1, Tp, P, SHAPE_LOWER, T), e)) != BE_OK) return rc;  // R1 S2 R1
     }
     SqrtmBuffers w2b = w;
     w2b.Y = S2;
@@ -231,6 +239,7 @@ int be_barycentre_fullcov(be_ctx* ctx, const double* mus, const double* sigmas, 
                           int T, double tolerance, double init_var, int max_iters, double sqrtm_tol,
                           int sqrtm_max_iters, double* mu, double* S_out, int* iters_host, int* info, void* workspace,
                           size_t workspace_bytes) {
+    NvtxRange nvtx_fn("be_barycentre_fullcov");
     if (!ctx) return -1;
     if (!mus) return -2;
     if (!sigmas) return -3;
@@ -282,12 +291,12 @@ int be_barycentre_fullcov(be_ctx* ctx, const double* mus, const double* sigmas, 
         {
             EpiPlain e;
             e.out = G; e.ld = ld; e.Tp = Tp; e.T = T;
-            if ((rc = launch_gemm(ctx, gemm_args_div(Sh, M, Sig, 1, Tp, B, SHAPE_FULL), e)) != BE_OK) return rc;
+            if ((rc = launch_gemm(ctx, gemm_args_div(Sh, M, Sig, 1, Tp, B, SHAPE_FULL, T), e)) != BE_OK) return rc;
         }
         {
             EpiSym e;
             e.out = w.Y; e.work = w.WY; e.ld = ld; e.Tp = Tp; e.T = T;
-            if ((rc = launch_gemm(ctx, gemm_args_div(Sh, M, G, 1, Tp, B, SHAPE_LOWER), e)) != BE_OK) return rc;
+            if ((rc = launch_gemm(ctx, gemm_args_div(Sh, M, G, 1, Tp, B, SHAPE_LOWER, T), e)) != BE_OK) return rc;
         }
         if ((rc = sqrtm_padded(ctx, w, B, T, sqrtm_tol, sqrtm_max_iters, nullptr, info)) != BE_OK) return rc;
         // candidate = sum_m w_m (.)^1/2 ; signed stop rule on tr(candidate - S) / T       wasserstein.py:85-92
@@ -321,6 +330,7 @@ int be_barycentre_fullcov(be_ctx* ctx, const double* mus, const double* sigmas, 
 /* ---- SURVEY 8f "next": CRPSWeight and ModelSimilarityWeight ------------------------------------ */
 int be_crps_weights(be_ctx* ctx, const double* loc, const double* scale, const double* obs, int C, int M, int Ro,
                     int N, double* weights, double* crps_mean) {
+    NvtxRange nvtx_fn("be_crps_weights");
     if (!ctx) return -1;
     if (!loc) return -2;
     if (!scale) return -3;
@@ -340,6 +350,7 @@ int be_crps_weights(be_ctx* ctx, const double* loc, const double* scale, const d
 
 int be_ksd_weights(be_ctx* ctx, const double* loc, const double* scale, const double* obs, int C, int M, int Ro,
                    int N, double* weights, double* ksd) {
+    NvtxRange nvtx_fn("be_ksd_weights");
     if (!ctx) return -1;
     if (!loc) return -2;
     if (!scale) return -3;
@@ -373,6 +384,7 @@ int be_w2_collapse(be_ctx* ctx, const double* w2, int C, int M, int N, double* w
 
 int be_similarity_weights_pointwise(be_ctx* ctx, const double* mean, const double* var, int C, int M, int N,
                                     double* weights, double* w2_out) {
+    NvtxRange nvtx_fn("be_similarity_weights_pointwise");
     if (!ctx) return -1;
     if (!mean) return -2;
     if (!var) return -3;

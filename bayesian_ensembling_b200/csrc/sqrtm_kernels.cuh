@@ -155,6 +155,14 @@ __global__ void k_db_delta(const double* __restrict__ partial, int ctas_per_prob
     delta[b] = n2 > 0.0 ? sqrt(d2 / n2) : (d2 > 0.0 ? INFINITY : 0.0);
 }
 
+// a problem that leaves the Denman-Beavers loop above the tolerance (max_iters reached, or a NaN iterate that the
+// Cholesky did not already report) is marked BE_INFO_NOT_CONVERGED; Cholesky reports (> 0) are kept
+__global__ void k_mark_unconverged(const double* __restrict__ delta, double tol, int B, int* __restrict__ info) {
+    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    if (!(delta[b] < tol) && info[b] == 0) info[b] = BE_INFO_NOT_CONVERGED;
+}
+
 // symmetric product computed on lower tiles: out[i,j] = out[j,i] = acc (j <= i), identity padding
 struct EpiSym : EpiBase {
     double* out;

@@ -24,6 +24,7 @@ struct GemmArgs {
     int divA, divB;           // problem b reads operand slot b / div (one S^1/2 shared by the M members of a cell)
     int Tp, nblk, B;
     int shape, klo, khi;
+    int T;                    // real dimension (host-side flop booking only)
 };
 
 __host__ __device__ inline int gemm_tiles(int nblk, int shape) {

@@ -53,7 +53,7 @@ __global__ void k_crps_weights(const double* __restrict__ loc, const double* __r
         if (crps_mean) crps_mean[o] = mean;
         double inv = 1.0 / mean;
         st[m] = inv;
-        total += inv;
+        if (inv == inv) total += inv;  // xarray .sum('model') skips NaN
     }
     for (int m = 0; m < M; ++m) w[((size_t)c * M + m) * N + i] = st[m] / total;
 }
@@ -121,7 +121,7 @@ __global__ void k_ksd_weights(const double* __restrict__ loc, const double* __re
         if (ksd_out) ksd_out[o] = ksd;
         const double inv = 1.0 / ksd;
         st[m] = inv;
-        total += inv;
+        if (inv == inv) total += inv;  // xarray .sum('model') skips NaN
     }
     for (int m = 0; m < M; ++m) w[((size_t)c * M + m) * N + i] = st[m] / total;
 }
@@ -147,7 +147,7 @@ __global__ void k_w2_collapse(const double* __restrict__ d, int C, int M, int N,
         }
         double m = s / cnt;
         st[i] = m;
-        total += m;
+        if (m == m) total += m;  // xarray .sum('model') skips NaN
     }
     for (int i = 0; i < M; ++i) w[((size_t)c * M + i) * N + n] = st[i] / total;
 }
@@ -189,7 +189,7 @@ __global__ void k_similarity_pointwise(const double* __restrict__ mean, const do
                 for (int j = 0; j < M; ++j) sabs += fabs(mi - mc[(size_t)j * N]);
                 const double m = (sabs + (((double)M * vi + Sv) - 2.0 * sqrt(vi) * Sr)) / (double)M;
                 st[i] = m;
-                total += m;
+                if (m == m) total += m;  // xarray .sum('model') skips NaN
             }
             for (int i = 0; i < M; ++i) w[((size_t)c * M + i) * N + n] = st[i] / total;
             return;
@@ -210,7 +210,7 @@ __global__ void k_similarity_pointwise(const double* __restrict__ mean, const do
         }
         double m = s / cnt;
         st[i] = m;
-        total += m;
+        if (m == m) total += m;  // xarray .sum('model') skips NaN
     }
     for (int i = 0; i < M; ++i) w[((size_t)c * M + i) * N + n] = st[i] / total;
 }

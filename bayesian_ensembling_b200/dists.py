@@ -78,20 +78,13 @@ class MultivariateNormalFullCovariance:
         return self._log_prob_general(value)
 
     def _log_prob_general(self, value):
-        # General vectors: whiten with the device-computed factor through the augmented
-        # Cholesky (rows ride along): |L^-1 (x - mu)|^2 for a batch of x.
+        # General vectors: ONE forward substitution per vector against the factor stored at construction
+        # (be_mvn_log_prob), as distrax does -- no re-factorisation.
         be = Backend.get()
         T = self.event_shape[0]
-        flat = value.reshape(-1, T)
-        out = np.empty(flat.shape[0])
-        mu = self._loc
-        for i in range(flat.shape[0]):
-            d = be._in(flat[i][None]) - mu[None]
-            # stats for the pair (1, d): b = L^-1 d  -> maha = |b|^2
-            _, _, stats, _ = be.mvn_from_cov(d, self._cov[None], want_scale_tri=False)
-            s = _np(stats)[0]
-            out[i] = -0.5 * s[2] - 0.5 * T * np.log(2 * np.pi) - s[3]
-        return out.reshape(value.shape[:-1])
+        flat = np.ascontiguousarray(value.reshape(-1, T))
+        ll = be.mvn_log_prob(self._loc, self._scale_tri, flat, float(self._stats[3]))
+        return _np(ll).reshape(value.shape[:-1])
 
     def sample(self, seed=0, sample_shape=()):
         rng = np.random.default_rng(int(np.asarray(seed).ravel()[0]) if np.ndim(seed) else int(seed))

@@ -48,6 +48,53 @@ def _per_problem(x, C, M, device):
     return t.reshape(C * M).contiguous()
 
 
+HOST_PIPELINE_MIN_CELLS = 16  # below this a wave is too small to be worth splitting for copy / compute overlap
+
+
+def _is_host(x) -> bool:
+    return not (isinstance(x, torch.Tensor) and x.is_cuda)
+
+
+def _as_f64(x) -> torch.Tensor:
+    """host array / tensor -> contiguous fp64 host tensor (no copy when it already is one, e.g. a pinned buffer)"""
+    if not isinstance(x, torch.Tensor):
+        if hasattr(x, "flags") and not x.flags.writeable:
+            x = x.copy()
+        x = torch.as_tensor(x)
+    return x.to(torch.float64).contiguous()
+
+
+class _HostPrefetcher:
+    """Wave-by-wave host-to-device staging of the realisations on a side stream, one wave ahead of the compute
+    stream (double buffered): the copy of wave k+1 overlaps the kernels of wave k.  Pinned host memory makes the
+    copies truly asynchronous; pageable memory still works (the copy then blocks the host, not the device)."""
+
+    def __init__(self, be: Backend, r_host: torch.Tensor, waves):
+        self.be, self.r, self.waves = be, r_host, waves
+        self.stream = torch.cuda.Stream(device=be.device)
+        self.pending = {}
+        self._issue(0)
+
+    def _issue(self, wi):
+        if wi >= len(self.waves) or wi in self.pending:
+            return
+        c0, c1 = self.waves[wi]
+        with torch.cuda.stream(self.stream):
+            buf = self.r[c0:c1].to(self.be.device, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(self.stream)
+        self.pending[wi] = (buf, ev)
+
+    def get(self, wi):
+        self._issue(wi)
+        buf, ev = self.pending.pop(wi)
+        cur = torch.cuda.current_stream(self.be.device)
+        cur.wait_event(ev)
+        buf.record_stream(cur)
+        self._issue(wi + 1)  # the next wave's copy runs under this wave's kernels
+        return buf
+
+
 def wave_size(be: Backend, C: int, M: int, R: int, T: int, keep_posteriors: bool, budget_bytes: int | None = None):
     """Cells per wave so that workspace + outputs stay inside the memory budget (180 GB HBM3e
     holds ~1400 T=1980 problems with both work matrices resident)."""
@@ -78,7 +125,8 @@ def fit_weight_barycentre(realisations, observations, variance, lengthscale, *, 
     if posterior == "factored" and keep_posteriors:
         raise ValueError("posterior='factored' does not form the dense covariance keep_posteriors asks for")
     be = Backend.get()
-    r = be._in(realisations)
+    host_in = _is_host(realisations)
+    r = _as_f64(realisations) if host_in else be._in(realisations)
     o = be._in(observations)
     C, M, R, T = r.shape
     Ro = o.shape[1]
@@ -86,14 +134,20 @@ def fit_weight_barycentre(realisations, observations, variance, lengthscale, *, 
     ls = _per_problem(lengthscale, C, M, be.device)
     if cells_per_wave is None:
         cells_per_wave = wave_size(be, C, M, R, T, keep_posteriors)
+        if host_in and C >= 2 * HOST_PIPELINE_MIN_CELLS:
+            # host inputs: at least two waves, so that wave k+1's host-to-device copy (side stream) runs under
+            # wave k's kernels instead of in front of them
+            cells_per_wave = min(cells_per_wave, max(HOST_PIPELINE_MIN_CELLS, (C + 3) // 4))
+    waves = [(c0, min(C, c0 + cells_per_wave)) for c0 in range(0, C, cells_per_wave)]
+    fetch = _HostPrefetcher(be, r, waves) if host_in else None
     outs = []
-    for c0 in range(0, C, cells_per_wave):
-        c1 = min(C, c0 + cells_per_wave)
+    for wi, (c0, c1) in enumerate(waves):
         Cw = c1 - c0
-        X, ym, yv = be.gpdtw1d_inputs(r[c0:c1].reshape(Cw * M, R, T))
+        r_w = fetch.get(wi) if host_in else r[c0:c1]
+        X, ym, yv = be.gpdtw1d_inputs(r_w.reshape(Cw * M, R, T))
         if isinstance(y_mean, str):
             if y_mean == "dba":
-                ym = be.dtw_barycenter_averaging_subgradient(r[c0:c1].reshape(Cw * M, R, T), max_iter=50, tol=1e-3)
+                ym = be.dtw_barycenter_averaging_subgradient(r_w.reshape(Cw * M, R, T), max_iter=50, tol=1e-3)
             elif y_mean != "mean":
                 raise ValueError(f"y_mean must be 'mean', 'dba' or an array, got {y_mean!r}")
         else:

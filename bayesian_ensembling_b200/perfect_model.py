@@ -64,7 +64,9 @@ class PerfectModelTest:
         # :139-146
         nll_bary = -float(np.mean(barycentre._dist.log_prob(obs)))
         bmean = np.asarray(barycentre.mean.values, dtype=np.float64)
-        rmse_bary = float(np.mean(np.sqrt(np.mean((bmean - obs) ** 2, axis=0))))
+        # utils.py:141: xarray orders the dims of (barycentre.mean[time] - model_data[realisation,time]) by first
+        # appearance = (time, realisation), so its axis 0 is TIME: the mean inside the root runs over time
+        rmse_bary = float(np.mean(np.sqrt(np.mean((bmean[None, :] - obs) ** 2, axis=1))))
         truth = pseudo_observations_future.distribution._dist
         w2_bary = gaussian_w2_distance_distrax(barycentre._dist, truth, full_cov=hasattr(truth, "covariance"))
         # :148-155: the multi-model mean

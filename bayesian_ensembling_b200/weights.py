@@ -57,11 +57,21 @@ class LogLikelihoodWeight(AbstractWeight):
             loc = be._in(np.stack([m.distribution._dist.mean().ravel() for m in models])[None])
             scale = be._in(np.stack([m.distribution._dist.stddev().ravel() for m in models])[None])
             w, le, _ = be.loglik_weights_normal(loc, scale, obs_dev, standardisation_constant, want_lls=True)
-        elif not any(is_normal):  # weights.py:97-100 (quirk Q-LL)
+        elif all(hasattr(m.distribution._dist, "_stats") for m in models):  # weights.py:97-100 (quirk Q-LL)
             stats = torch.stack([m.distribution._dist._stats for m in models])  # [M,4] on device
             w, le, _ = be.loglik_weights_mvn(stats, obs_dev, M, standardisation_constant, want_lls=True)
         else:
-            raise NotImplementedError("mixed Normal / multivariate members")
+            # any other mix (a MultivariateNormalDiag member such as a Barycentre output or a diag checkpoint):
+            # the reference calls log_prob generically per member and realisation (weights.py:93-104)
+            lls_mean = []
+            for m, normal in zip(models, is_normal):
+                d = m.distribution._dist
+                lls = [np.asarray(d.log_prob(o if normal else o[:, None]), dtype=np.float64).ravel() for o in obs]
+                lls_mean.append(np.mean(np.asarray(lls), axis=0))
+            with np.errstate(over="ignore", under="ignore"):
+                le_t = be._in(np.exp(standardisation_constant * np.asarray(lls_mean))[None])  # :107
+            total = be.barycentre_1d_partial(le_t, le_t, le_t)[0]                        # NaN-skipping sum over models
+            w, le = be.weights_normalise(le_t, total), le_t                              # :122-123
         w = w[0].cpu().numpy()
         le = le[0].cpu().numpy()
 
@@ -174,15 +184,50 @@ class ModelSimilarityWeight(AbstractWeight):
 
                 warnings.warn('Mode "single" only really designed for small amounts of data. Kernel may crash. '
                               'Try mode="spatial"')
-            ii, jj = np.divmod(np.arange(M * M), M)
             dists_ = [m.distribution._dist for m in models]
             mu = torch.stack([_dev_vec(be, d, "mean") for d in dists_])
-            if all(isinstance(d, dists.Normal) for d in dists_):  # full_cov=False, weights.py:244-245
-                var = torch.stack([_dev_vec(be, d, "variance") for d in dists_])
-                w2 = be.w2_distance_diag(mu[ii], var[ii], mu[jj], var[jj])
-            else:
-                cov = torch.stack([be._in(d._cov if hasattr(d, "_cov") else np.asarray(d.covariance())) for d in dists_])
-                w2, _ = be.w2_distance(mu[ii], cov[ii], mu[jj], cov[jj])
+            var = torch.stack([_dev_vec(be, d, "variance") for d in dists_])
+            # weights.py:244-251: full_cov is decided per FIRST model of the pair (a dx.Normal i -> diagonal W2)
+            diag_i = np.array([isinstance(d, dists.Normal) for d in dists_])
+            w2 = torch.full((M, M), float("nan"), dtype=torch.float64, device=be.device)
+            iu, ju = np.triu_indices(M)
+            dg = diag_i[iu] & diag_i[ju]  # both diagonal: symmetric, one evaluation per unordered pair
+            if dg.any():
+                d2 = be.w2_distance_diag(mu[iu[dg]], var[iu[dg]], mu[ju[dg]], var[ju[dg]])
+                w2[iu[dg], ju[dg]] = d2
+                w2[ju[dg], iu[dg]] = d2
+            mixed = [(i, j) for i in range(M) for j in range(M) if diag_i[i] != diag_i[j]]
+            for i, j in mixed:  # the first model of the pair decides (rare: collections are homogeneous)
+                if diag_i[i]:
+                    w2[i, j] = be.w2_distance_diag(mu[i:i + 1], var[i:i + 1], mu[j:j + 1], var[j:j + 1])[0]
+                else:
+                    w2[i, j] = be.w2_distance(mu[i:i + 1], _dev_cov(be, dists_[i])[None], mu[j:j + 1],
+                                              _dev_cov(be, dists_[j])[None])[0][0]
+            fu = ~diag_i[iu] & ~diag_i[ju]
+            if fu.any():
+                # W2 is symmetric: only the pairs i <= j are evaluated, in chunks sized to the memory budget (the
+                # M*M materialised covariance copies of the first version ran out of memory at modest M, T)
+                cov = {k: _dev_cov(be, dists_[k]) for k in np.unique(np.concatenate([iu[fu], ju[fu]]))}
+                T_ = int(mu.shape[1])
+                free, _tot = torch.cuda.mem_get_info(be.device)
+                per_pair = 12 * (T_ + 18) ** 2 * 8
+                chunk = int(max(1, min(fu.sum(), (free * 0.5) // per_pair)))
+                pi, pj = iu[fu], ju[fu]
+                n_bad = 0
+                for s0 in range(0, len(pi), chunk):
+                    a, b = pi[s0:s0 + chunk], pj[s0:s0 + chunk]
+                    d2, info = be.w2_distance(mu[a], torch.stack([cov[k] for k in a]), mu[b],
+                                              torch.stack([cov[k] for k in b]))
+                    bad = info != 0
+                    n_bad += int(bad.sum())
+                    d2 = torch.where(bad, torch.full_like(d2, float("nan")), d2)  # nanmean then skips the pair
+                    w2[a, b] = d2
+                    w2[b, a] = d2
+                if n_bad:
+                    import warnings
+
+                    warnings.warn(f"ModelSimilarityWeight: {n_bad} pair(s) with a non-SPD covariance or an unconverged "
+                                  "matrix square root were left out (NaN)")
             w = be.w2_collapse(w2.reshape(1, M, M, 1))[0, :, 0].cpu().numpy()
             weights_array = DataArray(w[:, None], ("model", "time"), {"model": np.asarray(names), "time": np.asarray([0])},
                                       name="Model similarity weights")
@@ -231,6 +276,11 @@ class ModelSimilarityWeight(AbstractWeight):
         else:
             raise ValueError('Mode must be "single", "spatial", or "temporal"')
         return weights_array
+
+
+def _dev_cov(be, dist):
+    """[T,T] covariance of a member on the device."""
+    return dist._cov if hasattr(dist, "_cov") else be._in(np.asarray(dist.covariance(), dtype=np.float64))
 
 
 def _dev_vec(be, dist, what):

@@ -37,6 +37,10 @@ extern "C" {
 #define BE_ERR_CUDA 1000
 #define BE_ERR_WORKSPACE 1001
 #define BE_ERR_UNSUPPORTED 1002
+/* per-problem info of the iterative routines (be_sqrtm_psd, be_w2_distance, be_barycentre_fullcov): > 0 and
+ * below this value = first non-positive-definite leading minor (LAPACK style); this value = the iteration ended
+ * above its tolerance (max_iters reached or a NaN iterate) -- the result for that problem is not to be used */
+#define BE_INFO_NOT_CONVERGED 0x40000000
 
 #define BE_DEFAULT_JITTER 1e-6 /* gpflow.config.default_jitter() */
 
@@ -148,6 +152,11 @@ int be_loglik_weights_mvn(be_ctx* ctx, const double* mvn_stats, const double* ob
 /* per-realisation log-probs of the same branch, ll [C,M,Ro,T] (distribution.log_prob, :98-100) */
 int be_mvn_constvec_logprob(be_ctx* ctx, const double* mvn_stats, const double* obs,
                             int C, int M, int Ro, int T, double* ll);
+/* distrax MultivariateNormalTri.log_prob for N GENERAL vectors x [N,T] of one member (the NLL metric of
+ * ensembles/utils.py:139 calls it with the held-out realisations): z = L^-1 (x - mu) by forward substitution
+ * against the stored dense factor scale_tri [T,T] (data.py:38-39), sum_log_diag = mvn_stats[3]; ll [N]. */
+int be_mvn_log_prob(be_ctx* ctx, const double* mu, const double* scale_tri, const double* x,
+                    int T, int N, double sum_log_diag, double* ll);
 /* dx.Normal branch (:95-96): elementwise log N(x | loc, scale) -- 2nd argument is a SCALE
  * (quirk Q-SCALE).  n elements. */
 int be_normal_logprob(be_ctx* ctx, const double* loc, const double* scale, const double* x,

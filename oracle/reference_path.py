@@ -352,7 +352,7 @@ def loglik_weights_mvn(mus, scale_tris, obs, standardisation_constant=1.0):
     lls_mean = np.asarray(lls_mean)
     with np.errstate(over="ignore", under="ignore", invalid="ignore", divide="ignore"):
         model_lls = np.exp(standardisation_constant * lls_mean)
-        weights = model_lls / model_lls.sum(axis=0)
+        weights = model_lls / np.nansum(model_lls, axis=0)  # xarray .sum('model') skips NaN (skipna default)
     return weights, model_lls, lls_mean
 
 
@@ -363,7 +363,7 @@ def loglik_weights_normal(locs, scales, obs, standardisation_constant=1.0):
     )
     with np.errstate(over="ignore", under="ignore", invalid="ignore", divide="ignore"):
         model_lls = np.exp(standardisation_constant * lls_mean)
-        weights = model_lls / model_lls.sum(axis=0)
+        weights = model_lls / np.nansum(model_lls, axis=0)  # xarray .sum('model') skips NaN (skipna default)
     return weights, model_lls, lls_mean
 
 
@@ -476,7 +476,7 @@ def model_similarity_weights_single(mus, sigmas):
         for j in range(M):
             w2[i, j] = gaussian_w2_distance(mus[i], sigmas[i], mus[j], sigmas[j])
     v = np.nanmean(w2, axis=1)
-    return v / v.sum(), w2
+    return v / np.nansum(v), w2
 
 
 def w2_distance_diag(mu1, var1, mu2, var2):
@@ -500,7 +500,7 @@ def model_similarity_weights_temporal(means, variances):
             for t in range(T):
                 w2[i, j, t] = w2_distance_diag(means[i, t], v[i, t], means[j, t], v[j, t])
     m = np.nanmean(w2, axis=1)
-    return m / m.sum(axis=0), w2
+    return m / np.nansum(m, axis=0), w2
 
 
 def crps_gaussian(x, mu, sig):
@@ -524,7 +524,7 @@ def crps_weights(locs, variances, obs):
     crps = np.asarray([np.mean([crps_gaussian(o, l, s) for o in obs], axis=0) for l, s in zip(locs, variances)])
     with np.errstate(over="ignore", invalid="ignore", divide="ignore"):
         inv = 1.0 / crps
-        return inv / inv.sum(axis=0), crps
+        return inv / np.nansum(inv, axis=0), crps
 
 
 def ksd_imq(samples, grads, c=1.0, beta=-0.5):
@@ -561,7 +561,7 @@ def ksd_weights(locs, variances, obs):
             ksd[m, i] = ksd_imq(x, g)
     with np.errstate(over="ignore", invalid="ignore", divide="ignore"):
         inv = 1.0 / ksd
-        return inv / inv.sum(axis=0), ksd
+        return inv / np.nansum(inv, axis=0), ksd
 
 
 def inverse_square_weights(model_means, obs_mean):
@@ -569,7 +569,7 @@ def inverse_square_weights(model_means, obs_mean):
     normalised over models.  ``model_means [M,N]``, ``obs_mean [N]``."""
     with np.errstate(over="ignore", invalid="ignore", divide="ignore"):
         w = (np.asarray(model_means) - np.asarray(obs_mean)[None]) ** -2.0
-        return w / w.sum(axis=0)
+        return w / np.nansum(w, axis=0)
 
 
 def perfect_model_metrics(bary_mu, bary_scale, truth_mu, truth_cov, obs, forecast_realisations):
@@ -580,7 +580,9 @@ def perfect_model_metrics(bary_mu, bary_scale, truth_mu, truth_cov, obs, forecas
     ``forecast_realisations [sum R, T]`` (:148).  Returns (nll_bary, rmse_bary, w2_bary, nll_mmm, rmse_mmm, w2_mmm)."""
     obs = np.asarray(obs, dtype=np.float64)
     nll_bary = -np.mean(mvn_diag_log_prob(bary_mu, bary_scale, obs))                      # :139
-    rmse_bary = np.mean(np.sqrt(np.mean((bary_mu - obs) ** 2, axis=0)))                   # :141
+    # :141 -- xarray: dims of (mean[time] - data[realisation,time]) are (time, realisation), axis 0 = time;
+    # the multi-model-mean metric (:152) has a jnp array on the left and stays (realisation, time), axis 0
+    rmse_bary = np.mean(np.sqrt(np.mean((bary_mu[None, :] - obs) ** 2, axis=1)))
     w2_bary = gaussian_w2_distance(bary_mu, np.diag(bary_scale ** 2), truth_mu, truth_cov)  # :143-144 (full_cov=True)
     mmm_mu = np.mean(forecast_realisations, axis=0)
     mmm_scale = np.var(forecast_realisations, axis=0)                                     # :149 variance as scale

@@ -54,12 +54,12 @@ class OracleOps:
         lm = ll.mean(axis=2)
         with np.errstate(all="ignore"):
             le = np.exp(c * lm)
-            w = le / le.sum(axis=1, keepdims=True)
+            w = le / np.nansum(le, axis=1, keepdims=True)
         w, le, lm = torch.tensor(w), torch.tensor(le), torch.tensor(lm)
         return (w, le, lm) if want_lls else w
 
     def barycentre_1d_partial(self, means, variances, lls_exp):
-        return torch.stack([lls_exp.sum(1), (lls_exp * means).sum(1), (lls_exp * variances.sqrt()).sum(1)])
+        return torch.stack([torch.nansum(lls_exp, 1), (lls_exp * means).sum(1), (lls_exp * variances.sqrt()).sum(1)])
 
     def weights_normalise(self, lls_exp, total):
         with np.errstate(all="ignore"):

@@ -1,0 +1,180 @@
+"""Round-2 behaviour fixes, each against the oracle or a NumPy statement of the reference's semantics:
+NaN-skipping normalisers (xarray ``.sum('model')``), per-problem convergence of the batched matrix square
+root, the general-vector MVN log-density against the stored factor, and members without constant-vector
+statistics in LogLikelihoodWeight.  Needs a B200: ``-m gpu``."""
+import warnings
+
+import numpy as np
+import pytest
+import scipy.linalg as sla
+
+from bayesian_ensembling_b200 import synthetic
+from oracle import reference_path as rp
+from conftest import rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def _t(backend, a):
+    import torch
+
+    return torch.as_tensor(np.ascontiguousarray(a), dtype=torch.float64, device=backend.device)
+
+
+def _cell(M, R, T, Ro, seed):
+    cfg = synthetic.Config("t", 9, 1, M, R, T, Ro, False, "")
+    reals, obs = synthetic.make_cells(cfg, seed=seed)
+    return reals[0], obs[0]
+
+
+def _posteriors(M, R, T, seed):
+    reals, obs = _cell(M, R, T, 4, seed)
+    mus, covs = [], []
+    for m in range(M):
+        X, y, s = rp.gpdtw1d_inputs(reals[m])
+        mu, cov = rp.gp_posterior_closed_form(X, y, s, 0.5, 6.0)
+        mus.append(mu)
+        covs.append(cov)
+    return np.asarray(mus), np.asarray(covs), obs
+
+
+@pytest.mark.parametrize("M", [5, 40])
+def test_one_nan_member_leaves_the_others_normalised(backend, M):
+    """weights.py:122: xarray's .sum('model') skips NaN, so a member whose statistics are NaN (a failed
+    Cholesky) gets NaN weights while the others still sum to one -- in every normalising kernel."""
+    T, Ro = 40, 3
+    mus, covs, obs = _posteriors(M, 3, T, seed=12 + M)
+    tris = np.stack([np.linalg.cholesky(c) for c in covs])
+    stats = []
+    for m in range(M):
+        a = sla.solve_triangular(tris[m], np.ones(T), lower=True)
+        b = sla.solve_triangular(tris[m], mus[m], lower=True)
+        stats.append([a @ a, a @ b, b @ b, np.log(np.diag(tris[m])).sum()])
+    stats = np.array(stats) * np.array([1e-3, 1e-3, 1e-3, 0.0]) + np.array([0, 0, 0, -0.5 * T * rp.LOG_2PI])  # finite weights
+    bad = 2
+    stats[bad] = np.nan
+    w, le, lm = backend.loglik_weights_mvn(_t(backend, stats), _t(backend, obs[None, :Ro]), M, want_lls=True)
+    w = w[0].cpu().numpy()
+    assert np.isnan(w[bad]).all()
+    ok = np.arange(M) != bad
+    assert np.isfinite(w[ok]).all() and np.abs(w[ok].sum(axis=0) - 1.0).max() < 1e-12
+    le = le[0].cpu().numpy()
+    assert rel_err(w[ok], le[ok] / le[ok].sum(axis=0)) < 1e-12
+    # Normal branch, CRPS, KSD: same semantics
+    var = np.stack([np.diag(c) for c in covs])
+    loc, scale = mus.copy(), np.sqrt(var) + 0.3
+    loc[bad] = np.nan
+    for fn in (backend.loglik_weights_normal, backend.crps_weights, backend.ksd_weights):
+        wn = fn(_t(backend, loc[None]), _t(backend, scale[None]), _t(backend, obs[None, :Ro]))
+        wn = (wn[0] if isinstance(wn, tuple) else wn)[0].cpu().numpy()
+        assert np.isnan(wn[bad]).all(), fn.__name__
+        assert np.abs(wn[ok].sum(axis=0) - 1.0).max() < 1e-12, fn.__name__
+    # the oracle agrees (it normalises with nansum, as xarray does)
+    wo, _ = rp.crps_weights(loc, scale, obs[:Ro])
+    wc = backend.crps_weights(_t(backend, loc[None]), _t(backend, scale[None]), _t(backend, obs[None, :Ro]))[0].cpu().numpy()
+    assert (np.isnan(wo) == np.isnan(wc)).all() and rel_err(wc[ok], wo[ok]) < 1e-10
+    # member-sharded normaliser: the partial sum skips the NaN member too
+    part = backend.barycentre_1d_partial(_t(backend, mus[None]), _t(backend, var[None]), _t(backend, le[None]))
+    assert rel_err(part[0, 0].cpu().numpy(), le[ok].sum(axis=0)) < 1e-14
+
+
+def test_sqrtm_batch_with_one_bad_problem_converges_the_rest(backend):
+    """One non-SPD matrix in a batch must not stop the Denman-Beavers loop for the others."""
+    from bayesian_ensembling_b200 import _lib  # noqa: F401
+
+    T = 60
+    _, covs, _ = _posteriors(3, 4, T, seed=3)
+    rng = np.random.default_rng(0)
+    G = rng.standard_normal((T, T + 3))
+    slow = G @ G.T / T + 1e-6 * np.eye(T)       # ill-conditioned: needs many more iterations than the posteriors
+    bad = covs[1].copy()
+    bad[5, 5] = -1.0
+    A = np.stack([covs[0], bad, slow, covs[2]])
+    out, _, iters, info = backend.sqrtm_psd(_t(backend, A))
+    info = info.cpu().numpy()
+    assert info[1] != 0 and info[0] == 0 and info[2] == 0 and info[3] == 0
+    for b in (0, 2, 3):
+        got = out[b].cpu().numpy()
+        assert rel_err(got, rp.sqrtm_svd(A[b])) < 1e-8, b
+        assert rel_err(got @ got, A[b]) < 1e-10, b
+    # alone, the slow problem takes the same number of iterations as inside the batch
+    _, _, it_alone, _ = backend.sqrtm_psd(_t(backend, A[2:3]))
+    assert iters == it_alone
+    # an iteration cap that is too small is REPORTED, not silent
+    _, _, it2, info2 = backend.sqrtm_psd(_t(backend, A[2:3]), max_iters=2)
+    assert it2 == 2 and int(info2[0]) == 0x40000000
+
+
+def test_w2_batch_reports_bad_pair_and_keeps_the_others(backend):
+    T = 30
+    mus, covs, _ = _posteriors(3, 4, T, seed=9)
+    bad = covs[1].copy()
+    bad[3, 3] = -2.0
+    s1 = np.stack([covs[0], bad, covs[2]])
+    s2 = np.stack([covs[2], covs[0], covs[0]])
+    m1, m2 = mus, mus[[2, 0, 0]]
+    w2, info = backend.w2_distance(_t(backend, m1), _t(backend, s1), _t(backend, m2), _t(backend, s2))
+    info = info.cpu().numpy()
+    assert info[1] != 0 and info[0] == 0 and info[2] == 0
+    for p in (0, 2):
+        want = rp.gaussian_w2_distance(m1[p], s1[p], m2[p], s2[p])
+        assert abs(float(w2[p]) - want) < 1e-9 * max(1.0, abs(want))
+
+
+@pytest.mark.parametrize("T,N", [(1, 3), (33, 5), (165, 4), (300, 2)])
+def test_mvn_log_prob_general_vectors(backend, T, N):
+    """distrax MultivariateNormalTri.log_prob on general vectors: one forward substitution against the stored factor."""
+    mus, covs, _ = _posteriors(1, 4, T, seed=T)
+    L = np.linalg.cholesky(covs[0])
+    rng = np.random.default_rng(T)
+    x = mus[0] + 0.2 * rng.standard_normal((N, T))
+    ll = backend.mvn_log_prob(_t(backend, mus[0]), _t(backend, L), _t(backend, x), float(np.log(np.diag(L)).sum()))
+    want = rp.mvn_log_prob(mus[0], L, x)
+    assert rel_err(ll.cpu().numpy(), want) < 1e-12
+    from bayesian_ensembling_b200 import dists
+
+    d = dists.MultivariateNormalFullCovariance(mus[0], covs[0])
+    assert rel_err(d.log_prob(x), want) < 1e-11
+    if T > 1:
+        # and the constant-vector path (weights.py:98-100) is the same density at o * 1
+        o = np.array([0.3, -0.1])
+        assert rel_err(d.log_prob(o[:, None]), rp.mvn_log_prob(mus[0], L, np.outer(o, np.ones(T)))) < 1e-11
+
+
+def test_loglik_weight_accepts_members_without_constvec_statistics(backend):
+    """A MultivariateNormalDiag member (a Barycentre output, a diag checkpoint) goes through the generic
+    log_prob path of weights.py:93-104 instead of raising."""
+    import bayesian_ensembling_b200 as es
+    from bayesian_ensembling_b200 import dists
+    from bayesian_ensembling_b200.labelled import DataArray
+
+    M, R, T, Ro = 3, 3, 24, 2
+    reals, obs = _cell(M, R, T, Ro, seed=5)
+    time = np.arange(T)
+    pms = [es.ProcessModel(DataArray(reals[m], ("realisation", "time"), {"realisation": np.arange(R), "time": time}),
+                           f"model{m}") for m in range(M)]
+    obs_pm = es.ProcessModel(DataArray(obs, ("realisation", "time"), {"realisation": np.arange(Ro), "time": time}), "obs")
+    mc = es.ModelCollection(pms)
+    mc.fit(es.GPDTW1D(), n_optim_nits=2, progress_bar=False)
+    full = es.LogLikelihoodWeight()(mc, obs_pm, standardisation_constant=1e-3).values
+    # replace member 1 by a diagonal distribution with the same moments
+    d = mc[1].distribution
+    blank = d.dim_array
+    mc[1].distribution = es.Distribution(mu=d._dist.mean(), covariance=np.sqrt(d._dist.variance()), dim_array=blank,
+                                         dist_type=dists.MultivariateNormalDiag)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        mixed = es.LogLikelihoodWeight()(mc, obs_pm, standardisation_constant=1e-3).values
+    assert mixed.shape == full.shape and np.abs(np.nansum(mixed, axis=0) - 1.0).max() < 1e-9
+    # oracle: per member log_prob of the constant vectors, mean over realisations, exp, nansum-normalise
+    mus = [np.asarray(m.distribution._dist.mean()) for m in mc]
+    lls = []
+    for k, m in enumerate(mc):
+        dist = m.distribution._dist
+        if k == 1:
+            ll = [rp.mvn_diag_log_prob(mus[k], dist.stddev(), np.outer(o, np.ones(T))) for o in obs]
+        else:
+            ll = [rp.mvn_log_prob(mus[k], dist.scale_tri, o[:, None]) for o in obs]
+        lls.append(np.mean(ll, axis=0))
+    le = np.exp(1e-3 * np.asarray(lls))
+    assert rel_err(mixed, le / le.sum(axis=0)) < 1e-9

@@ -100,7 +100,10 @@ def wave_size(be: Backend, C: int, M: int, R: int, T: int, keep_posteriors: bool
     holds ~1400 T=1980 problems with both work matrices resident)."""
     if budget_bytes is None:
         free, _total = torch.cuda.mem_get_info(be.device)
-        budget_bytes = int(free * 0.8)
+        # memory torch's caching allocator holds but has not handed out is available to this call too (the
+        # workspace of the previous wave / step lives there)
+        cached = torch.cuda.memory_reserved(be.device) - torch.cuda.memory_allocated(be.device)
+        budget_bytes = int((free + max(cached, 0)) * 0.8)
     per_cell = be.posterior_workspace_bytes(M, T, R) + (2 * M * T * T * 8 if keep_posteriors else 0) + 64 * M * T
     return max(1, min(C, budget_bytes // max(per_cell, 1)))
 

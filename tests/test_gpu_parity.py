@@ -845,7 +845,7 @@ def test_similarity_weights_vs_oracle(backend):
             dist = np.abs(mu_b[:, None] - mu_b[None]) + ((v_b * np.abs(v_b))[:, None] + (v_b * np.abs(v_b))[None]
                                                          - 2.0 * np.sqrt(r[:, None] * (v_b * np.abs(v_b))[None] * r[:, None]))
             mean_d = np.nanmean(dist, axis=1)
-            want = mean_d / mean_d.sum(axis=0)
+            want = mean_d / np.nansum(mean_d, axis=0)  # weights.py:331: xarray .sum('model') skips NaN
     _nan_equal_close(got, want, 1e-12, "temporal similarity weights")
     # NaN distances are skipped by the nanmean
     d = np.arange(1.0, 1.0 + M * M * 3).reshape(1, M, M, 3)

@@ -25,9 +25,31 @@ def rel(a, b):
     return float(np.abs(a[ok] - b[ok]).max() / max(np.abs(b[ok]).max(), 1e-300)) if ok.any() else 0.0
 
 
+def repeat_check(n):
+    """Run-to-run determinism of the posterior pipeline: a shared-memory race or an ordering bug between launches
+    shows up as results that differ between identical calls (every kernel here has a fixed summation order)."""
+    for T, C in ((17, 3), (129, 2), (251, 40)):
+        cfg = synthetic.Config("s", 7, C, 4, 3, T, 3, False, "sanitize")
+        reals, obs = synthetic.make_cells(cfg)
+        first = None
+        for _ in range(n):
+            res = grid.fit_weight_barycentre(reals, obs, 0.5, 6.0, keep_posteriors=True)
+            got = [getattr(res, k).cpu().numpy() for k in ("mu", "cov", "scale_tri", "weights", "bary_mu", "bary_std")]
+            if first is None:
+                first = got
+            else:
+                for a, b in zip(first, got):
+                    assert np.array_equal(a, b, equal_nan=True), f"T={T}: results differ between identical calls"
+        print(f"T={T} x {C} cells: {n} identical calls, bit-identical results", flush=True)
+
+
 def main():
     quick = "--quick" in sys.argv
     be = Backend.get()
+    if "--repeat" in sys.argv:
+        repeat_check(int(sys.argv[sys.argv.index("--repeat") + 1]))
+        print("repeat check ok")
+        return
     worst = 0.0
     for T in ((17, 129) if quick else (17, 129, 251)):
         cfg = synthetic.Config("s", 7, 2, 3, 3, T, 3, False, "sanitize")

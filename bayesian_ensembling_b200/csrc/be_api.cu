@@ -10,6 +10,7 @@
 
 #include "../../include/be_b200.h"
 #include "be_kernels.cuh"
+#include "small_posterior.cuh"
 #include "vgp_kernels.cuh"
 #include "sqrtm_kernels.cuh"
 #include "weights_next_kernels.cuh"
@@ -21,12 +22,13 @@ using namespace be;
 // kernel families of the profiler (be_ctx_profile_*): one per kernel of be_kernels.cuh
 enum Family {
     F_INPUTS = 0, F_GRAM, F_DIAG, F_PANEL, F_SYRK, F_TRTRI, F_LAUUM, F_MEAN, F_STATS, F_COPY, F_WEIGHTS, F_BARY,
-    F_GEMM, F_VGP_MISC, F_SQRTM_MISC, F_DTW_DP, F_DTW_BACK, F_DBA_UPDATE, F_COUNT
+    F_GEMM, F_VGP_MISC, F_SQRTM_MISC, F_DTW_DP, F_DTW_BACK, F_DBA_UPDATE, F_SMALL_A, F_SMALL_B, F_COUNT
 };
 static const char* const kFamilyName[F_COUNT] = {
     "k_gpdtw1d_inputs", "k_matern32", "k_diag_block", "k_panel_scale", "k_chol_update", "k_trtri_accum",
     "k_lauum_cov", "k_posterior_mean", "k_mvn_stats", "copy/pad", "k_loglik_weights", "k_barycentre",
-    "k_gemm_nt", "vgp elementwise", "sqrtm elementwise", "k_dtw_dp", "k_dtw_backtrack", "k_dba_update"};
+    "k_gemm_nt", "vgp elementwise", "sqrtm elementwise", "k_dtw_dp", "k_dtw_backtrack", "k_dba_update",
+    "k_small_factor_inverse", "k_small_cov_factor"};
 
 struct ProfRecord {
     int family;
@@ -139,6 +141,8 @@ int ensure_kernel_attrs(be_ctx* ctx) {
     BE_CUDA(cudaFuncSetAttribute(k_panel_scale, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
     BE_CUDA(cudaFuncSetAttribute(k_trtri_accum, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
     BE_CUDA(cudaFuncSetAttribute(k_lauum_cov, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
+    BE_CUDA(cudaFuncSetAttribute(k_small_factor_inverse, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_SMEM_BYTES));
+    BE_CUDA(cudaFuncSetAttribute(k_small_cov_factor, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_SMEM_BYTES));
     BE_CUDA(cudaFuncSetAttribute(k_diag_block, cudaFuncAttributeMaxDynamicSharedMemorySize, DIAG_SMEM_BYTES));
     BE_CUDA(cudaFuncSetAttribute(k_diag_block2, cudaFuncAttributeMaxDynamicSharedMemorySize, DG2_SMEM_BYTES));
     BE_CUDA(cudaFuncSetAttribute(k_matern32<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
@@ -362,6 +366,77 @@ int vgp_iteration(be_ctx* ctx, const VgpBuffers& w, const double* X, const doubl
     return BE_OK;
 }
 
+
+// ---- small-T member path (small_posterior.cuh): T + 2 <= 256 ---------------------------------------------------
+// BE_NO_SMALL_T (environment) sends every size through the blocked path: the A/B switch of the parity tests.
+inline bool small_path(int T) {
+    const bool off = getenv("BE_NO_SMALL_T") != nullptr;  // read per call: the tests flip it inside one process
+    return !off && small_dim(T) <= SM_MAX_DIM;
+}
+inline size_t small_matrix_doubles(int B, int T) { return (size_t)B * small_dim(T) * small_dim(T); }
+inline size_t small_dinv_doubles(int B, int T) { return (size_t)B * (small_dim(T) / SB) * SB * SB; }
+
+size_t gp_posterior_small_workspace_bytes(int B, int T) {
+    return 2 * align_up(small_matrix_doubles(B, T) * 8, 256) + align_up(small_dinv_doubles(B, T) * 8, 256) +
+           align_up((size_t)B * T * 8, 256) + 1024;
+}
+
+int gp_posterior_small(be_ctx* ctx, const double* X, const double* y_mean, const double* y_var, const double* variance,
+                       const double* lengthscale, double jitter, int B, int T, int R, double* mu, double* var_diag,
+                       double* cov, double* scale_tri, double* mvn_stats, int* info_fit, int* info_dist,
+                       void* workspace, size_t workspace_bytes) {
+    const int n = small_dim(T);
+    Carver cv(workspace, workspace_bytes);
+    double* Mw = cv.take<double>(small_matrix_doubles(B, T));  // M -> C -> cov -> scale_tri
+    double* Vw = cv.take<double>(small_matrix_doubles(B, T));  // V = C^-T
+    double* Dinv = cv.take<double>(small_dinv_doubles(B, T));
+    double* u = cv.take<double>((size_t)B * T);
+    if (!Mw || !Vw || !Dinv || !u) return BE_ERR_WORKSPACE;
+    BE_CUDA(cudaMemsetAsync(info_fit, 0, sizeof(int) * B, ctx->stream));
+    BE_CUDA(cudaMemsetAsync(info_dist, 0, sizeof(int) * B, ctx->stream));
+    const int nblk = num_blocks(n), ntl = nblk * (nblk + 1) / 2;
+    const double dT = (double)T, dB = (double)B;
+    {
+        NvtxRange nv("be:small:gram");
+        Prof pr(ctx, F_GRAM, dB * 0.5 * dT * dT * (2.0 * R + 12.0), (dB * dT * R + dB * 0.5 * dT * dT) * 8);
+        k_matern32<1><<<(unsigned)((size_t)ntl * B), 256, matern_smem(R), ctx->stream>>>(
+            X, B, T, R, variance, lengthscale, y_mean, y_var, jitter, Mw, n, n, ntl);
+        BE_LAUNCHED();
+    }
+    {
+        // potrf (T^3/3) + triangular inverse (T^3/3); one pass over M and V in global memory (L2-resident)
+        NvtxRange nv("be:small:factor_inverse");
+        Prof pr(ctx, F_SMALL_A, dB * 2.0 / 3.0 * dT * dT * dT, dB * 1.5 * dT * dT * 8);
+        k_small_factor_inverse<<<B, SM_THREADS, SM_SMEM_BYTES, ctx->stream>>>(Mw, Vw, Dinv, u, info_fit, n, T);
+        BE_LAUNCHED();
+    }
+    {
+        NvtxRange nv("be:small:mean");
+        Prof pr(ctx, F_MEAN, dB * dT * dT, dB * (0.5 * dT * dT + 4.0 * dT) * 8);
+        k_posterior_mean<<<grid1d((size_t)B * T, 8), 256, 0, ctx->stream>>>(Vw, n, n, T, u, y_mean, y_var, jitter, mu, B);
+        BE_LAUNCHED();
+    }
+    {
+        // lauum (T^3/3) + Cholesky of the covariance (T^3/3)
+        NvtxRange nv("be:small:cov_factor");
+        Prof pr(ctx, F_SMALL_B, dB * 2.0 / 3.0 * dT * dT * dT, dB * dT * dT * (cov ? 2.5 : 1.5) * 8);
+        k_small_cov_factor<<<B, SM_THREADS, SM_SMEM_BYTES, ctx->stream>>>(Vw, Mw, y_var, jitter, mu, var_diag, cov,
+                                                                        info_dist, n, T);
+        BE_LAUNCHED();
+    }
+    {
+        Prof pr(ctx, F_STATS, 8.0 * dB * dT, dB * 3.0 * dT * 8);
+        k_mvn_stats<<<B, 256, 0, ctx->stream>>>(Mw, n, n, T, mvn_stats);
+        BE_LAUNCHED();
+    }
+    if (scale_tri) {
+        Prof pr(ctx, F_COPY, 0.0, dB * 1.5 * dT * dT * 8);
+        k_copy_out_tri<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(Mw, n, n, T, scale_tri, B);
+        BE_LAUNCHED();
+    }
+    return BE_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -538,8 +613,13 @@ int be_potrf_batched(be_ctx* ctx, const double* A, int B, int T, double* L, int*
 size_t be_gp_posterior_workspace_bytes(int B, int T, int R) {
     (void)R;
     size_t Tp = pad_dim(T);
-    return 2 * align_up(padded_matrix_doubles(B, T) * 8, 256) + align_up(dinv_doubles(B, T) * 8, 256) +
-           align_up(pbuf_doubles(B, T) * 8, 256) + align_up((size_t)B * Tp * 8, 256) + 1024;
+    size_t blocked = 2 * align_up(padded_matrix_doubles(B, T) * 8, 256) + align_up(dinv_doubles(B, T) * 8, 256) +
+                     align_up(pbuf_doubles(B, T) * 8, 256) + align_up((size_t)B * Tp * 8, 256) + 1024;
+    if (small_dim(T) <= SM_MAX_DIM) {  // either path may run (BE_NO_SMALL_T): room for both
+        size_t small = gp_posterior_small_workspace_bytes(B, T);
+        return small > blocked ? small : blocked;
+    }
+    return blocked;
 }
 
 int be_gp_posterior(be_ctx* ctx, const double* X, const double* y_mean, const double* y_var, const double* variance,
@@ -563,6 +643,9 @@ int be_gp_posterior(be_ctx* ctx, const double* X, const double* y_mean, const do
     if (!info_fit) return -16;
     if (!info_dist) return -17;
     if (!workspace || workspace_bytes < be_gp_posterior_workspace_bytes(B, T, R)) return BE_ERR_WORKSPACE;
+    if (small_path(T))  // T + 2 <= 256: one CTA per member problem, two fused kernels (small_posterior.cuh)
+        return gp_posterior_small(ctx, X, y_mean, y_var, variance, lengthscale, jitter, B, T, R, mu, var_diag, cov,
+                                  scale_tri, mvn_stats, info_fit, info_dist, workspace, workspace_bytes);
     const int Tp = pad_dim(T), ld = Tp, nblk = num_blocks(Tp);
     Carver cv(workspace, workspace_bytes);
     double* Mw = cv.take<double>(padded_matrix_doubles(B, T));  // M -> C -> cov -> scale_tri

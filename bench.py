@@ -338,7 +338,8 @@ def measure_dba(be, r_dev, cfg, step_ms, max_iter, with_cpu):
 # ------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------
-TENSOR_FAMILIES = {"k_chol_update", "k_trtri_accum", "k_lauum_cov", "k_panel_scale", "k_diag_block"}
+TENSOR_FAMILIES = {"k_chol_update", "k_trtri_accum", "k_lauum_cov", "k_panel_scale", "k_diag_block",
+                   "k_small_factor_inverse", "k_small_cov_factor"}
 
 # ------------------------------------------------------------------------------------------------
 # one workload, timed: device-resident steps (CUDA events, per-kernel profile) and end-to-end steps

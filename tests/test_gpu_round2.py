@@ -178,3 +178,71 @@ def test_loglik_weight_accepts_members_without_constvec_statistics(backend):
         lls.append(np.mean(ll, axis=0))
     le = np.exp(1e-3 * np.asarray(lls))
     assert rel_err(mixed, le / le.sum(axis=0)) < 1e-9
+
+
+# ------------------------------------------------------------------------------------ small-T member kernels
+@pytest.mark.parametrize("T,R,M", [(1, 2, 2), (2, 3, 2), (7, 2, 3), (30, 3, 3), (31, 3, 2), (32, 3, 2), (33, 4, 2),
+                                   (62, 3, 2), (86, 5, 3), (128, 4, 2), (165, 10, 4), (222, 3, 2), (223, 3, 2),
+                                   (251, 10, 5), (254, 3, 2)])
+def test_small_t_member_kernels_vs_oracle_and_blocked_path(backend, T, R, M, monkeypatch):
+    """T + 2 <= 256 runs through the one-CTA-per-member kernels (small_posterior.cuh); BE_NO_SMALL_T sends the same
+    call through the blocked path.  Both against the oracle (<= 1e-8, north star) and against each other."""
+    reals, obs = _cell(M, R, T, 3, seed=4000 + T)
+    X, ym, yv = backend.gpdtw1d_inputs(_t(backend, reals))
+    var, ls = np.full(M, 0.5), np.full(M, 6.0)
+    monkeypatch.delenv("BE_NO_SMALL_T", raising=False)
+    small = backend.gp_posterior(X, ym, yv, var, ls)
+    monkeypatch.setenv("BE_NO_SMALL_T", "1")
+    blocked = backend.gp_posterior(X, ym, yv, var, ls)
+    monkeypatch.delenv("BE_NO_SMALL_T", raising=False)
+    assert int(small.info_fit.abs().sum()) == 0 and int(small.info_dist.abs().sum()) == 0
+    worst = 0.0
+    for m in range(M):
+        Xo, yo, so = rp.gpdtw1d_inputs(reals[m])
+        mu_o, cov_o = rp.gp_posterior_closed_form(Xo, yo, so, 0.5, 6.0)
+        L_o = np.linalg.cholesky(cov_o)
+        a = sla.solve_triangular(L_o, np.ones(T), lower=True)
+        b = sla.solve_triangular(L_o, mu_o, lower=True)
+        st_o = np.array([a @ a, a @ b, b @ b, np.log(np.diag(L_o)).sum()])
+        for name, got, want, tol in (("mu", small.mu[m], mu_o, 1e-8), ("cov", small.cov[m], cov_o, 1e-8),
+                                     ("scale_tri", small.scale_tri[m], L_o, 1e-8),
+                                     ("var_diag", small.var_diag[m], np.diag(cov_o), 1e-8)):
+            e = rel_err(got.cpu().numpy(), want)
+            worst = max(worst, e)
+            assert e <= tol, (T, m, name, e)
+        st = small.mvn_stats[m].cpu().numpy()
+        scale = np.array([st_o[0], np.sqrt(st_o[0] * st_o[2]), st_o[2], max(abs(st_o[3]), 1.0)])
+        assert (np.abs(st - st_o) / scale).max() <= 1e-10, (T, m, st, st_o)
+        assert np.array_equal(small.cov[m].cpu().numpy(), small.cov[m].cpu().numpy().T)
+        assert np.abs(np.triu(small.scale_tri[m].cpu().numpy(), 1)).max() == 0.0
+    for name in ("mu", "cov", "scale_tri", "var_diag", "mvn_stats"):
+        x, y = getattr(small, name).cpu().numpy(), getattr(blocked, name).cpu().numpy()
+        assert rel_err(x, y) <= 1e-10, (T, name, rel_err(x, y))
+    print(f"small-T kernels T={T}: worst rel err vs oracle {worst:.2e}")
+
+
+def test_small_t_member_kernels_many_problems_and_non_pd_report(backend):
+    """Thousands of CTAs (more than two waves), one of them non-positive-definite: its report is LAPACK's, the
+    others are untouched; a repeated call returns bit-identical results."""
+    T, M, C = 100, 5, 240
+    cfg = synthetic.Config("t", 9, C, M, 3, T, 3, False, "")
+    reals, obs = synthetic.make_cells(cfg, seed=99)
+    r = _t(backend, reals.reshape(C * M, 3, T))
+    X, ym, yv = backend.gpdtw1d_inputs(r)
+    yv = yv.clone()
+    bad = 777
+    yv[bad, 40] = -5.0  # M[40, 40] = K + y_var + jitter < 0: leading minor of order 41 is not positive definite
+    var, ls = np.full(C * M, 0.5), np.full(C * M, 6.0)
+    a = backend.gp_posterior(X, ym, yv, var, ls, want_cov=False, want_scale_tri=False)
+    b = backend.gp_posterior(X, ym, yv, var, ls, want_cov=False, want_scale_tri=False)
+    info = a.info_fit.cpu().numpy()
+    assert info[bad] == 41 and np.count_nonzero(info) == 1
+    ok = np.arange(C * M) != bad
+    assert int(a.info_dist.cpu().numpy()[ok].sum()) == 0
+    for name in ("mu", "var_diag", "mvn_stats"):
+        assert np.array_equal(getattr(a, name).cpu().numpy()[ok], getattr(b, name).cpu().numpy()[ok]), name
+    for k in (0, 776, 778, C * M - 1):
+        Xo, yo, so = rp.gpdtw1d_inputs(reals.reshape(C * M, 3, T)[k])
+        mu_o, cov_o = rp.gp_posterior_closed_form(Xo, yo, so, 0.5, 6.0)
+        assert rel_err(a.mu[k].cpu().numpy(), mu_o) <= 1e-8
+        assert rel_err(a.var_diag[k].cpu().numpy(), np.diag(cov_o)) <= 1e-8

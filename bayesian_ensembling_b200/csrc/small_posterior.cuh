@@ -23,9 +23,9 @@
 //   * the accumulators (16 rows x 32 columns per warp pass) stay in registers through the triangular scale that
 //     follows (X <- +/- OUT * Linv^T): with the k-permutation of dmma_gemm.cuh the accumulator pair of a thread IS
 //     the A fragment of the next product, so no shuffle or shared-memory transpose is needed.
-// The 32 x 32 diagonal blocks are factored and inverted by one warp in shared memory (8-column steps, every lane
-// factors the 8 x 8 pivot block redundantly in registers -- no shuffles -- and eliminates its own row; the inverse
-// is one column per lane).  FP64 DMMA issues at one instruction per 16 cycles per SM sub-partition, so fragment
+// The 32 x 32 diagonal blocks are factored and inverted in shared memory by the whole CTA (8-column steps: one warp
+// factors the 8 x 8 pivot block redundantly per lane -- no shuffles -- and eliminates the rows, all threads update
+// the trailing entries; the inverse is recursive doubling on the tensor pipe).  FP64 DMMA issues at one instruction per 16 cycles per SM sub-partition, so fragment
 // traffic (one LDS.128 / LDG.128 per 2-4 DMMAs) is far from any limit: the design problem at this size is latency
 // and barriers, not bandwidth.
 //
@@ -43,8 +43,9 @@ constexpr int SM_LDB = SM_MAX_DIM + 8;  // B-panel row stride: == 8 (mod 16) dou
 constexpr int SM_LDD = SB + 8;          // diagonal-block tiles, same residue
 constexpr int SM_THREADS = 256;
 constexpr int SM_WARPS = SM_THREADS / 32;
-constexpr int SM_SMEM_DOUBLES = SB * SM_LDB + 2 * SB * SM_LDD + SB;
-constexpr int SM_SMEM_BYTES = SM_SMEM_DOUBLES * 8;  // 88 064 B: two CTAs per SM
+constexpr int SM_LDT = 20;              // scratch tile of the recursive-doubling inverse (== 4 mod 16)
+constexpr int SM_SMEM_DOUBLES = SB * SM_LDB + 2 * SB * SM_LDD + SB + 16 * SM_LDT;
+constexpr int SM_SMEM_BYTES = SM_SMEM_DOUBLES * 8;  // 90 624 B: two CTAs per SM
 
 __host__ __device__ inline int small_dim(int T) { return ((T + 2 + SB - 1) / SB) * SB; }
 
@@ -53,8 +54,10 @@ struct SmallSmem {
     double* D;    // [32][SM_LDD]  diagonal block being factored
     double* Inv;  // [32][SM_LDD]  its inverse (lower)
     double* rd;   // [32]          1 / diag
+    double* Tmp;  // [16][SM_LDT]  scratch of the inverse
     __device__ explicit SmallSmem(double* base)
-        : B(base), D(base + SB * SM_LDB), Inv(base + SB * SM_LDB + SB * SM_LDD), rd(base + SB * SM_LDB + 2 * SB * SM_LDD) {}
+        : B(base), D(base + SB * SM_LDB), Inv(base + SB * SM_LDB + SB * SM_LDD), rd(base + SB * SM_LDB + 2 * SB * SM_LDD),
+          Tmp(base + SB * SM_LDB + 2 * SB * SM_LDD + SB) {}
 };
 
 // 16 rows x 32 columns of output per warp pass, in DMMA accumulator layout: thread (g = lane / 4, q = lane % 4) holds
@@ -178,102 +181,144 @@ __device__ __forceinline__ void load_panel(double* sB, const double* src, int ld
 // shrinking (potrf, lauum) or growing (trtri) set of active rows of a block step is spread over all warps
 __device__ __forceinline__ int first_owned(int lo, int warp) { return lo + ((warp - lo) & (SM_WARPS - 1)); }
 
-// Cholesky of the 32 x 32 block in sD (lower part, columns < nr real), by ONE warp; lane = row.  Rows >= nr (padding /
-// right-hand sides inside the band) are eliminated like any row below the real block; columns >= nr are never
-// touched.  sRd receives 1 / diag (1 for the padding columns).  Returns the LAPACK-style report (0 = fine).
+// Cholesky of the 32 x 32 block in sD (lower part, columns < nr real) by the whole CTA, in four 8-column steps:
+//   phase 1 (warp 0, lane = row): every lane factors the 8 x 8 pivot block REDUNDANTLY in its registers (no
+//            shuffles, no hand-off) and eliminates its own row with it -- the 8 dependent rsqrt of this chain
+//            (~100 cycles each, profiles/r02c ubench: rsqrt 75, dfma 8.4) are the irreducible serial part;
+//   phase 2 (all 256 threads): one trailing entry per thread, D[i, c] -= L[i, c0:c0+8] . L[c, c0:c0+8].
+// (The first version did phase 2 inside warp 0, one dependent chain per column: 15 k cycles per block, with seven
+// warps waiting at the barrier -- 38 % of the kernel, ncu r02c.)  Rows >= nr (padding / right-hand sides inside the
+// band) are eliminated like any row below the real block; columns >= nr are never touched.  sRd receives 1 / diag
+// (1 for the padding columns).  Returns the LAPACK-style report (0 = fine), valid in warp 0.  Ends with a barrier.
 __device__ __forceinline__ int diag_factor32(double* sD, double* sRd, int nr, int base) {
-    const int i = threadIdx.x & 31;
+    const int tid = threadIdx.x, i = tid & 31, warp = tid >> 5;
     int bad = 0;
 #pragma unroll 1
     for (int s = 0; s < 4; ++s) {
         const int c0 = 8 * s;
         const int w = min(8, nr - c0);
-        if (w <= 0) {
-            if (i < 8) sRd[c0 + i] = 1.0;
+        if (w <= 0) {  // CTA-uniform
+            if (tid < 8) sRd[c0 + tid] = 1.0;
             continue;
         }
-        double Lb[8][8], pv[8], rs[8];
+        if (warp == 0) {
+            double Lb[8][8], pv[8], rs[8];
 #pragma unroll
-        for (int a = 0; a < 8; ++a)
+            for (int a = 0; a < 8; ++a)
 #pragma unroll
-            for (int b = 0; b <= a; ++b) {
-                const double v = sD[(c0 + a) * SM_LDD + c0 + b];
-                Lb[a][b] = (a < w) ? v : (a == b ? 1.0 : 0.0);
-            }
-#pragma unroll
-        for (int b = 0; b < 8; b += 2) {
-            const double2 t = *reinterpret_cast<const double2*>(sD + i * SM_LDD + c0 + b);
-            pv[b] = t.x;
-            pv[b + 1] = t.y;
-        }
-        __syncwarp();  // every lane holds its copy of the pivot block before rows are rewritten
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const double piv = Lb[j][j];
-            bad = (bad == 0 && j < w && !(piv > 0.0)) ? base + c0 + j + 1 : bad;
-            const double r = fast_rsqrt(piv);
-            rs[j] = r;
-#pragma unroll
-            for (int a = j + 1; a < 8; ++a) Lb[a][j] *= r;
-#pragma unroll
-            for (int b = j + 1; b < 8; ++b)
-#pragma unroll
-                for (int a = b; a < 8; ++a) Lb[a][b] = fma(-Lb[a][j], Lb[b][j], Lb[a][b]);
-            pv[j] *= r;
-#pragma unroll
-            for (int b = j + 1; b < 8; ++b) pv[b] = fma(-pv[j], Lb[b][j], pv[b]);
-        }
-        if (i >= c0) {
+                for (int b = 0; b <= a; ++b) {
+                    const double v = sD[(c0 + a) * SM_LDD + c0 + b];
+                    Lb[a][b] = (a < w) ? v : (a == b ? 1.0 : 0.0);
+                }
 #pragma unroll
             for (int b = 0; b < 8; b += 2) {
-                double2 o;
-                o.x = (c0 + b <= i) ? pv[b] : 0.0;
-                o.y = (c0 + b + 1 <= i) ? pv[b + 1] : 0.0;
-                *reinterpret_cast<double2*>(sD + i * SM_LDD + c0 + b) = o;
+                const double2 t = *reinterpret_cast<const double2*>(sD + i * SM_LDD + c0 + b);
+                pv[b] = t.x;
+                pv[b + 1] = t.y;
             }
-        }
-        if (i == 0) {
+            __syncwarp();  // every lane holds its copy of the pivot block before rows are rewritten
 #pragma unroll
-            for (int j = 0; j < 8; ++j) sRd[c0 + j] = rs[j];
-        }
-        __syncwarp();
-        // trailing real columns of the lane's own row: D[i, c] -= sum_j L[i, c0 + j] L[c, c0 + j]
-        if (i >= c0 + 8) {
-            const int cend = min(nr - 1, i);
-#pragma unroll 1
-            for (int c = c0 + 8; c <= cend; ++c) {
-                const double* lc = sD + c * SM_LDD + c0;
-                double acc = sD[i * SM_LDD + c];
+            for (int j = 0; j < 8; ++j) {
+                const double piv = Lb[j][j];
+                bad = (bad == 0 && j < w && !(piv > 0.0)) ? base + c0 + j + 1 : bad;
+                const double r = fast_rsqrt(piv);
+                rs[j] = r;
 #pragma unroll
-                for (int j = 0; j < 8; j += 2) {
-                    const double2 t = *reinterpret_cast<const double2*>(lc + j);
-                    acc = fma(-pv[j], t.x, acc);
-                    acc = fma(-pv[j + 1], t.y, acc);
+                for (int a = j + 1; a < 8; ++a) Lb[a][j] *= r;
+#pragma unroll
+                for (int b = j + 1; b < 8; ++b)
+#pragma unroll
+                    for (int a = b; a < 8; ++a) Lb[a][b] = fma(-Lb[a][j], Lb[b][j], Lb[a][b]);
+                pv[j] *= r;
+#pragma unroll
+                for (int b = j + 1; b < 8; ++b) pv[b] = fma(-pv[j], Lb[b][j], pv[b]);
+            }
+            if (i >= c0) {
+#pragma unroll
+                for (int b = 0; b < 8; b += 2) {
+                    double2 o;
+                    o.x = (c0 + b <= i) ? pv[b] : 0.0;
+                    o.y = (c0 + b + 1 <= i) ? pv[b + 1] : 0.0;
+                    *reinterpret_cast<double2*>(sD + i * SM_LDD + c0 + b) = o;
                 }
-                sD[i * SM_LDD + c] = acc;
+            }
+            if (i == 0) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) sRd[c0 + j] = rs[j];
             }
         }
-        __syncwarp();
+        __syncthreads();
+        // trailing real columns [c0 + 8, nr): one entry (row, col <= row) per thread
+        const int m = SB - c0 - 8;
+        for (int e = tid; e < m * m; e += SM_THREADS) {
+            const int ii = e / m, cc = e - ii * m;
+            const int r = c0 + 8 + ii, c = c0 + 8 + cc;
+            if (c > r || c >= nr) continue;
+            const double* lr = sD + r * SM_LDD + c0;
+            const double* lc = sD + c * SM_LDD + c0;
+            double acc0 = sD[r * SM_LDD + c], acc1 = 0.0;
+#pragma unroll
+            for (int j = 0; j < 8; j += 4) {
+                const double2 a0 = *reinterpret_cast<const double2*>(lr + j), a1 = *reinterpret_cast<const double2*>(lr + j + 2);
+                const double2 b0 = *reinterpret_cast<const double2*>(lc + j), b1 = *reinterpret_cast<const double2*>(lc + j + 2);
+                acc0 = fma(-a0.x, b0.x, acc0);
+                acc1 = fma(-a0.y, b0.y, acc1);
+                acc0 = fma(-a1.x, b1.x, acc0);
+                acc1 = fma(-a1.y, b1.y, acc1);
+            }
+            sD[r * SM_LDD + c] = acc0 + acc1;
+        }
+        __syncthreads();
     }
+    __syncthreads();
     return bad;
 }
 
-// Inverse of blockdiag(L11, I) (L11 = the nr real rows / columns of the factored block in sD) by ONE warp: lane c
-// solves column c by forward substitution, x_i = (delta_ic - sum_{k<i} L_ik x_k) / L_ii.
-__device__ __forceinline__ void diag_inverse32(const double* sD, const double* sRd, double* sInv, int nr) {
-    const int c = threadIdx.x & 31;
-    double x[32];
-#pragma unroll
-    for (int i = 0; i < 32; ++i) {
-        double s = (i == c) ? 1.0 : 0.0;
-        if (i < nr) {  // warp-uniform; rows >= nr are identity rows
-#pragma unroll
-            for (int k = 0; k < i; ++k) s = fma(-sD[i * SM_LDD + k], x[k], s);
-        }
-        x[i] = (i >= c) ? s * sRd[i] : 0.0;
+// sInv = inverse of blockdiag(L11, I) (L11 = the nr real rows / columns of the factored block in sD), by the whole
+// CTA: the four 8 x 8 diagonal blocks by forward substitution (one column per thread), then recursive doubling
+//   inv([[A, 0], [B, C]]) = [[A^-1, 0], [-C^-1 B A^-1, C^-1]]
+// at block sizes 8 and 16, every product on the FP64 tensor pipe (level_product of chol_diag.cuh).  The first
+// version solved one column per lane in ONE warp: a 496-FMA dependent chain, 10 k cycles per block (ncu r02c).
+// Ends with a barrier.
+__device__ __forceinline__ void diag_inverse32(const double* sD, const double* sRd, double* S, double* sTmp, int nr) {
+    const int tid = threadIdx.x;
+    for (int e = tid; e < SB * SB; e += SM_THREADS) {
+        const int r = e >> 5, c = e & 31;
+        S[r * SM_LDD + c] = c <= r ? (r < nr ? sD[r * SM_LDD + c] : (r == c ? 1.0 : 0.0)) : 0.0;
     }
+    __syncthreads();
+    {
+        double x[8];
+        const int blk = (tid >> 3) & 3, cidx = tid & 7;
+        double* Lb = S + (blk * 8) * SM_LDD + blk * 8;
+        if (tid < 32) {
 #pragma unroll
-    for (int i = 0; i < 32; ++i) sInv[i * SM_LDD + c] = x[i];
+            for (int i = 0; i < 8; ++i) {
+                double sacc = (i == cidx) ? 1.0 : 0.0;
+#pragma unroll
+                for (int k = 0; k < i; ++k) sacc = fma(-Lb[i * SM_LDD + k], (k >= cidx) ? x[k] : 0.0, sacc);
+                x[i] = (i >= cidx) ? sacc * sRd[blk * 8 + i] : 0.0;
+            }
+        }
+        __syncthreads();
+        if (tid < 32) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+                if (i >= cidx) Lb[i * SM_LDD + cidx] = x[i];
+        }
+        __syncthreads();
+    }
+#pragma unroll 1
+    for (int s = 8; s <= 16; s *= 2) {
+        const int npairs = 16 / s;
+        const int stride = 2 * s * SM_LDD + 2 * s;  // from one pair's A to the next
+        // T_p = B_p * Ainv_p -> Tmp (pair p at column offset p * s, rows 0 .. s)
+        level_product(S + s * SM_LDD, SM_LDD, stride, S, SM_LDD, stride, sTmp, SM_LDT, s, s, npairs, 1.0);
+        __syncthreads();
+        // B_p = -Cinv_p * T_p
+        level_product(S + s * SM_LDD + s, SM_LDD, stride, sTmp, SM_LDT, s, S + s * SM_LDD, SM_LDD, stride, s, npairs, -1.0);
+        __syncthreads();
+    }
 }
 
 // In-place Cholesky of the lower triangle of the padded n x n matrix Mat (n = 32 nb), real dimension T, left-looking
@@ -308,13 +353,11 @@ __device__ __forceinline__ void potrf_small(double* Mat, int ld, int nb, int T, 
                 sub_store(c, Mat + (size_t)16 * r * ld + kc, ld);  // unscaled; scaled below once the inverse exists
         }
         __syncthreads();
-        if (warp == 0) {
+        {
             const int bad = diag_factor32(sm.D, sm.rd, nr, kc);
-            __syncwarp();
-            diag_inverse32(sm.D, sm.rd, sm.Inv, nr);
-            if ((threadIdx.x & 31) == 0 && bad != 0 && info_b && *info_b == 0) *info_b = bad;
+            if (threadIdx.x == 0 && bad != 0 && info_b && *info_b == 0) *info_b = bad;
+            diag_inverse32(sm.D, sm.rd, sm.Inv, sm.Tmp, nr);
         }
-        __syncthreads();
         // the factor's diagonal block (lower, real columns only; strict upper part of the real rows cleaned), the
         // inverse for the triangular-inverse stage and the diagonal tile of V = C^-T
         for (int e = threadIdx.x; e < SB * SB; e += SM_THREADS) {
@@ -347,12 +390,16 @@ __device__ __forceinline__ void trtri_small(double* Vt, const double* Cm, int ld
 #pragma unroll 1
     for (int i = 1; i < nb; ++i) {
         const int ic = SB * i;
+        // the inverted diagonal block rides in the same cp.async group as the panel
+        for (int c = threadIdx.x; c < SB * SB / 2; c += SM_THREADS)
+            cp_async16(sm.Inv + (c >> 4) * SM_LDD + 2 * (c & 15), Dinv + (size_t)i * SB * SB + 2 * c, true);
         load_panel(sm.B, Cm + (size_t)ic * ld, ld, ic);
-        for (int e = threadIdx.x; e < SB * SB; e += SM_THREADS)
-            sm.Inv[(e >> 5) * SM_LDD + (e & 31)] = Dinv[(size_t)i * SB * SB + e];
         __syncthreads();
+        // row sub-block r contracts K = 32 (i - r / 2) columns: warps take r and (2 i - 1 - r) in turns ("snake"), so
+        // that every warp's total K is about the same
 #pragma unroll 1
-        for (int r = first_owned(0, warp); r < 2 * i; r += SM_WARPS) {
+        for (int t = warp; t < 2 * i; t += SM_WARPS) {
+            const int r = t >= SM_WARPS ? 2 * i - 1 - (t - SM_WARPS) : t;  // at most two rounds (2 i <= 16)
             SubAcc acc, x;
             sub_zero(acc);
             sub_gemm(acc, Vt + (size_t)16 * r * ld, ld, sm.B, 0, SB * (r >> 1), ic);

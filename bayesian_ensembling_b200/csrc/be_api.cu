@@ -374,11 +374,9 @@ inline bool small_path(int T) {
     return !off && small_dim(T) <= SM_MAX_DIM;
 }
 inline size_t small_matrix_doubles(int B, int T) { return (size_t)B * small_dim(T) * small_dim(T); }
-inline size_t small_dinv_doubles(int B, int T) { return (size_t)B * (small_dim(T) / SB) * SB * SB; }
 
 size_t gp_posterior_small_workspace_bytes(int B, int T) {
-    return 2 * align_up(small_matrix_doubles(B, T) * 8, 256) + align_up(small_dinv_doubles(B, T) * 8, 256) +
-           align_up((size_t)B * T * 8, 256) + 1024;
+    return 2 * align_up(small_matrix_doubles(B, T) * 8, 256) + align_up((size_t)B * T * 8, 256) + 1024;
 }
 
 int gp_posterior_small(be_ctx* ctx, const double* X, const double* y_mean, const double* y_var, const double* variance,
@@ -389,9 +387,8 @@ int gp_posterior_small(be_ctx* ctx, const double* X, const double* y_mean, const
     Carver cv(workspace, workspace_bytes);
     double* Mw = cv.take<double>(small_matrix_doubles(B, T));  // M -> C -> cov -> scale_tri
     double* Vw = cv.take<double>(small_matrix_doubles(B, T));  // V = C^-T
-    double* Dinv = cv.take<double>(small_dinv_doubles(B, T));
     double* u = cv.take<double>((size_t)B * T);
-    if (!Mw || !Vw || !Dinv || !u) return BE_ERR_WORKSPACE;
+    if (!Mw || !Vw || !u) return BE_ERR_WORKSPACE;
     BE_CUDA(cudaMemsetAsync(info_fit, 0, sizeof(int) * B, ctx->stream));
     BE_CUDA(cudaMemsetAsync(info_dist, 0, sizeof(int) * B, ctx->stream));
     const int nblk = num_blocks(n), ntl = nblk * (nblk + 1) / 2;
@@ -407,7 +404,7 @@ int gp_posterior_small(be_ctx* ctx, const double* X, const double* y_mean, const
         // potrf (T^3/3) + triangular inverse (T^3/3); one pass over M and V in global memory (L2-resident)
         NvtxRange nv("be:small:factor_inverse");
         Prof pr(ctx, F_SMALL_A, dB * 2.0 / 3.0 * dT * dT * dT, dB * 1.5 * dT * dT * 8);
-        k_small_factor_inverse<<<B, SM_THREADS, SM_SMEM_BYTES, ctx->stream>>>(Mw, Vw, Dinv, u, info_fit, n, T);
+        k_small_factor_inverse<<<B, SM_THREADS, SM_SMEM_BYTES, ctx->stream>>>(Mw, Vw, u, info_fit, n, T);
         BE_LAUNCHED();
     }
     {
@@ -442,6 +439,18 @@ int gp_posterior_small(be_ctx* ctx, const double* X, const double* y_mean, const
 extern "C" {
 
 int be_version(void) { return 100; }
+
+#ifdef BE_SMALL_TIMING
+/* developer build only (tools/gpu_small_timing.sh): per-phase cycle totals of one CTA of the small-T kernels */
+int be_debug_small_timing(long long* out, int reset) {
+    if (out) cudaMemcpyFromSymbol(out, g_small_timing, sizeof(long long) * 2 * 256);
+    if (reset) {
+        static long long zeros[2 * 256];
+        cudaMemcpyToSymbol(g_small_timing, zeros, sizeof(zeros));
+    }
+    return 0;
+}
+#endif
 
 int be_ctx_create(int device, void* stream, be_ctx** out) {
     if (!out) return -3;

@@ -44,20 +44,52 @@ constexpr int SM_LDD = SB + 8;          // diagonal-block tiles, same residue
 constexpr int SM_THREADS = 256;
 constexpr int SM_WARPS = SM_THREADS / 32;
 constexpr int SM_LDT = 20;              // scratch tile of the recursive-doubling inverse (== 4 mod 16)
-constexpr int SM_SMEM_DOUBLES = SB * SM_LDB + 2 * SB * SM_LDD + SB + 16 * SM_LDT;
-constexpr int SM_SMEM_BYTES = SM_SMEM_DOUBLES * 8;  // 90 624 B: two CTAs per SM
+constexpr int SM_SMEM_DOUBLES = SB * SM_LDB + 3 * SB * SM_LDD + SB + 16 * SM_LDT;
+constexpr int SM_SMEM_BYTES = SM_SMEM_DOUBLES * 8;  // 100 864 B: two CTAs per SM
 
 __host__ __device__ inline int small_dim(int T) { return ((T + 2 + SB - 1) / SB) * SB; }
+
+// -DBE_SMALL_TIMING (tools/gpu_small_timing.sh builds a second library with it): per-phase clock64 totals of ONE CTA
+// (block BE_SMALL_TIMING_BLOCK), read back through be_debug_small_timing.  Thread 0 speaks for the diagonal-block
+// group, thread 128 for the product group.  slot = 16 * block step + 8 * group + phase.
+#ifdef BE_SMALL_TIMING
+#ifndef BE_SMALL_TIMING_BLOCK
+#define BE_SMALL_TIMING_BLOCK 1000
+#endif
+__device__ long long g_small_timing[2][16 * 16];
+__device__ __forceinline__ long long st_now() {
+    long long t;
+    asm volatile("mov.u64 %0, %%clock64;" : "=l"(t));
+    return t;
+}
+struct PhaseClock {
+    long long t;
+    int kern;
+    __device__ explicit PhaseClock(int kernel_id) : t(st_now()), kern(kernel_id) {}
+    __device__ void mark(int step, int phase) {
+        if (blockIdx.x != BE_SMALL_TIMING_BLOCK || (threadIdx.x != 0 && threadIdx.x != 64 /* first thread of the product group */)) return;
+        const long long now = st_now();
+        g_small_timing[kern][16 * step + 8 * (threadIdx.x != 0) + phase] += now - t;
+        t = now;
+    }
+};
+#define ST_MARK(clk, step, phase) (clk).mark(step, phase)
+#else
+struct PhaseClock {
+    __device__ explicit PhaseClock(int) {}
+};
+#define ST_MARK(clk, step, phase) ((void)0)
+#endif
 
 struct SmallSmem {
     double* B;    // [32][SM_LDB]  panel
     double* D;    // [32][SM_LDD]  diagonal block being factored
-    double* Inv;  // [32][SM_LDD]  its inverse (lower)
+    double* Inv;  // [2][32][SM_LDD] inverses (lower) of diagonal blocks k (half k & 1) and k - 1
     double* rd;   // [32]          1 / diag
     double* Tmp;  // [16][SM_LDT]  scratch of the inverse
     __device__ explicit SmallSmem(double* base)
-        : B(base), D(base + SB * SM_LDB), Inv(base + SB * SM_LDB + SB * SM_LDD), rd(base + SB * SM_LDB + 2 * SB * SM_LDD),
-          Tmp(base + SB * SM_LDB + 2 * SB * SM_LDD + SB) {}
+        : B(base), D(base + SB * SM_LDB), Inv(base + SB * SM_LDB + SB * SM_LDD), rd(base + SB * SM_LDB + 3 * SB * SM_LDD),
+          Tmp(base + SB * SM_LDB + 3 * SB * SM_LDD + SB) {}
 };
 
 // 16 rows x 32 columns of output per warp pass, in DMMA accumulator layout: thread (g = lane / 4, q = lane % 4) holds
@@ -105,38 +137,41 @@ __device__ __forceinline__ void sub_gemm(SubAcc& acc, const double* A, int lda, 
     const double* a0p = A + (size_t)g * lda + 2 * q;
     const double* a1p = a0p + (size_t)8 * lda;
     const double* bp = sB + g * SM_LDB + 2 * q - kB0;
-    // two k-groups of A in flight ahead of the one being multiplied
-    double2 a0 = *reinterpret_cast<const double2*>(a0p + k0);
-    double2 a1 = *reinterpret_cast<const double2*>(a1p + k0);
-    double2 n0 = a0, n1 = a1;
-    if (k0 + 8 < k1) {
-        n0 = *reinterpret_cast<const double2*>(a0p + k0 + 8);
-        n1 = *reinterpret_cast<const double2*>(a1p + k0 + 8);
+    // A fragments run PF k-groups ahead of the DMMAs that consume them (L2 latency is ~800 cycles, a k-group is 16
+    // DMMAs = 256 cycles of this sub-partition's FP64 pipe: two groups ahead left the pipe waiting, ncu r02e)
+    constexpr int PF = 4;
+    double2 ra[PF][2];
+#pragma unroll
+    for (int p = 0; p < PF; ++p) {
+        const int kk = min(k0 + 8 * p, k1 - 8);  // past the end: a harmless reload of the last group
+        ra[p][0] = *reinterpret_cast<const double2*>(a0p + kk);
+        ra[p][1] = *reinterpret_cast<const double2*>(a1p + kk);
     }
-#pragma unroll 2
-    for (int k = k0; k < k1; k += 8) {
-        double2 m0 = n0, m1 = n1;
-        if (k + 16 < k1) {
-            m0 = *reinterpret_cast<const double2*>(a0p + k + 16);
-            m1 = *reinterpret_cast<const double2*>(a1p + k + 16);
-        }
-        double2 b[4];
+#pragma unroll 1
+    for (int k = k0; k < k1; k += 8 * PF) {
 #pragma unroll
-        for (int ni = 0; ni < 4; ++ni) b[ni] = *reinterpret_cast<const double2*>(bp + ni * 8 * SM_LDB + k);
+        for (int p = 0; p < PF; ++p) {
+            const int kc = k + 8 * p;
+            if (kc < k1) {  // warp-uniform
+                const double2 a0 = ra[p][0], a1 = ra[p][1];
+                const int kn = min(kc + 8 * PF, k1 - 8);
+                ra[p][0] = *reinterpret_cast<const double2*>(a0p + kn);
+                ra[p][1] = *reinterpret_cast<const double2*>(a1p + kn);
+                double2 b[4];
 #pragma unroll
-        for (int ni = 0; ni < 4; ++ni) {
-            dmma884(acc.v[0][ni][0], acc.v[0][ni][1], a0.x, b[ni].x);
-            dmma884(acc.v[1][ni][0], acc.v[1][ni][1], a1.x, b[ni].x);
-        }
+                for (int ni = 0; ni < 4; ++ni) b[ni] = *reinterpret_cast<const double2*>(bp + ni * 8 * SM_LDB + kc);
 #pragma unroll
-        for (int ni = 0; ni < 4; ++ni) {
-            dmma884(acc.v[0][ni][0], acc.v[0][ni][1], a0.y, b[ni].y);
-            dmma884(acc.v[1][ni][0], acc.v[1][ni][1], a1.y, b[ni].y);
+                for (int ni = 0; ni < 4; ++ni) {
+                    dmma884(acc.v[0][ni][0], acc.v[0][ni][1], a0.x, b[ni].x);
+                    dmma884(acc.v[1][ni][0], acc.v[1][ni][1], a1.x, b[ni].x);
+                }
+#pragma unroll
+                for (int ni = 0; ni < 4; ++ni) {
+                    dmma884(acc.v[0][ni][0], acc.v[0][ni][1], a0.y, b[ni].y);
+                    dmma884(acc.v[1][ni][0], acc.v[1][ni][1], a1.y, b[ni].y);
+                }
+            }
         }
-        a0 = n0;
-        a1 = n1;
-        n0 = m0;
-        n1 = m1;
     }
 }
 
@@ -165,11 +200,52 @@ __device__ __forceinline__ void sub_scale(SubAcc& out, const SubAcc& t, const do
         }
 }
 
-// 32 rows x klen columns (klen a multiple of 2) of a global row-major matrix -> the shared panel; the caller syncs
-__device__ __forceinline__ void load_panel(double* sB, const double* src, int ld, int klen) {
+// 1 / sqrt(x) with a SHORT dependent chain: MUFU seed (relative error < 2^-22) and one third-order (Halley) step,
+//   e = 1 - x y^2,  y <- y (1 + e / 2 + 3 e^2 / 8)      (error -> ~e^3 < 2^-65),
+// four dependent FP64 operations instead of the six of two Newton steps (fast_rsqrt, chol_diag.cuh).  The pivot
+// chain of the diagonal blocks is the serial spine of these kernels and every FP64 operation in it queues behind the
+// DMMAs of the other warps on the same pipe.  x <= 0 gives NaN / inf like a failed LAPACK pivot would.
+__device__ __forceinline__ double rsqrt_halley(double x) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    const double t = x * y;
+    const double e = fma(-t, y, 1.0);
+    const double p = fma(e, 0.375, 0.5);
+    const double ye = y * e;
+    return fma(ye, p, y);
+}
+
+// A thread group inside the CTA: the whole CTA (barrier 0) or one of the two warp groups of the look-ahead windows
+// (named barriers 1 and 2).  t / n = thread index in / size of the group, w / nw = warp index in / warps of it.
+struct Grp {
+    int t, n, w, nw, bar;
+    __device__ __forceinline__ void sync() const {
+        if (bar == 0)
+            __syncthreads();
+        else if (bar == 1)
+            asm volatile("bar.sync 1, %0;" ::"n"(64) : "memory");
+        else
+            asm volatile("bar.sync 2, %0;" ::"n"(192) : "memory");
+    }
+};
+__device__ __forceinline__ Grp grp_cta() { return Grp{(int)threadIdx.x, SM_THREADS, (int)threadIdx.x >> 5, SM_WARPS, 0}; }
+// warps 0-1: diagonal-block group (the serial pivot chain lives in warp 0; the group's other phases are small);
+// warps 2-7: product group.  (A 4 / 4 split left the product group the longer side of the late windows and the
+// diagonal group the longer side of the early ones: profiles/r02f_small_timing.txt.)
+constexpr int SM_DIAG_WARPS = 2;
+constexpr int SM_DIAG_THREADS = 32 * SM_DIAG_WARPS;
+__device__ __forceinline__ Grp grp_half() {
+    const int tid = threadIdx.x;
+    if (tid < SM_DIAG_THREADS) return Grp{tid, SM_DIAG_THREADS, tid >> 5, SM_DIAG_WARPS, 1};
+    return Grp{tid - SM_DIAG_THREADS, SM_THREADS - SM_DIAG_THREADS, (tid - SM_DIAG_THREADS) >> 5, SM_WARPS - SM_DIAG_WARPS, 2};
+}
+
+// 32 rows x klen columns (klen a multiple of 2) of a global row-major matrix -> the shared panel, by the threads of
+// group g; the caller synchronises the group
+__device__ __forceinline__ void load_panel(const Grp& g, double* sB, const double* src, int ld, int klen) {
     const int cpr = klen >> 1;  // 16-byte chunks per row
     const int total = SB * cpr;
-    for (int c = threadIdx.x; c < total; c += SM_THREADS) {
+    for (int c = g.t; c < total; c += g.n) {
         const int r = c / cpr, kc = c - r * cpr;
         cp_async16(sB + r * SM_LDB + 2 * kc, src + (size_t)r * ld + 2 * kc, true);
     }
@@ -177,31 +253,37 @@ __device__ __forceinline__ void load_panel(double* sB, const double* src, int ld
     cp_async_wait<0>();
 }
 
-// first sub-block (16 rows) >= lo that this warp owns: sub-blocks are dealt to the 8 warps round-robin, so that the
-// shrinking (potrf, lauum) or growing (trtri) set of active rows of a block step is spread over all warps
-__device__ __forceinline__ int first_owned(int lo, int warp) { return lo + ((warp - lo) & (SM_WARPS - 1)); }
+// first sub-block (16 rows) >= lo that warp w of nw owns: sub-blocks are dealt round-robin
+__device__ __forceinline__ int first_owned(int lo, int w, int nw) { return lo + (((w - lo) % nw + nw) % nw); }
 
-// Cholesky of the 32 x 32 block in sD (lower part, columns < nr real) by the whole CTA, in four 8-column steps:
-//   phase 1 (warp 0, lane = row): every lane factors the 8 x 8 pivot block REDUNDANTLY in its registers (no
-//            shuffles, no hand-off) and eliminates its own row with it -- the 8 dependent rsqrt of this chain
-//            (~100 cycles each, profiles/r02c ubench: rsqrt 75, dfma 8.4) are the irreducible serial part;
-//   phase 2 (all 256 threads): one trailing entry per thread, D[i, c] -= L[i, c0:c0+8] . L[c, c0:c0+8].
-// (The first version did phase 2 inside warp 0, one dependent chain per column: 15 k cycles per block, with seven
-// warps waiting at the barrier -- 38 % of the kernel, ncu r02c.)  Rows >= nr (padding / right-hand sides inside the
-// band) are eliminated like any row below the real block; columns >= nr are never touched.  sRd receives 1 / diag
-// (1 for the padding columns).  Returns the LAPACK-style report (0 = fine), valid in warp 0.  Ends with a barrier.
-__device__ __forceinline__ int diag_factor32(double* sD, double* sRd, int nr, int base) {
-    const int tid = threadIdx.x, i = tid & 31, warp = tid >> 5;
+// item t of a "snake" deal of count items to nw warps (even rounds ascending, odd rounds descending): with costs that
+// fall linearly in the item index every warp's total is about the same.  Returns -1 past the end.
+__device__ __forceinline__ int snake_item(int t, int nw, int count) {
+    const int round = t / nw, pos = t - round * nw;
+    const int r = (round & 1) ? round * nw + (nw - 1 - pos) : t;
+    return r < count ? r : -1;
+}
+
+// Cholesky of the 32 x 32 block in sD (lower part, columns < nr real) by the threads of group g, in four 8-column steps:
+//   phase 1 (first warp of the group, lane = row): every lane factors the 8 x 8 pivot block REDUNDANTLY in its
+//            registers (no shuffles, no hand-off) and eliminates its own row with it -- the 8 dependent rsqrt of this
+//            chain (~100 cycles each, profiles/r02c ubench: rsqrt 75, dfma 8.4) are the irreducible serial part;
+//   phase 2 (all threads of the group): one trailing entry per thread, D[i, c] -= L[i, c0:c0+8] . L[c, c0:c0+8].
+// Rows >= nr (padding / right-hand sides inside the band) are eliminated like any row below the real block; columns
+// >= nr are never touched.  sRd receives 1 / diag (1 for the padding columns).  Returns the LAPACK-style report
+// (0 = fine), valid in the first warp of the group.  Ends with a group barrier.
+__device__ __forceinline__ int diag_factor32(const Grp& g, double* sD, double* sRd, int nr, int base) {
+    const int i = g.t & 31;
     int bad = 0;
 #pragma unroll 1
     for (int s = 0; s < 4; ++s) {
         const int c0 = 8 * s;
         const int w = min(8, nr - c0);
-        if (w <= 0) {  // CTA-uniform
-            if (tid < 8) sRd[c0 + tid] = 1.0;
+        if (w <= 0) {  // group-uniform
+            if (g.t < 8) sRd[c0 + g.t] = 1.0;
             continue;
         }
-        if (warp == 0) {
+        if (g.w == 0) {
             double Lb[8][8], pv[8], rs[8];
 #pragma unroll
             for (int a = 0; a < 8; ++a)
@@ -221,7 +303,7 @@ __device__ __forceinline__ int diag_factor32(double* sD, double* sRd, int nr, in
             for (int j = 0; j < 8; ++j) {
                 const double piv = Lb[j][j];
                 bad = (bad == 0 && j < w && !(piv > 0.0)) ? base + c0 + j + 1 : bad;
-                const double r = fast_rsqrt(piv);
+                const double r = rsqrt_halley(piv);
                 rs[j] = r;
 #pragma unroll
                 for (int a = j + 1; a < 8; ++a) Lb[a][j] *= r;
@@ -247,10 +329,10 @@ __device__ __forceinline__ int diag_factor32(double* sD, double* sRd, int nr, in
                 for (int j = 0; j < 8; ++j) sRd[c0 + j] = rs[j];
             }
         }
-        __syncthreads();
+        g.sync();
         // trailing real columns [c0 + 8, nr): one entry (row, col <= row) per thread
         const int m = SB - c0 - 8;
-        for (int e = tid; e < m * m; e += SM_THREADS) {
+        for (int e = g.t; e < m * m; e += g.n) {
             const int ii = e / m, cc = e - ii * m;
             const int r = c0 + 8 + ii, c = c0 + 8 + cc;
             if (c > r || c >= nr) continue;
@@ -268,30 +350,45 @@ __device__ __forceinline__ int diag_factor32(double* sD, double* sRd, int nr, in
             }
             sD[r * SM_LDD + c] = acc0 + acc1;
         }
-        __syncthreads();
+        g.sync();
     }
-    __syncthreads();
+    g.sync();
     return bad;
 }
 
-// sInv = inverse of blockdiag(L11, I) (L11 = the nr real rows / columns of the factored block in sD), by the whole
-// CTA: the four 8 x 8 diagonal blocks by forward substitution (one column per thread), then recursive doubling
+// OUT_p[s x s] = sign * X_p * Y_p for npairs pairs (row-major, "NN"), 8 x 8 output pieces dealt to the warps of g
+__device__ __forceinline__ void pair_product(const Grp& g, const double* X, int ldx, int xs, const double* Y, int ldy, int ys,
+                                             double* OUT, int ldo, int os, int s, int npairs, double sign) {
+    const int lane = g.t & 31, gq = lane >> 2, q = lane & 3;
+    const int fn = s / 8, per_pair = fn * fn;
+    for (int task = g.w; task < npairs * per_pair; task += g.nw) {
+        const int p = task / per_pair, rem = task - p * per_pair;
+        const int fr = rem / fn, fc = rem - fr * fn;
+        const double* A = X + (size_t)p * xs + fr * 8 * ldx;
+        const double* Bm = Y + (size_t)p * ys + fc * 8;
+        double acc[1][2] = {};
+        frag_nn<1>(A, ldx, Bm, ldy, s, acc);
+        *reinterpret_cast<double2*>(OUT + (size_t)p * os + (fr * 8 + gq) * ldo + fc * 8 + 2 * q) =
+            make_double2(sign * acc[0][0], sign * acc[0][1]);
+    }
+}
+
+// S = inverse of blockdiag(L11, I) (L11 = the nr real rows / columns of the factored block in sD), by the threads of
+// group g: the four 8 x 8 diagonal blocks by forward substitution (one column per thread), then recursive doubling
 //   inv([[A, 0], [B, C]]) = [[A^-1, 0], [-C^-1 B A^-1, C^-1]]
-// at block sizes 8 and 16, every product on the FP64 tensor pipe (level_product of chol_diag.cuh).  The first
-// version solved one column per lane in ONE warp: a 496-FMA dependent chain, 10 k cycles per block (ncu r02c).
-// Ends with a barrier.
-__device__ __forceinline__ void diag_inverse32(const double* sD, const double* sRd, double* S, double* sTmp, int nr) {
-    const int tid = threadIdx.x;
-    for (int e = tid; e < SB * SB; e += SM_THREADS) {
+// at block sizes 8 and 16, every product on the FP64 tensor pipe.  Ends with a group barrier.
+__device__ __forceinline__ void diag_inverse32(const Grp& g, const double* sD, const double* sRd, double* S, double* sTmp,
+                                               int nr) {
+    for (int e = g.t; e < SB * SB; e += g.n) {
         const int r = e >> 5, c = e & 31;
         S[r * SM_LDD + c] = c <= r ? (r < nr ? sD[r * SM_LDD + c] : (r == c ? 1.0 : 0.0)) : 0.0;
     }
-    __syncthreads();
+    g.sync();
     {
         double x[8];
-        const int blk = (tid >> 3) & 3, cidx = tid & 7;
+        const int blk = (g.t >> 3) & 3, cidx = g.t & 7;
         double* Lb = S + (blk * 8) * SM_LDD + blk * 8;
-        if (tid < 32) {
+        if (g.t < 32) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 double sacc = (i == cidx) ? 1.0 : 0.0;
@@ -300,66 +397,182 @@ __device__ __forceinline__ void diag_inverse32(const double* sD, const double* s
                 x[i] = (i >= cidx) ? sacc * sRd[blk * 8 + i] : 0.0;
             }
         }
-        __syncthreads();
-        if (tid < 32) {
+        g.sync();
+        if (g.t < 32) {
 #pragma unroll
             for (int i = 0; i < 8; ++i)
                 if (i >= cidx) Lb[i * SM_LDD + cidx] = x[i];
         }
-        __syncthreads();
+        g.sync();
     }
 #pragma unroll 1
     for (int s = 8; s <= 16; s *= 2) {
         const int npairs = 16 / s;
         const int stride = 2 * s * SM_LDD + 2 * s;  // from one pair's A to the next
         // T_p = B_p * Ainv_p -> Tmp (pair p at column offset p * s, rows 0 .. s)
-        level_product(S + s * SM_LDD, SM_LDD, stride, S, SM_LDD, stride, sTmp, SM_LDT, s, s, npairs, 1.0);
-        __syncthreads();
+        pair_product(g, S + s * SM_LDD, SM_LDD, stride, S, SM_LDD, stride, sTmp, SM_LDT, s, s, npairs, 1.0);
+        g.sync();
         // B_p = -Cinv_p * T_p
-        level_product(S + s * SM_LDD + s, SM_LDD, stride, sTmp, SM_LDT, s, S + s * SM_LDD, SM_LDD, stride, s, npairs, -1.0);
-        __syncthreads();
+        pair_product(g, S + s * SM_LDD + s, SM_LDD, stride, sTmp, SM_LDT, s, S + s * SM_LDD, SM_LDD, stride, s, npairs, -1.0);
+        g.sync();
     }
 }
 
-// In-place Cholesky of the lower triangle of the padded n x n matrix Mat (n = 32 nb), real dimension T, left-looking
-// in 32-column block steps.  If Vt != nullptr the diagonal tiles of Vt = C^-T (upper) and the inverted diagonal
-// blocks Dinv [nb][32][32] are written as well.  Ends with a barrier: every write is visible to the whole CTA.
-__device__ __forceinline__ void potrf_small(double* Mat, int ld, int nb, int T, double* Vt, double* Dinv, int* info_b,
-                                            const SmallSmem& sm) {
-    const int warp = threadIdx.x >> 5;
+// One column step of the triangular inverse by the warps of group g, V = C^-T (upper, row-major):
+//   V[j, i] = -(sum_{p=j}^{i-1} V[j, p] C[i, p]^T) Linv_i^T,  j < i   (the diagonal tile V[i, i] is already in place).
+// Loads the panel C[i, 0:32 i) into sm.B itself; sInv = Linv_i.  Begins and ends with a group barrier on sm.B.
+__device__ __forceinline__ void trtri_column(const Grp& g, double* Vt, const double* Cm, int ld, int i, const double* sInv,
+                                             const SmallSmem& sm) {
+    const int ic = SB * i;
+    load_panel(g, sm.B, Cm + (size_t)ic * ld, ld, ic);
+    g.sync();
+    // row sub-block r contracts K = 32 (i - r / 2) columns: snake deal, so that every warp's total K is about the same
+#pragma unroll 1
+    for (int t = g.w; t < 2 * i + g.nw; t += g.nw) {
+        const int r = snake_item(t, g.nw, 2 * i);
+        if (r < 0) continue;
+        SubAcc acc, x;
+        sub_zero(acc);
+        sub_gemm(acc, Vt + (size_t)16 * r * ld, ld, sm.B, 0, SB * (r >> 1), ic);
+        sub_scale(x, acc, sInv, -1.0);
+        sub_store(x, Vt + (size_t)16 * r * ld + ic, ld);
+    }
+    g.sync();
+}
+
+// Early part of the left-looking update of block column kn ("part A": the columns [0, kend) of the factor that are
+// final while the diagonal block kn - 1 is still being factored), by the warps of group g:
+//   Mat[r, kn] -= Mat[r, 0:kend) Mat[kn, 0:kend)^T   for every 16-row sub-block r of block rows >= kn, in place.
+__device__ __forceinline__ void update_early(const Grp& g, double* Mat, int ld, int nb, int kn, int kend, const SmallSmem& sm) {
+    load_panel(g, sm.B, Mat + (size_t)SB * kn * ld, ld, kend);
+    g.sync();
+#pragma unroll 1
+    for (int r = first_owned(2 * kn, g.w, g.nw); r < 2 * nb; r += g.nw) {
+        SubAcc acc, c;
+        sub_zero(acc);
+        sub_gemm(acc, Mat + (size_t)16 * r * ld, ld, sm.B, 0, 0, kend);
+        double* tile = Mat + (size_t)16 * r * ld + SB * kn;
+        sub_load(c, tile, ld);
+#pragma unroll
+        for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+            for (int ni = 0; ni < 4; ++ni) {
+                c.v[mi][ni][0] -= acc.v[mi][ni][0];
+                c.v[mi][ni][1] -= acc.v[mi][ni][1];
+            }
+        sub_store(c, tile, ld);
+    }
+}
+
+// One block column of lauum with the posterior epilogue (semantics of k_lauum_cov, be_kernels.cuh) by the warps of g:
+//   cov[i, j] = D + E - E (sum_{k >= 32 i} V[i, k] V[j, k]) E  for the sub-blocks of block rows i >= j; Work receives the
+// padded lower covariance, rows T / T+1 = (1, mu), identity padding.  Loads its panel V[j, 32 j : n) into sm.B.
+struct CovEpilogue {
+    const double* yv;   // y_var of this problem [T]
+    const double* mu;   // posterior mean [T]
+    double* var_diag;   // [T]
+    double* cov_dense;  // [T][T] or nullptr
+    double jitter;
+    int T;
+};
+__device__ __forceinline__ void lauum_column(const Grp& g, const double* Vb, double* Wb, int n, int nb, int j,
+                                             const CovEpilogue& ep, const SmallSmem& sm) {
+    const int lane = g.t & 31, gq = lane >> 2, q = lane & 3;
+    const int jc = SB * j, T = ep.T;
+    load_panel(g, sm.B, Vb + (size_t)jc * n + jc, n, n - jc);
+    g.sync();
+#pragma unroll 1
+    for (int t = g.w; t < 2 * (nb - j) + g.nw; t += g.nw) {
+        // sub-block 2 j + it contracts K = n - 32 (j + it / 2) columns: snake deal again
+        const int it = snake_item(t, g.nw, 2 * (nb - j));
+        if (it < 0) continue;
+        const int r = 2 * j + it;
+        SubAcc acc;
+        sub_zero(acc);
+        sub_gemm(acc, Vb + (size_t)16 * r * n, n, sm.B, jc, SB * (r >> 1), n);
+#pragma unroll
+        for (int mi = 0; mi < 2; ++mi) {
+            const int gr = 16 * r + 8 * mi + gq;
+            const double dr = gr < T ? ep.yv[gr] : 0.0;
+            const double er = dr + ep.jitter;
+#pragma unroll
+            for (int ni = 0; ni < 4; ++ni) {
+                double out[2];
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int gc = jc + 8 * ni + 2 * q + e;
+                    double val;
+                    if (gr < T && gc < T) {
+                        const double ec = ep.yv[gc] + ep.jitter;
+                        val = -er * ec * acc.v[mi][ni][e];
+                        if (gr == gc) {
+                            val += dr + er;
+                            ep.var_diag[gr] = val;
+                        }
+                        if (ep.cov_dense && gc <= gr) {
+                            ep.cov_dense[(size_t)gr * T + gc] = val;
+                            ep.cov_dense[(size_t)gc * T + gr] = val;
+                        }
+                    } else if (gr == T && gc < T) {
+                        val = 1.0;
+                    } else if (gr == T + 1 && gc < T) {
+                        val = ep.mu[gc];
+                    } else {
+                        val = gr == gc ? 1.0 : 0.0;
+                    }
+                    out[e] = val;
+                }
+                *reinterpret_cast<double2*>(Wb + (size_t)gr * n + jc + 8 * ni + 2 * q) = make_double2(out[0], out[1]);
+            }
+        }
+    }
+    g.sync();
+}
+
+// In-place Cholesky of the lower triangle of the padded n x n matrix Mat (n = 32 nb), real dimension T, left-looking in
+// 32-column block steps WITH LOOK-AHEAD.  The update of block column k + 1 is split in two: its early part (all
+// columns of the factor but the last 32) does not depend on the diagonal block k, so it runs -- on warps 4-7, one per
+// SM sub-partition -- in the same "window" in which warps 0-3 factor and invert diagonal block k (the serial spine:
+// 32 dependent rsqrt per block).  The window also takes independent work of the caller's (`extra`: the triangular
+// inverse's column k - 1 in kernel A, lauum's column k + 1 in kernel B).  After the window the whole CTA scales
+// column k by the inverse (panel TRSM recast as a product) and applies the late part (K = 32) of the update of column
+// k + 1, which leaves the next diagonal block in shared memory.  Three CTA barriers per step.
+// If Vt != nullptr the diagonal tiles of V = C^-T are written as well.
+// On return sm.Inv (ping-pong half (nb - 1) & 1) still holds the inverse of the last diagonal block.
+template <class Extra>
+__device__ __forceinline__ void potrf_small(double* Mat, int ld, int nb, int T, double* Vt, int* info_b, const SmallSmem& sm,
+                                            Extra extra, PhaseClock& clk) {
+    const Grp cta = grp_cta(), half = grp_half();
+    const bool diag_group = threadIdx.x < SM_DIAG_THREADS;
+    {   // diagonal block 0
+        SubAcc c;
+        if (cta.w < 2) {
+            sub_load(c, Mat + (size_t)16 * cta.w * ld, ld);
+            sub_store(c, sm.D + cta.w * 16 * SM_LDD, SM_LDD);
+        }
+    }
+    __syncthreads();
+    ST_MARK(clk, 15, 0);
 #pragma unroll 1
     for (int k = 0; k < nb; ++k) {
         const int kc = SB * k;
         const int nr = max(0, min(SB, T - kc));
-        if (k > 0) load_panel(sm.B, Mat + (size_t)kc * ld, ld, kc);
-        __syncthreads();
-        // column update of every 16-row sub-block at or below the diagonal block
-#pragma unroll 1
-        for (int r = first_owned(2 * k, warp); r < 2 * nb; r += SM_WARPS) {
-            SubAcc acc, c;
-            sub_zero(acc);
-            sub_gemm(acc, Mat + (size_t)16 * r * ld, ld, sm.B, 0, 0, kc);
-            sub_load(c, Mat + (size_t)16 * r * ld + kc, ld);
-#pragma unroll
-            for (int mi = 0; mi < 2; ++mi)
-#pragma unroll
-                for (int ni = 0; ni < 4; ++ni) {
-                    c.v[mi][ni][0] -= acc.v[mi][ni][0];
-                    c.v[mi][ni][1] -= acc.v[mi][ni][1];
-                }
-            if (r < 2 * k + 2)
-                sub_store(c, sm.D + (r - 2 * k) * 16 * SM_LDD, SM_LDD);
-            else
-                sub_store(c, Mat + (size_t)16 * r * ld + kc, ld);  // unscaled; scaled below once the inverse exists
-        }
-        __syncthreads();
-        {
-            const int bad = diag_factor32(sm.D, sm.rd, nr, kc);
+        double* sInv = sm.Inv + (k & 1) * SB * SM_LDD;
+        // ---- window: diagonal block k  ||  independent products
+        if (diag_group) {
+            const int bad = diag_factor32(half, sm.D, sm.rd, nr, kc);
             if (threadIdx.x == 0 && bad != 0 && info_b && *info_b == 0) *info_b = bad;
-            diag_inverse32(sm.D, sm.rd, sm.Inv, sm.Tmp, nr);
+            diag_inverse32(half, sm.D, sm.rd, sInv, sm.Tmp, nr);
+        } else {
+            extra(half, k);
+            ST_MARK(clk, k, 6);
+            if (k >= 1 && k + 1 < nb) update_early(half, Mat, ld, nb, k + 1, kc, sm);
         }
-        // the factor's diagonal block (lower, real columns only; strict upper part of the real rows cleaned), the
-        // inverse for the triangular-inverse stage and the diagonal tile of V = C^-T
+        ST_MARK(clk, k, 0);  // the group's own work in the window
+        __syncthreads();
+        ST_MARK(clk, k, 1);  // waiting for the other group
+        // ---- the factor's diagonal block (lower, real columns only; strict upper part of the real rows cleaned) and
+        // the diagonal tile of V = C^-T
         for (int e = threadIdx.x; e < SB * SB; e += SM_THREADS) {
             const int r = e >> 5, c = e & 31;
             double* dst = Mat + (size_t)(kc + r) * ld + kc + c;
@@ -367,74 +580,82 @@ __device__ __forceinline__ void potrf_small(double* Mat, int ld, int nb, int T, 
                 *dst = sm.D[r * SM_LDD + c];
             else if (r < nr && c > r)
                 *dst = 0.0;
-            if (Dinv) Dinv[(size_t)k * SB * SB + e] = c <= r ? sm.Inv[r * SM_LDD + c] : 0.0;
-            if (Vt) Vt[(size_t)(kc + r) * ld + kc + c] = r <= c ? sm.Inv[c * SM_LDD + r] : 0.0;
+            if (Vt) Vt[(size_t)(kc + r) * ld + kc + c] = r <= c ? sInv[c * SM_LDD + r] : 0.0;
         }
-        // panel below the diagonal block: L[r, k] = unscaled * Linv^T
+        // ---- panel below the diagonal block: L[r, k] = unscaled * Linv^T; the rows of block k + 1 also go to sm.B,
+        // where they are the B operand of the late update
 #pragma unroll 1
-        for (int r = first_owned(2 * k + 2, warp); r < 2 * nb; r += SM_WARPS) {
+        for (int r = first_owned(2 * k + 2, cta.w, cta.nw); r < 2 * nb; r += cta.nw) {
             SubAcc t, x;
             sub_load(t, Mat + (size_t)16 * r * ld + kc, ld);
-            sub_scale(x, t, sm.Inv, 1.0);
+            sub_scale(x, t, sInv, 1.0);
             sub_store(x, Mat + (size_t)16 * r * ld + kc, ld);
+            if (r < 2 * k + 4) sub_store(x, sm.B + (r - 2 * k - 2) * 16 * SM_LDB, SM_LDB);
         }
-        __syncthreads();  // the next step's panel is made of rows written here
-    }
-}
-
-// V = C^-T (upper, row-major) from the factor C (lower, in Cm) and the inverted diagonal blocks; the diagonal tiles
-// of V are already in place.  Column step i:  V[j, i] = -(sum_{p=j}^{i-1} V[j, p] C[i, p]^T) Dinv[i]^T,  j < i.
-__device__ __forceinline__ void trtri_small(double* Vt, const double* Cm, int ld, int nb, const double* Dinv,
-                                            const SmallSmem& sm) {
-    const int warp = threadIdx.x >> 5;
-#pragma unroll 1
-    for (int i = 1; i < nb; ++i) {
-        const int ic = SB * i;
-        // the inverted diagonal block rides in the same cp.async group as the panel
-        for (int c = threadIdx.x; c < SB * SB / 2; c += SM_THREADS)
-            cp_async16(sm.Inv + (c >> 4) * SM_LDD + 2 * (c & 15), Dinv + (size_t)i * SB * SB + 2 * c, true);
-        load_panel(sm.B, Cm + (size_t)ic * ld, ld, ic);
+        ST_MARK(clk, k, 2);  // diagonal tile + panel scale
         __syncthreads();
-        // row sub-block r contracts K = 32 (i - r / 2) columns: warps take r and (2 i - 1 - r) in turns ("snake"), so
-        // that every warp's total K is about the same
+        ST_MARK(clk, k, 3);
+        // ---- late part of the update of column k + 1 (K = the 32 columns just scaled)
+        if (k + 1 < nb) {
 #pragma unroll 1
-        for (int t = warp; t < 2 * i; t += SM_WARPS) {
-            const int r = t >= SM_WARPS ? 2 * i - 1 - (t - SM_WARPS) : t;  // at most two rounds (2 i <= 16)
-            SubAcc acc, x;
-            sub_zero(acc);
-            sub_gemm(acc, Vt + (size_t)16 * r * ld, ld, sm.B, 0, SB * (r >> 1), ic);
-            sub_scale(x, acc, sm.Inv, -1.0);
-            sub_store(x, Vt + (size_t)16 * r * ld + ic, ld);
+            for (int r = first_owned(2 * k + 2, cta.w, cta.nw); r < 2 * nb; r += cta.nw) {
+                SubAcc acc, c;
+                sub_zero(acc);
+                sub_gemm(acc, Mat + (size_t)16 * r * ld, ld, sm.B, kc, kc, kc + SB);  // A = the rows this warp just stored
+                double* tile = Mat + (size_t)16 * r * ld + kc + SB;
+                sub_load(c, tile, ld);
+#pragma unroll
+                for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+                    for (int ni = 0; ni < 4; ++ni) {
+                        c.v[mi][ni][0] -= acc.v[mi][ni][0];
+                        c.v[mi][ni][1] -= acc.v[mi][ni][1];
+                    }
+                if (r < 2 * k + 4)
+                    sub_store(c, sm.D + (r - 2 * k - 2) * 16 * SM_LDD, SM_LDD);
+                else
+                    sub_store(c, tile, ld);
+            }
         }
+        ST_MARK(clk, k, 4);  // late update
         __syncthreads();
+        ST_MARK(clk, k, 5);
     }
 }
 
 // ---- kernel A: M = C C^T, u = C^-1 y (row T), V = C^-T ------------------------------------------------------
 // Mat [B][n][n] holds the lower tiles of M = K + diag(y_var + jitter) with row T = y_mean (k_matern32<1>); on return
-// it holds C (row T zeroed), Vt holds C^-T, u [B][T] the forward-substituted right-hand side.
+// it holds C (row T zeroed), Vt holds C^-T, u [B][T] the forward-substituted right-hand side.  The triangular
+// inverse's column k - 1 runs in the window of diagonal block k; its last column after the loop.
 __global__ void __launch_bounds__(SM_THREADS, 2)
-    k_small_factor_inverse(double* Mat, double* Vt, double* Dinv, double* u, int* info, int n, int T) {
+    k_small_factor_inverse(double* Mat, double* Vt, double* u, int* info, int n, int T) {
     extern __shared__ __align__(16) double small_smem[];
     const SmallSmem sm(small_smem);
     const int b = blockIdx.x, nb = n / SB;
     double* Mb = Mat + (size_t)b * n * n;
     double* Vb = Vt + (size_t)b * n * n;
-    double* Db = Dinv + (size_t)b * nb * SB * SB;
-    potrf_small(Mb, n, nb, T, Vb, Db, info + b, sm);
+    // Row T (the right-hand side y, becoming u) must be zeroed before a column of the triangular inverse reads the block
+    // row it lives in: block tb = T / 32 -- the last block, or the one before it when T + 1 is a multiple of 32.
+    const int tb = T / SB;
+    PhaseClock clk(0);
+    potrf_small(Mb, n, nb, T, Vb, info + b, sm, [&](const Grp& g, int k) {
+        if (k >= 2 && k - 1 < tb) trtri_column(g, Vb, Mb, n, k - 1, sm.Inv + ((k - 1) & 1) * SB * SM_LDD, sm);
+    }, clk);
     for (int j = threadIdx.x; j < T; j += SM_THREADS) {
         double* p = Mb + (size_t)T * n + j;
         u[(size_t)b * T + j] = *p;
         *p = 0.0;  // the triangular inverse sees blockdiag(C, I)
     }
     __syncthreads();
-    trtri_small(Vb, Mb, n, nb, Db, sm);
+    ST_MARK(clk, 15, 1);
+    // the remaining columns (normally just the last one).  Only the inverses of the last two diagonal blocks are still
+    // in shared memory, which is all that can be asked for: tb >= nb - 2.
+    for (int i = max(1, tb); i < nb; ++i) trtri_column(grp_cta(), Vb, Mb, n, i, sm.Inv + (i & 1) * SB * SM_LDD, sm);
+    ST_MARK(clk, 15, 2);
 }
 
 // ---- kernel B: cov = D + E - E (V V^T) E, then scale_tri = chol(cov) with (1, mu) riding along ---------------------
-// Epilogue semantics are those of k_lauum_cov (be_kernels.cuh): Work (aliases the buffer that held C) receives the
-// padded lower covariance, rows T / T+1 = (1, mu), identity padding; var_diag and the optional dense symmetric
-// covariance are written on the way.
+// lauum's block column 0 is formed by the whole CTA, column k + 1 in the window of diagonal block k (it only reads V).
 __global__ void __launch_bounds__(SM_THREADS, 2)
     k_small_cov_factor(const double* Vt, double* Work, const double* __restrict__ y_var, double jitter,
                        const double* __restrict__ mu, double* __restrict__ var_diag, double* __restrict__ cov_dense,
@@ -442,61 +663,16 @@ __global__ void __launch_bounds__(SM_THREADS, 2)
     extern __shared__ __align__(16) double small_smem[];
     const SmallSmem sm(small_smem);
     const int b = blockIdx.x, nb = n / SB;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, q = lane & 3;
     const double* Vb = Vt + (size_t)b * n * n;
     double* Wb = Work + (size_t)b * n * n;
-    const double* yv = y_var + (size_t)b * T;
-    const double* mub = mu + (size_t)b * T;
-    double* cd = cov_dense ? cov_dense + (size_t)b * T * T : nullptr;
-#pragma unroll 1
-    for (int j = 0; j < nb; ++j) {
-        const int jc = SB * j;
-        load_panel(sm.B, Vb + (size_t)jc * n + jc, n, n - jc);
-        __syncthreads();
-#pragma unroll 1
-        for (int r = first_owned(2 * j, warp); r < 2 * nb; r += SM_WARPS) {
-            SubAcc acc;
-            sub_zero(acc);
-            sub_gemm(acc, Vb + (size_t)16 * r * n, n, sm.B, jc, SB * (r >> 1), n);
-#pragma unroll
-            for (int mi = 0; mi < 2; ++mi) {
-                const int gr = 16 * r + 8 * mi + g;
-                const double dr = gr < T ? yv[gr] : 0.0;
-                const double er = dr + jitter;
-#pragma unroll
-                for (int ni = 0; ni < 4; ++ni) {
-                    double out[2];
-#pragma unroll
-                    for (int e = 0; e < 2; ++e) {
-                        const int gc = jc + 8 * ni + 2 * q + e;
-                        double val;
-                        if (gr < T && gc < T) {
-                            const double ec = yv[gc] + jitter;
-                            val = -er * ec * acc.v[mi][ni][e];
-                            if (gr == gc) {
-                                val += dr + er;
-                                var_diag[(size_t)b * T + gr] = val;
-                            }
-                            if (cd && gc <= gr) {
-                                cd[(size_t)gr * T + gc] = val;
-                                cd[(size_t)gc * T + gr] = val;
-                            }
-                        } else if (gr == T && gc < T) {
-                            val = 1.0;
-                        } else if (gr == T + 1 && gc < T) {
-                            val = mub[gc];
-                        } else {
-                            val = gr == gc ? 1.0 : 0.0;
-                        }
-                        out[e] = val;
-                    }
-                    *reinterpret_cast<double2*>(Wb + (size_t)gr * n + jc + 8 * ni + 2 * q) = make_double2(out[0], out[1]);
-                }
-            }
-        }
-        __syncthreads();
-    }
-    potrf_small(Wb, n, nb, T, nullptr, nullptr, info + b, sm);
+    const CovEpilogue ep{y_var + (size_t)b * T, mu + (size_t)b * T, var_diag + (size_t)b * T,
+                         cov_dense ? cov_dense + (size_t)b * T * T : nullptr, jitter, T};
+    PhaseClock clk(1);
+    lauum_column(grp_cta(), Vb, Wb, n, nb, 0, ep, sm);
+    ST_MARK(clk, 15, 3);
+    potrf_small(Wb, n, nb, T, nullptr, info + b, sm, [&](const Grp& g, int k) {
+        if (k + 1 < nb) lauum_column(g, Vb, Wb, n, nb, k + 1, ep, sm);
+    }, clk);
 }
 
 }  // namespace be

@@ -43,6 +43,12 @@ constexpr int SM_LDB = SM_MAX_DIM + 8;  // B-panel row stride: == 8 (mod 16) dou
 constexpr int SM_LDD = SB + 8;          // diagonal-block tiles, same residue
 constexpr int SM_THREADS = 256;
 constexpr int SM_WARPS = SM_THREADS / 32;
+#ifndef BE_SMALL_DIAG_WARPS
+#define BE_SMALL_DIAG_WARPS 2
+#endif
+constexpr int SM_DIAG_WARPS = BE_SMALL_DIAG_WARPS;
+constexpr int SM_DIAG_THREADS = 32 * SM_DIAG_WARPS;
+constexpr int SM_PROD_THREADS = SM_THREADS - SM_DIAG_THREADS;
 constexpr int SM_LDT = 20;              // scratch tile of the recursive-doubling inverse (== 4 mod 16)
 constexpr int SM_SMEM_DOUBLES = SB * SM_LDB + 3 * SB * SM_LDD + SB + 16 * SM_LDT;
 constexpr int SM_SMEM_BYTES = SM_SMEM_DOUBLES * 8;  // 100 864 B: two CTAs per SM
@@ -67,7 +73,7 @@ struct PhaseClock {
     int kern;
     __device__ explicit PhaseClock(int kernel_id) : t(st_now()), kern(kernel_id) {}
     __device__ void mark(int step, int phase) {
-        if (blockIdx.x != BE_SMALL_TIMING_BLOCK || (threadIdx.x != 0 && threadIdx.x != 64 /* first thread of the product group */)) return;
+        if (blockIdx.x != BE_SMALL_TIMING_BLOCK || (threadIdx.x != 0 && threadIdx.x != 32 * BE_SMALL_DIAG_WARPS /* first thread of the product group */)) return;
         const long long now = st_now();
         g_small_timing[kern][16 * step + 8 * (threadIdx.x != 0) + phase] += now - t;
         t = now;
@@ -223,21 +229,23 @@ struct Grp {
         if (bar == 0)
             __syncthreads();
         else if (bar == 1)
-            asm volatile("bar.sync 1, %0;" ::"n"(64) : "memory");
+            asm volatile("bar.sync 1, %0;" ::"n"(SM_DIAG_THREADS) : "memory");
         else
-            asm volatile("bar.sync 2, %0;" ::"n"(192) : "memory");
+            asm volatile("bar.sync 2, %0;" ::"n"(SM_PROD_THREADS) : "memory");
     }
 };
 __device__ __forceinline__ Grp grp_cta() { return Grp{(int)threadIdx.x, SM_THREADS, (int)threadIdx.x >> 5, SM_WARPS, 0}; }
-// warps 0-1: diagonal-block group (the serial pivot chain lives in warp 0; the group's other phases are small);
-// warps 2-7: product group.  (A 4 / 4 split left the product group the longer side of the late windows and the
-// diagonal group the longer side of the early ones: profiles/r02f_small_timing.txt.)
-constexpr int SM_DIAG_WARPS = 2;
-constexpr int SM_DIAG_THREADS = 32 * SM_DIAG_WARPS;
+// Warp groups of the look-ahead windows: the diagonal-block group = the first SM_DIAG_WARPS warps (named barrier 1;
+// the serial pivot chain lives in warp 0, the group's other phases are small), the product group = the rest (named
+// barrier 2).  Measured at the cfg4 shape (profiles/r02*_bench_cfg4.json, per-phase tables r02f/g/h_small_timing.txt):
+// 2 / 6: 12.8 k cells/s, 3 / 5: 11.7 k, 4 / 4: 12.1 k (tools/gpu_small_split.sh); a split that keeps every DMMA off
+// warp 0's SM sub-partition (diagonal = warps 0, 1, 4: FP64 DMMA and DFMA share one pipe per sub-partition, and the
+// pivot chain queues behind the DMMAs) made the pivot chain 30 % faster and the products slower: 11.7 k.
+__device__ __forceinline__ bool in_diag_group() { return threadIdx.x < SM_DIAG_THREADS; }
 __device__ __forceinline__ Grp grp_half() {
     const int tid = threadIdx.x;
     if (tid < SM_DIAG_THREADS) return Grp{tid, SM_DIAG_THREADS, tid >> 5, SM_DIAG_WARPS, 1};
-    return Grp{tid - SM_DIAG_THREADS, SM_THREADS - SM_DIAG_THREADS, (tid - SM_DIAG_THREADS) >> 5, SM_WARPS - SM_DIAG_WARPS, 2};
+    return Grp{tid - SM_DIAG_THREADS, SM_PROD_THREADS, (tid - SM_DIAG_THREADS) >> 5, SM_WARPS - SM_DIAG_WARPS, 2};
 }
 
 // 32 rows x klen columns (klen a multiple of 2) of a global row-major matrix -> the shared panel, by the threads of
@@ -543,7 +551,7 @@ template <class Extra>
 __device__ __forceinline__ void potrf_small(double* Mat, int ld, int nb, int T, double* Vt, int* info_b, const SmallSmem& sm,
                                             Extra extra, PhaseClock& clk) {
     const Grp cta = grp_cta(), half = grp_half();
-    const bool diag_group = threadIdx.x < SM_DIAG_THREADS;
+    const bool diag_group = in_diag_group();
     {   // diagonal block 0
         SubAcc c;
         if (cta.w < 2) {

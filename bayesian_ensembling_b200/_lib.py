@@ -75,8 +75,6 @@ SIGNATURES = {
     "be_dtw_barycenter_averaging_subgradient": (_I, [_P, _P, _I, _I, _I, _I, _D, _D, _D, _P, _P, _P, _P, _P, _Z]),
     "be_perform_dba": (_I, [_P, _P, _I, _I, _I, _I, _P, _P, _P, _Z]),
     "be_dtw_squared": (_I, [_P, _P, _P, _I, _I, _P]),
-    "be_dgemm_nt_i8tc_workspace_bytes": (_Z, [_I, _I, _I]),
-    "be_dgemm_nt_i8tc": (_I, [_P, _P, _P, _I, _I, _I, _P, _P, _Z]),
     "be_barycentre_fullcov": (_I, [_P, _P, _P, _P, _I, _I, _I, _D, _D, _I, _D, _I, _P, _P, _P, _P, _P, _Z]),
 }
 

@@ -440,26 +440,6 @@ class Backend:
         _lib.check(self.ctx, rc, "be_barycentre_fullcov")
         return mu, S, list(iters), info
 
-    # ------------------------------------------------------------------ fp64-equivalent GEMM on the int8 tensor cores
-    def dgemm_nt_i8tc(self, A, B):
-        """A [M,K], B [N,K] (fp64) -> A @ B.T computed on the int8 tensor cores (Ozaki scheme, ~1e-16 of
-        sum|a||b|).  M % 128 == 0, N % 256 == 0, K % 32 == 0.  Not on the hot path yet."""
-        A = self._in(A)
-        B = self._in(B)
-        M, K = A.shape
-        N, K2 = B.shape
-        if K != K2:
-            raise ValueError(f"dgemm_nt_i8tc: inner dimensions differ ({K} vs {K2})")
-        nbytes = int(self.lib.be_dgemm_nt_i8tc_workspace_bytes(M, N, K))
-        if nbytes == 0:
-            raise ValueError(f"dgemm_nt_i8tc: unsupported shape M={M} N={N} K={K} (M % 128, N % 256, K % 32 must be 0)")
-        C = self._new(M, N)
-        ws = self._ws(nbytes)
-        self._sync_stream()
-        rc = self.lib.be_dgemm_nt_i8tc(self.ctx, _ptr(A), _ptr(B), M, N, K, _ptr(C), _ptr(ws), nbytes)
-        _lib.check(self.ctx, rc, "be_dgemm_nt_i8tc")
-        return C
-
     # ------------------------------------------------------------------ SURVEY 8f "next" row 1: DTW barycentre averaging
     def dtw_barycenter_averaging_subgradient(self, reals, max_iter=30, initial_step_size=0.05, final_step_size=0.005,
                                              tol=1e-5, init_barycenter=None, want_info=False):

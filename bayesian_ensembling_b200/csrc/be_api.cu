@@ -15,7 +15,6 @@
 #include "sqrtm_kernels.cuh"
 #include "weights_next_kernels.cuh"
 #include "dtw_kernels.cuh"
-#include "ozaki_gemm.cuh"
 
 using namespace be;
 

@@ -252,54 +252,4 @@ int be_perform_dba(be_ctx* ctx, const double* X, int B, int R, int T, int n_iter
     return BE_OK;
 }
 
-/* ---- fp64-equivalent GEMM on the int8 tensor cores (ozaki_gemm.cuh) ---- */
-size_t be_dgemm_nt_i8tc_workspace_bytes(int M, int N, int K) {
-    if (M <= 0 || N <= 0 || K <= 0 || M % oz::TM || N % oz::TN || K % 32) return 0;
-    return align_up((size_t)oz::S * M * K, 256) + align_up((size_t)oz::S * N * K, 256) + align_up((size_t)M * 4, 256) +
-           align_up((size_t)N * 4, 256) + align_up((size_t)M * N * 8, 256);
-}
-
-int be_dgemm_nt_i8tc(be_ctx* ctx, const double* A, const double* B, int M, int N, int K, double* C, void* workspace,
-                     size_t workspace_bytes) {
-    if (!ctx) return -1;
-    if (!A) return -2;
-    if (!B) return -3;
-    if (M <= 0 || M % oz::TM) return -4;
-    if (N <= 0 || N % oz::TN) return -5;
-    if (K <= 0 || K % 32) return -6;
-    if (!C) return -7;
-    if (!workspace || workspace_bytes < be_dgemm_nt_i8tc_workspace_bytes(M, N, K)) return BE_ERR_WORKSPACE;
-    Carver cv(workspace, workspace_bytes);
-    int8_t* As = cv.take<int8_t>((size_t)oz::S * M * K);
-    int8_t* Bs = cv.take<int8_t>((size_t)oz::S * N * K);
-    int* EA = cv.take<int>(M);
-    int* FB = cv.take<int>(N);
-    double* U = cv.take<double>((size_t)M * N);
-    if (!As || !Bs || !EA || !FB || !U) return BE_ERR_WORKSPACE;
-    const size_t smem = (size_t)oz::RING_BYTES + 1024;
-    static bool attr_done[64] = {};
-    const int slot = ctx->device >= 0 && ctx->device < 64 ? ctx->device : 0;
-    if (!attr_done[slot]) {
-        BE_CUDA(cudaFuncSetAttribute(oz::k_ozaki_dgemm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_done[slot] = true;
-    }
-    {
-        Prof p(ctx, F_COPY, 0.0, 16.0 * ((double)M + N) * K);
-        oz::k_row_exponents<<<(M + 7) / 8, 256, 0, ctx->stream>>>(A, M, K, EA);
-        BE_LAUNCHED();
-        oz::k_row_exponents<<<(N + 7) / 8, 256, 0, ctx->stream>>>(B, N, K, FB);
-        BE_LAUNCHED();
-        oz::k_slice_rows<<<grid1d((size_t)M * (K / 16), 128), 128, 0, ctx->stream>>>(A, M, K, oz::TM, EA, As);
-        BE_LAUNCHED();
-        oz::k_slice_rows<<<grid1d((size_t)N * (K / 16), 128), 128, 0, ctx->stream>>>(B, N, K, oz::TN, FB, Bs);
-        BE_LAUNCHED();
-    }
-    {
-        Prof p(ctx, F_GEMM, 2.0 * M * (double)N * K, 8.0 * ((double)M * K + (double)N * K + (double)M * N));
-        oz::k_ozaki_dgemm<<<(M / oz::TM) * (N / oz::TN), 192, smem, ctx->stream>>>(As, Bs, EA, FB, C, U, M, N, K);
-        BE_LAUNCHED();
-    }
-    return BE_OK;
-}
-
 }  // extern "C"

@@ -71,7 +71,11 @@ class _HostPrefetcher:
 
     def __init__(self, be: Backend, r_host: torch.Tensor, waves):
         self.be, self.r, self.waves = be, r_host, waves
-        self.stream = torch.cuda.Stream(device=be.device)
+        # one copy stream per backend, kept: a fresh stream per call would give every staging buffer its own
+        # allocator pool (a cudaMalloc per call)
+        if getattr(be, "_copy_stream", None) is None:
+            be._copy_stream = torch.cuda.Stream(device=be.device)
+        self.stream = be._copy_stream
         self.pending = {}
         self._issue(0)
 
@@ -79,18 +83,24 @@ class _HostPrefetcher:
         if wi >= len(self.waves) or wi in self.pending:
             return
         c0, c1 = self.waves[wi]
+        cur = torch.cuda.current_stream(self.be.device)
+        # the staging buffer comes from the compute stream's pool (reused from step to step); the copy stream waits
+        # for whatever the compute stream last did with that block, then fills it
+        buf = torch.empty((c1 - c0,) + tuple(self.r.shape[1:]), dtype=torch.float64, device=self.be.device)
+        free_ev = torch.cuda.Event()
+        free_ev.record(cur)
         with torch.cuda.stream(self.stream):
-            buf = self.r[c0:c1].to(self.be.device, non_blocking=True)
+            self.stream.wait_event(free_ev)
+            buf.copy_(self.r[c0:c1], non_blocking=True)
             ev = torch.cuda.Event()
             ev.record(self.stream)
+        buf.record_stream(self.stream)
         self.pending[wi] = (buf, ev)
 
     def get(self, wi):
         self._issue(wi)
         buf, ev = self.pending.pop(wi)
-        cur = torch.cuda.current_stream(self.be.device)
-        cur.wait_event(ev)
-        buf.record_stream(cur)
+        torch.cuda.current_stream(self.be.device).wait_event(ev)
         self._issue(wi + 1)  # the next wave's copy runs under this wave's kernels
         return buf
 

@@ -283,15 +283,6 @@ int be_perform_dba(be_ctx* ctx, const double* X, int B, int R, int T, int n_iter
                    int* medoid, void* workspace, size_t workspace_bytes);
 int be_dtw_squared(be_ctx* ctx, const double* A, const double* X, int P, int T, double* sqcost);
 
-/* ---- fp64-equivalent GEMM on the int8 tensor cores (no call site in the reference) ----
- * C [M,N] = A [M,K] B [N,K]^T, all fp64 row-major, computed with tcgen05.mma kind::i8 by the Ozaki scheme (8 signed
- * 7-bit slices per operand row under a shared exponent, 36 exact int8 products recombined in fp64): error
- * ~1e-16 of sum_k |a_ik b_jk|, i.e. that of a compensated fp64 product.  M % 128 == 0, N % 256 == 0, K % 32 == 0
- * (negative argument index otherwise).  A building block for the next round's factorisation kernels -- the
- * fit -> weight -> barycentre path does not call it yet. */
-size_t be_dgemm_nt_i8tc_workspace_bytes(int M, int N, int K);
-int be_dgemm_nt_i8tc(be_ctx* ctx, const double* A, const double* B, int M, int N, int K, double* C,
-                     void* workspace, size_t workspace_bytes);
 
 #ifdef __cplusplus
 }

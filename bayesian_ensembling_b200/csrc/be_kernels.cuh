@@ -154,6 +154,10 @@ __global__ void __launch_bounds__(256, BE_MATERN_CTAS) k_matern32(const double* 
         const double2 si2 = *reinterpret_cast<const double2*>(si + lr);
 #pragma unroll 1
         for (int c = 0; c < 4; ++c) {
+            // MODE 1 writes the LOWER triangle: in a diagonal tile the 32-column groups strictly right of the rows'
+            // own 32-block are never read (the factorisations load j <= i, the small-T kernels 32-blocks at or below
+            // the diagonal) -- 6 of the tile's 16 sub-blocks, a quarter of the whole gram at T = 251
+            if (MODE == 1 && ti == tj && c > (lr >> 5)) continue;
             const int lc = 2 * tx + 32 * c;  // local columns lc, lc + 1
             const int gj = tj * NB + lc;
             double acc[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
@@ -902,6 +906,64 @@ __global__ void __launch_bounds__(128, 8)
     }
 }
 
+// log by a 64-entry table: x = 2^e m, m in [1, 2); j = the top six mantissa bits, c_j = 1 + (j + 1/2) / 64 the centre of
+// m's interval; r = m * (1 / c_j) - 1 (one FMA, |r| <= 2^-7); log x = e ln2 - log(1 / c_j) + log1p(r) with a degree-7
+// polynomial (truncation < 2^-59).  The table holds the ROUNDED reciprocals and minus the logarithms of exactly those
+// doubles, so the split is exact up to the final roundings: absolute error ~1.5e-16 (1 + |log x|).  ~20 instructions
+// against the library's ~50; valid for positive NORMAL x (callers send everything else to the library).
+__constant__ double LOG_INV_C[64] = {
+    0x1.fc07f01fc07f0p-1, 0x1.f44659e4a4271p-1, 0x1.ecc07b301ecc0p-1, 0x1.e573ac901e574p-1,
+    0x1.de5d6e3f8868ap-1, 0x1.d77b654b82c34p-1, 0x1.d0cb58f6ec074p-1, 0x1.ca4b3055ee191p-1,
+    0x1.c3f8f01c3f8f0p-1, 0x1.bdd2b899406f7p-1, 0x1.b7d6c3dda338bp-1, 0x1.b2036406c80d9p-1,
+    0x1.ac5701ac5701bp-1, 0x1.a6d01a6d01a6dp-1, 0x1.a16d3f97a4b02p-1, 0x1.9c2d14ee4a102p-1,
+    0x1.970e4f80cb872p-1, 0x1.920fb49d0e229p-1, 0x1.8d3018d3018d3p-1, 0x1.886e5f0abb04ap-1,
+    0x1.83c977ab2beddp-1, 0x1.7f405fd017f40p-1, 0x1.7ad2208e0ecc3p-1, 0x1.767dce434a9b1p-1,
+    0x1.724287f46debcp-1, 0x1.6e1f76b4337c7p-1, 0x1.6a13cd1537290p-1, 0x1.661ec6a5122f9p-1,
+    0x1.623fa77016240p-1, 0x1.5e75bb8d015e7p-1, 0x1.5ac056b015ac0p-1, 0x1.571ed3c506b3ap-1,
+    0x1.5390948f40febp-1, 0x1.5015015015015p-1, 0x1.4cab88725af6ep-1, 0x1.49539e3b2d067p-1,
+    0x1.460cbc7f5cf9ap-1, 0x1.42d6625d51f87p-1, 0x1.3fb013fb013fbp-1, 0x1.3c995a47babe7p-1,
+    0x1.3991c2c187f63p-1, 0x1.3698df3de0748p-1, 0x1.33ae45b57bcb2p-1, 0x1.30d190130d190p-1,
+    0x1.2e025c04b8097p-1, 0x1.2b404ad012b40p-1, 0x1.288b01288b013p-1, 0x1.25e22708092f1p-1,
+    0x1.23456789abcdfp-1, 0x1.20b470c67c0d9p-1, 0x1.1e2ef3b3fb874p-1, 0x1.1bb4a4046ed29p-1,
+    0x1.19453808ca29cp-1, 0x1.16e0689427379p-1, 0x1.1485f0e0acd3bp-1, 0x1.12358e75d3033p-1,
+    0x1.0fef010fef011p-1, 0x1.0db20a88f4696p-1, 0x1.0b7e6ec259dc8p-1, 0x1.0953f39010954p-1,
+    0x1.073260a47f7c6p-1, 0x1.05197f7d73404p-1, 0x1.03091b51f5e1ap-1, 0x1.0101010101010p-1};
+__constant__ double LOG_NEG_LOG_INV_C[64] = {
+    0x1.fe02a6b106799p-8, 0x1.7b91b07d5b126p-6, 0x1.39e87b9febd68p-5, 0x1.b42dd711971b9p-5,
+    0x1.16536eea37ae3p-4, 0x1.51b073f06183cp-4, 0x1.8c345d6319b23p-4, 0x1.c5e548f5bc743p-4,
+    0x1.fec9131dbeabcp-4, 0x1.1b72ad52f67a2p-3, 0x1.371fc201e8f75p-3, 0x1.526e5e3a1b438p-3,
+    0x1.6d60fe719d21bp-3, 0x1.87fa06520c911p-3, 0x1.a23bc1fe2b561p-3, 0x1.bc286742d8cd4p-3,
+    0x1.d5c216b4fbb94p-3, 0x1.ef0adcbdc5935p-3, 0x1.0402594b4d041p-2, 0x1.1058bf9ae4ad4p-2,
+    0x1.1c898c16999fbp-2, 0x1.2895a13de86a4p-2, 0x1.347dd9a987d56p-2, 0x1.404308686a7e4p-2,
+    0x1.4be5f957778a1p-2, 0x1.5767717455a6cp-2, 0x1.62c82f2b9c796p-2, 0x1.6e08eaa2ba1e4p-2,
+    0x1.792a55fdd47a1p-2, 0x1.842d1da1e8b18p-2, 0x1.8f11e873662c8p-2, 0x1.99d958117e08ap-2,
+    0x1.a484090e5bb09p-2, 0x1.af1293247786bp-2, 0x1.b9858969310fdp-2, 0x1.c3dd7a7cdad4dp-2,
+    0x1.ce1af0b85f3ecp-2, 0x1.d83e7258a2f3ep-2, 0x1.e24881a7c6c26p-2, 0x1.ec399d2468cc1p-2,
+    0x1.f6123fa7028adp-2, 0x1.ffd2e0857f497p-2, 0x1.04bdf9da926d2p-1, 0x1.0986f4f573521p-1,
+    0x1.0e44985d1cc8cp-1, 0x1.12f719593efbdp-1, 0x1.179eabbd899a0p-1, 0x1.1c3b81f713c25p-1,
+    0x1.20cdcd192ab6ep-1, 0x1.2555bce98f7cap-1, 0x1.29d37fec2b08bp-1, 0x1.2e47436e40268p-1,
+    0x1.32b1339121d71p-1, 0x1.37117b54747b6p-1, 0x1.3b68449fffc23p-1, 0x1.3fb5b84d16f43p-1,
+    0x1.43f9fe2f9ce67p-1, 0x1.48353d1ea88dfp-1, 0x1.4c679afccee39p-1, 0x1.50913cc01686bp-1,
+    0x1.54b2467999498p-1, 0x1.58cadb5cd7989p-1, 0x1.5cdb1dc6c1765p-1, 0x1.60e32f44788d9p-1};
+
+// sm_log: [0, 64) = LOG_INV_C, [64, 128) = LOG_NEG_LOG_INV_C (shared memory: any index pattern, no serialisation)
+__device__ __forceinline__ double log_tab64(double x, const double* __restrict__ sm_log) {
+    const int hi = __double2hiint(x), lo = __double2loint(x);
+    const int e = (hi >> 20) - 1023;
+    const int j = (hi >> 14) & 63;
+    const double m = __hiloint2double((hi & 0x000FFFFF) | 0x3FF00000, lo);
+    const double r = fma(m, sm_log[j], -1.0);
+    double q = fma(r, 0x1.2492492492492p-3, -0x1.5555555555555p-3);  // 1/7, -1/6
+    q = fma(q, r, 0x1.999999999999ap-3);                              // 1/5
+    q = fma(q, r, -0.25);
+    q = fma(q, r, 0x1.5555555555555p-2);                              // 1/3
+    q = fma(q, r, -0.5);
+    const double l1p = fma(r * r, q, r);
+    const double ed = (double)e;
+    double lg = fma(ed, 1.90821492927058770002e-10, l1p) + sm_log[64 + j];
+    return fma(ed, 6.93147180369123816490e-01, lg);  // ln2 split as in exp_core: e * hi is exact
+}
+
 __global__ void k_normal_logprob(const double* __restrict__ loc, const double* __restrict__ scale,
                                  const double* __restrict__ x, size_t n, double* __restrict__ ll) {
     size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -923,7 +985,9 @@ __global__ void k_loglik_weights_normal(const double* __restrict__ loc, const do
                                         double* __restrict__ lls_mean, int smem_ok) {
     extern __shared__ double wstage[];
     __shared__ double tab[16];
+    __shared__ double ltab[128];
     if (threadIdx.x < 16) tab[threadIdx.x] = EXP2_16TH[threadIdx.x];
+    for (int e = threadIdx.x; e < 128; e += blockDim.x) ltab[e] = e < 64 ? LOG_INV_C[e] : LOG_NEG_LOG_INV_C[e - 64];
     __syncthreads();
     size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (gid >= (size_t)C * N) return;
@@ -941,15 +1005,18 @@ __global__ void k_loglik_weights_normal(const double* __restrict__ loc, const do
     }
     var_o /= Ro;
     mean_d /= Ro;
+    const double two_mean_d = 2.0 * mean_d;
     double total = 0.0;
-    for (int m = 0; m < M; ++m) {
-        size_t o = ((size_t)c * M + m) * N + i;
-        double l = loc[o], sc = scale[o];
-        double lsc = log(sc);
+    const size_t o0 = (size_t)c * M * N + i;
+    // the general member: library log / exp, the per-realisation form for scales that are not ordinary numbers
+    auto slow_member = [&](int m) {
+        const size_t o = o0 + (size_t)m * N;
+        const double l = loc[o], sc = scale[o];
+        const double lsc = log(sc);
         double mean;
         if (sc > 0x1p-500 && sc < 0x1p500) {
             const double dl = mean_o - l;  // (o_r - loc) = d_r + dl exactly, for any pivot
-            mean = (-0.5 * (fma(dl, 2.0 * mean_d + dl, var_o) / (sc * sc)) - 0.5 * LOG_2PI) - lsc;
+            mean = (-0.5 * (fma(dl, two_mean_d + dl, var_o) * __drcp_rn(sc * sc)) - 0.5 * LOG_2PI) - lsc;
         } else {
             double s = 0.0;
             for (int r = 0; r < Ro; ++r) {
@@ -965,8 +1032,51 @@ __global__ void k_loglik_weights_normal(const double* __restrict__ loc, const do
         if (lls_exp) lls_exp[o] = e;
         st[m] = e;
         if (e == e) total += e;  // xarray .sum('model') skips NaN (weights.py:122)
+    };
+    // members four at a time: the loads are issued together and the four log / reciprocal / exp chains are independent
+    // and branch-free (table log, rounded reciprocal, table exp) -- ~45 instead of ~130 instructions per member.
+    // A group with a scale or an exponent outside the tables' range goes through the general member one by one.
+    int m = 0;
+    for (; m + 4 <= M; m += 4) {
+        double l[4], sc[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            l[j] = loc[o0 + (size_t)(m + j) * N];
+            sc[j] = scale[o0 + (size_t)(m + j) * N];
+        }
+        bool ok = true;
+        double mean[4], x[4], e[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            ok = ok && sc[j] > 0x1p-500 && sc[j] < 0x1p500;
+            const double lsc = log_tab64(sc[j], ltab);
+            const double dl = mean_o - l[j];
+            mean[j] = (-0.5 * (fma(dl, two_mean_d + dl, var_o) * __drcp_rn(sc[j] * sc[j])) - 0.5 * LOG_2PI) - lsc;
+            x[j] = cst * mean[j];
+            e[j] = exp_tab16_core(x[j], tab);
+            ok = ok && exp_tab16_ok(x[j]);
+        }
+        if (ok) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const size_t o = o0 + (size_t)(m + j) * N;
+                if (lls_mean) lls_mean[o] = mean[j];
+                if (lls_exp) lls_exp[o] = e[j];
+                st[m + j] = e[j];
+                total += e[j];  // finite by construction (|x| < 700)
+            }
+        } else {
+            for (int j = 0; j < 4; ++j) slow_member(m + j);
+        }
     }
-    for (int m = 0; m < M; ++m) w[((size_t)c * M + m) * N + i] = st[m] / total;
+    for (; m < M; ++m) slow_member(m);
+    if (total > 0x1p-1000 && total < 0x1p1000) {  // ordinary normaliser: one reciprocal, M products (as the MVN kernel)
+        const double inv = 1.0 / total;
+#pragma unroll 4
+        for (int mm = 0; mm < M; ++mm) w[o0 + (size_t)mm * N] = st[mm] * inv;
+    } else {  // zero, subnormal, huge, infinite, NaN: the divisions, so that 0/0, x/inf and NaN come out as in the reference
+        for (int mm = 0; mm < M; ++mm) w[o0 + (size_t)mm * N] = st[mm] / total;
+    }
 }
 
 // member-sharded normalisation: w = lls_exp / total  (weights.py:122-123 after an all-reduce of the sum)

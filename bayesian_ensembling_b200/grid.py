@@ -107,7 +107,14 @@ class _HostPrefetcher:
 
 def wave_size(be: Backend, C: int, M: int, R: int, T: int, keep_posteriors: bool, budget_bytes: int | None = None):
     """Cells per wave so that workspace + outputs stay inside the memory budget (180 GB HBM3e
-    holds ~1400 T=1980 problems with both work matrices resident)."""
+    holds ~1400 T=1980 problems with both work matrices resident).  The driver's free-memory query costs
+    ~20 ms on a B200 with a large pool (measured: profiles/r02k_bench.json e2e vs value), so its answer is kept per
+    problem shape for the life of the process; a call that runs out of memory drops the cache and asks again."""
+    key = (C, M, R, T, keep_posteriors)
+    cache = be.__dict__.setdefault("_wave_cache", {})
+    if budget_bytes is None and key in cache:
+        return cache[key]
+    explicit = budget_bytes is not None
     if budget_bytes is None:
         free, _total = torch.cuda.mem_get_info(be.device)
         # memory torch's caching allocator holds but has not handed out is available to this call too (the
@@ -115,13 +122,32 @@ def wave_size(be: Backend, C: int, M: int, R: int, T: int, keep_posteriors: bool
         cached = torch.cuda.memory_reserved(be.device) - torch.cuda.memory_allocated(be.device)
         budget_bytes = int((free + max(cached, 0)) * 0.8)
     per_cell = be.posterior_workspace_bytes(M, T, R) + (2 * M * T * T * 8 if keep_posteriors else 0) + 64 * M * T
-    return max(1, min(C, budget_bytes // max(per_cell, 1)))
+    n = max(1, min(C, budget_bytes // max(per_cell, 1)))
+    if not explicit:
+        cache[key] = n
+    return n
 
 
-def fit_weight_barycentre(realisations, observations, variance, lengthscale, *, jitter=DEFAULT_JITTER,
-                          standardisation_constant=1.0, time_mean_weights=False, keep_posteriors=False,
-                          cells_per_wave=None, tolerance=1e-6, init_var=1.0, y_mean="mean",
-                          posterior="dense") -> CellBatchResult:
+def fit_weight_barycentre(realisations, observations, variance, lengthscale, *, cells_per_wave=None, **kwargs):
+    """See ``_fit_weight_barycentre``.  With ``cells_per_wave`` left to the library, a wave that runs out of device
+    memory (the cached wave size is from an earlier, roomier moment) is retried once with a fresh memory query."""
+    try:
+        return _fit_weight_barycentre(realisations, observations, variance, lengthscale, cells_per_wave=cells_per_wave,
+                                      **kwargs)
+    except torch.cuda.OutOfMemoryError:
+        if cells_per_wave is not None:
+            raise
+        be = Backend.get()
+        be.__dict__.pop("_wave_cache", None)
+        be._workspace = None
+        torch.cuda.empty_cache()
+        return _fit_weight_barycentre(realisations, observations, variance, lengthscale, cells_per_wave=None, **kwargs)
+
+
+def _fit_weight_barycentre(realisations, observations, variance, lengthscale, *, jitter=DEFAULT_JITTER,
+                           standardisation_constant=1.0, time_mean_weights=False, keep_posteriors=False,
+                           cells_per_wave=None, tolerance=1e-6, init_var=1.0, y_mean="mean",
+                           posterior="dense") -> CellBatchResult:
     """realisations [C,M,R,T], observations [C,Ro,T] (host arrays or device tensors);
     variance / lengthscale: scalar, [M] or [C,M] kernel hyper-parameters (fixed-theta posterior,
     the fixed point of models.py:208-215).  Order of operations follows

@@ -75,3 +75,59 @@ def test_emulated_sequence_within_one_ulp():
         rmax = max(rmax, abs(r))
     assert rmax <= math.log(2) / 32 * (1 + 1e-9)
     assert worst <= 2.0**-52, worst  # one ulp
+
+
+# ------------------------------------------------------------------------------------ log_tab64 (Normal-branch weights)
+def _log_constants():
+    src = open(SRC).read()
+    inv = [float.fromhex(h) for h in re.findall(HEX, re.search(r"LOG_INV_C\[64\]\s*=\s*\{(.*?)\};", src, re.S).group(1))]
+    nlg = [float.fromhex(h) for h in re.findall(HEX, re.search(r"LOG_NEG_LOG_INV_C\[64\]\s*=\s*\{(.*?)\};", src, re.S).group(1))]
+    body = src[src.index("double log_tab64"):src.index("__global__ void k_normal_logprob")]
+    coef = [float.fromhex(h) for h in re.findall(HEX, body)]  # 1/7, -1/6, 1/5, 1/3 (the others are literals)
+    return inv, nlg, coef
+
+
+def _log_tab64(x, inv, nlg):
+    bits = struct.unpack("<Q", struct.pack("<d", x))[0]
+    hi = bits >> 32
+    e = (hi >> 20) - 1023
+    j = (hi >> 14) & 63
+    m = struct.unpack("<d", struct.pack("<Q", (bits & 0x000FFFFFFFFFFFFF) | (0x3FF << 52)))[0]
+    r = _fma(m, inv[j], -1.0)
+    q = _fma(r, 1.0 / 7.0, -1.0 / 6.0)
+    for c in (0.2, -0.25, 1.0 / 3.0, -0.5):
+        q = _fma(q, r, c)
+    l1p = _fma(r * r, q, r)
+    lg = _fma(float(e), 1.90821492927058770002e-10, l1p) + nlg[j]
+    return _fma(float(e), 6.93147180369123816490e-01, lg), r
+
+
+def test_log_table_constants():
+    getcontext().prec = 60
+    inv, nlg, coef = _log_constants()
+    assert len(inv) == 64 and len(nlg) == 64
+    for j in range(64):
+        c = Decimal(1) + (Decimal(j) + Decimal(1) / 2) / 64
+        assert inv[j] == float(1 / c)
+        assert nlg[j] == float(-(Decimal(inv[j]).ln()))  # minus the log of the ROUNDED reciprocal
+    assert coef[:4] == [1.0 / 7.0, -1.0 / 6.0, 0.2, 1.0 / 3.0]
+    hi = 6.93147180369123816490e-01
+    assert struct.unpack("<Q", struct.pack("<d", hi))[0] & 0xFFFFF == 0  # e * hi is exact for |e| < 2^11
+    assert abs(Decimal(hi) + Decimal(1.90821492927058770002e-10) - Decimal(2).ln()) < Decimal(2) ** -84
+
+
+def test_emulated_log_sequence():
+    getcontext().prec = 50
+    inv, nlg, _ = _log_constants()
+    rng = random.Random(11)
+    xs = [math.ldexp(rng.uniform(1.0, 2.0), rng.randint(-500, 500)) for _ in range(1500)]
+    xs += [rng.uniform(0.5, 2.0) for _ in range(1500)]  # around 1, where log x is small
+    xs += [1.0, 1.0 + 2.0**-52, 2.0 - 2.0**-52, 1.0 + 1.0 / 64, 1.0 + 1.0 / 128, 0.3, 0.01, 1e-3, 37.5]
+    worst, rmax = 0.0, 0.0
+    for x in xs:
+        got, r = _log_tab64(x, inv, nlg)
+        want = Decimal(x).ln()
+        worst = max(worst, float(abs(Decimal(got) - want)) / (1.0 + abs(float(want))))
+        rmax = max(rmax, abs(r))
+    assert rmax <= 2.0**-7 * (1 + 1e-9)
+    assert worst <= 2.5e-16, worst  # absolute, relative to 1 + |log x|: what an exponent needs

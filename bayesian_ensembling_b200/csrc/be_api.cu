@@ -697,8 +697,9 @@ int be_gp_posterior(be_ctx* ctx, const double* X, const double* y_mean, const do
     {
         // lauum: T^3/3 flops; reads V (upper, T^2/2), writes the padded lower cov (+ dense cov if asked)
         Prof pr(ctx, F_LAUUM, dB * dT * dT * dT / 3.0, dB * dT * dT * (cov ? 2.0 : 1.0) * 8);
+        const int raster = getenv("BE_LAUUM_TILE_MAJOR") ? 0 : 1;  // A/B switch (tools/gpu_traffic.sh)
         k_lauum_cov<<<(unsigned)((size_t)ntl * 2 * B), GEMM_THREADS, GEMM_SMEM_BYTES, ctx->stream>>>(
-            Vw, ld, Tp, T, y_var, jitter, mu, Mw, var_diag, cov, B);
+            Vw, ld, Tp, T, y_var, jitter, mu, Mw, var_diag, cov, B, raster);
         BE_LAUNCHED();
     }
     // 6. scale_tri = chol(cov) (data.py:38-39); rows T/T+1 become a = L^-1 1, b = L^-1 mu

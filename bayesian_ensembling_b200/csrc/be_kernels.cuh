@@ -380,12 +380,29 @@ __global__ void __launch_bounds__(GEMM_THREADS, GEMM_CTAS_PER_SM)
 __global__ void __launch_bounds__(GEMM_THREADS, GEMM_CTAS_PER_SM)
     k_lauum_cov(const double* __restrict__ V, int ld, int Tp, int T, const double* __restrict__ y_var, double jitter,
                 const double* __restrict__ mu, double* __restrict__ Work, double* __restrict__ var_diag,
-                double* __restrict__ cov_dense, int B) {
+                double* __restrict__ cov_dense, int B, int row_major_raster) {
     extern __shared__ __align__(16) double2 smem2[];
     int tile, half, b;
-    cta_decode(B, tile, half, b);
     int ti, tj;
-    tri_decode(tile, ti, tj);
+    if (row_major_raster) {
+        // Block-row-major order: all (problem, tj, half) of block row ti side by side.  Every CTA of the group has the
+        // same K length (Tp - 128 ti, as in the tile-major order, so waves still drain together) and CONSECUTIVE CTAs
+        // are the 2 (ti + 1) half-tiles of ONE problem's block row: they read the same A operand (V rows ti) through
+        // L2 instead of each from DRAM (tile-major: 12.8x the algorithmic bytes, profiles/traffic.json r01).
+        const long long idx = blockIdx.x;
+        int t = (int)((sqrt(1.0 + 4.0 * (double)idx / (double)B) - 1.0) * 0.5);
+        while ((long long)B * (t + 1) * (t + 2) <= idx) ++t;
+        while ((long long)B * t * (t + 1) > idx) --t;
+        ti = t;
+        const int rem = (int)(idx - (long long)B * t * (t + 1));
+        b = rem / (2 * (ti + 1));
+        const int r2 = rem - b * 2 * (ti + 1);
+        tj = r2 >> 1;
+        half = r2 & 1;
+    } else {
+        cta_decode(B, tile, half, b);
+        tri_decode(tile, ti, tj);
+    }
     const double* Vb = V + (size_t)b * Tp * ld;
     const int a_rows = blk_rows(Tp, ti), b_rows = min(BN, blk_rows(Tp, tj) - half * BN);
     if (b_rows <= 0) return;

@@ -4,7 +4,7 @@
 tag=${1:-r01}
 out=gpurun_out
 # one step = 190 launches of these kernels (48 + 48 + 69 + 23 + 1 + 1); 3 warm-up steps are skipped
-CMD="python bench.py --steps 1 --warmup 3 --no-cpu-baseline --l2-iters 0 --hbm-points 0 --dba-iters 0 --factored-steps 0"
+CMD="python bench.py --steps 1 --warmup 3 --no-cpu-baseline --l2-iters 0 --hbm-points 0 --dba-iters 0 --factored-steps 0 --no-side-configs --no-reference-api"
 $CMD > $out/plain_traffic_$tag.log 2>&1 &&
 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none \
     -k 'regex:k_chol_update|k_trtri_accum|k_lauum_cov|k_panel_scale|k_diag_block|k_matern32' -s 570 -c 190 \

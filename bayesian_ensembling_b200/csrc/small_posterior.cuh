@@ -73,7 +73,7 @@ struct PhaseClock {
     int kern;
     __device__ explicit PhaseClock(int kernel_id) : t(st_now()), kern(kernel_id) {}
     __device__ void mark(int step, int phase) {
-        if (blockIdx.x != BE_SMALL_TIMING_BLOCK || (threadIdx.x != 0 && threadIdx.x != 32 * BE_SMALL_DIAG_WARPS /* first thread of the product group */)) return;
+        if (blockIdx.x != BE_SMALL_TIMING_BLOCK || (threadIdx.x != 0 && threadIdx.x != 32 * BE_SMALL_DIAG_WARPS /* a thread of the product group (either mapping) */)) return;
         const long long now = st_now();
         g_small_timing[kern][16 * step + 8 * (threadIdx.x != 0) + phase] += now - t;
         t = now;
@@ -241,12 +241,24 @@ __device__ __forceinline__ Grp grp_cta() { return Grp{(int)threadIdx.x, SM_THREA
 // 2 / 6: 12.8 k cells/s, 3 / 5: 11.7 k, 4 / 4: 12.1 k (tools/gpu_small_split.sh); a split that keeps every DMMA off
 // warp 0's SM sub-partition (diagonal = warps 0, 1, 4: FP64 DMMA and DFMA share one pipe per sub-partition, and the
 // pivot chain queues behind the DMMAs) made the pivot chain 30 % faster and the products slower: 11.7 k.
+#ifdef BE_SMALL_DIAG_ON_SUBPARTITION0
+// variant: diagonal group = warps 0 and 4 (both on SM sub-partition 0), product group = warps 1, 2, 3, 5, 6, 7: no
+// DMMA is issued on sub-partition 0 during the windows (both CTAs of an SM use the same mapping)
+__device__ __forceinline__ bool in_diag_group() { return (threadIdx.x & 127) < 32; }
+__device__ __forceinline__ Grp grp_half() {
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if ((w & 3) == 0) return Grp{(w >> 2) * 32 + lane, 64, w >> 2, 2, 1};
+    const int gw = w < 4 ? w - 1 : w - 2;  // 1, 2, 3, 5, 6, 7 -> 0 .. 5
+    return Grp{gw * 32 + lane, 192, gw, 6, 2};
+}
+#else
 __device__ __forceinline__ bool in_diag_group() { return threadIdx.x < SM_DIAG_THREADS; }
 __device__ __forceinline__ Grp grp_half() {
     const int tid = threadIdx.x;
     if (tid < SM_DIAG_THREADS) return Grp{tid, SM_DIAG_THREADS, tid >> 5, SM_DIAG_WARPS, 1};
     return Grp{tid - SM_DIAG_THREADS, SM_PROD_THREADS, (tid - SM_DIAG_THREADS) >> 5, SM_WARPS - SM_DIAG_WARPS, 2};
 }
+#endif
 
 // 32 rows x klen columns (klen a multiple of 2) of a global row-major matrix -> the shared panel, by the threads of
 // group g; the caller synchronises the group
@@ -280,7 +292,7 @@ __device__ __forceinline__ int snake_item(int t, int nw, int count) {
 // Rows >= nr (padding / right-hand sides inside the band) are eliminated like any row below the real block; columns
 // >= nr are never touched.  sRd receives 1 / diag (1 for the padding columns).  Returns the LAPACK-style report
 // (0 = fine), valid in the first warp of the group.  Ends with a group barrier.
-__device__ __forceinline__ int diag_factor32(const Grp& g, double* sD, double* sRd, int nr, int base) {
+__device__ __forceinline__ int diag_factor32(const Grp& g, double* sD, double* sRd, int nr, int base, PhaseClock& clk, int step) {
     const int i = g.t & 31;
     int bad = 0;
 #pragma unroll 1
@@ -337,28 +349,32 @@ __device__ __forceinline__ int diag_factor32(const Grp& g, double* sD, double* s
                 for (int j = 0; j < 8; ++j) sRd[c0 + j] = rs[j];
             }
         }
+        ST_MARK(clk, step, 7);  // timing build only: pivot chain + row elimination (thread 0)
         g.sync();
-        // trailing real columns [c0 + 8, nr): one entry (row, col <= row) per thread
-        const int m = SB - c0 - 8;
-        for (int e = g.t; e < m * m; e += g.n) {
-            const int ii = e / m, cc = e - ii * m;
-            const int r = c0 + 8 + ii, c = c0 + 8 + cc;
-            if (c > r || c >= nr) continue;
-            const double* lr = sD + r * SM_LDD + c0;
-            const double* lc = sD + c * SM_LDD + c0;
-            double acc0 = sD[r * SM_LDD + c], acc1 = 0.0;
-#pragma unroll
-            for (int j = 0; j < 8; j += 4) {
-                const double2 a0 = *reinterpret_cast<const double2*>(lr + j), a1 = *reinterpret_cast<const double2*>(lr + j + 2);
-                const double2 b0 = *reinterpret_cast<const double2*>(lc + j), b1 = *reinterpret_cast<const double2*>(lc + j + 2);
-                acc0 = fma(-a0.x, b0.x, acc0);
-                acc1 = fma(-a0.y, b0.y, acc1);
-                acc0 = fma(-a1.x, b1.x, acc0);
-                acc1 = fma(-a1.y, b1.y, acc1);
+        // trailing real columns [c0 + 8, nr): D[r, c] -= L[r, c0:c0+8] . L[c, c0:c0+8] for c <= r, one 8 x 8 tile per warp
+        // pass on DMMA (two k-steps).  (One entry per thread with plain FMAs took 2.8 k cycles per step under the
+        // other warps' DMMA traffic: profiles/r02p_small_timing.txt.)
+        {
+            const int lane = g.t & 31, gq = lane >> 2, q = lane & 3;
+            const int p0 = c0 + 8, nt = (SB - p0) / 8;  // tile rows below the pivot block
+            for (int task = g.w; task < nt * (nt + 1) / 2; task += g.nw) {
+                int tr = 0;
+                while ((tr + 1) * (tr + 2) / 2 <= task) ++tr;
+                const int tc = task - tr * (tr + 1) / 2;
+                const int r = p0 + 8 * tr + gq, cc = p0 + 8 * tc + 2 * q;
+                const double* Pr = sD + (p0 + 8 * tr + gq) * SM_LDD + c0;
+                const double* Pc = sD + (p0 + 8 * tc + gq) * SM_LDD + c0;
+                double2 cv = *reinterpret_cast<const double2*>(sD + r * SM_LDD + cc);
+                double acc0 = 0.0, acc1 = 0.0;
+                dmma884(acc0, acc1, Pr[q], Pc[q]);
+                dmma884(acc0, acc1, Pr[4 + q], Pc[4 + q]);
+                cv.x = (cc < nr && cc <= r) ? cv.x - acc0 : cv.x;
+                cv.y = (cc + 1 < nr && cc + 1 <= r) ? cv.y - acc1 : cv.y;
+                *reinterpret_cast<double2*>(sD + r * SM_LDD + cc) = cv;
             }
-            sD[r * SM_LDD + c] = acc0 + acc1;
         }
         g.sync();
+        ST_MARK(clk, step, 6);  // timing build only: barrier + trailing entries + barrier (thread 0)
     }
     g.sync();
     return bad;
@@ -568,7 +584,8 @@ __device__ __forceinline__ void potrf_small(double* Mat, int ld, int nb, int T, 
         double* sInv = sm.Inv + (k & 1) * SB * SM_LDD;
         // ---- window: diagonal block k  ||  independent products
         if (diag_group) {
-            const int bad = diag_factor32(half, sm.D, sm.rd, nr, kc);
+            const int bad = diag_factor32(half, sm.D, sm.rd, nr, kc, clk, k);
+            ST_MARK(clk, k, 6);
             if (threadIdx.x == 0 && bad != 0 && info_b && *info_b == 0) *info_b = bad;
             diag_inverse32(half, sm.D, sm.rd, sInv, sm.Tmp, nr);
         } else {

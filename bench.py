@@ -577,7 +577,7 @@ def measure_reference_api(be, cfg, reals, obs):
                     "holds it on the host"}
 
 
-SIDE_CONFIGS = {"cfg1": 64, "cfg3": 6, "cfg4": 256}  # cells per step per GPU of the short side runs
+SIDE_CONFIGS = {"cfg1": 512, "cfg3": 6, "cfg4": 256}  # cells per step per GPU of the short side runs
 
 
 def run_ours(args, cfg):

@@ -30,15 +30,15 @@ for _ in range(reps):
 torch.cuda.synchronize()
 be.lib.be_debug_small_timing(buf, 0)
 t = np.array(list(buf), dtype=np.float64).reshape(2, 16, 2, 8) / reps
-names = ["own work in window", "wait at S1", "diag tile + scale", "wait S2", "late update", "wait S3", "extra (trtri/lauum) part of window", "-"]
+names = ["window: D inverse / G update_early", "S1 (clock read may precede the wait)", "diag tile + scale (+ S1 wait)", "S2", "late update (+ S2 wait)", "S3", "D trailing+barriers / G extra", "D pivot chain"]
 for kern, kn in enumerate(["k_small_factor_inverse", "k_small_cov_factor"]):
     print(f"== {kn}: cycles per phase of one CTA (rows: block step k; 'D' = diagonal group thread 0, 'G' = product group thread 128)")
-    print("step | " + " | ".join(f"{n[:18]:>18s}" for n in names[:7]))
+    print("step | " + " | ".join(f"{n[:18]:>18s}" for n in names[:8]))
     tot = np.zeros((2, 8))
     for k in range(8):
         for g, gn in enumerate("DG"):
-            print(f"{k} {gn}  | " + " | ".join(f"{t[kern, k, g, p]:18.0f}" for p in range(7)))
+            print(f"{k} {gn}  | " + " | ".join(f"{t[kern, k, g, p]:18.0f}" for p in range(8)))
             tot[g] += t[kern, k, g]
     for g, gn in enumerate("DG"):
-        print(f"sum {gn}| " + " | ".join(f"{tot[g, p]:18.0f}" for p in range(7)), f"  total {tot[g, :6].sum():.0f}")
+        print(f"sum {gn}| " + " | ".join(f"{tot[g, p]:18.0f}" for p in range(8)), f"  total {tot[g].sum():.0f}")
     print("pre / post:", {i: float(t[kern, 15, 0, i]) for i in range(4)})

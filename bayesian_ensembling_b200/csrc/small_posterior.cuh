@@ -50,7 +50,7 @@ constexpr int SM_DIAG_WARPS = BE_SMALL_DIAG_WARPS;
 constexpr int SM_DIAG_THREADS = 32 * SM_DIAG_WARPS;
 constexpr int SM_PROD_THREADS = SM_THREADS - SM_DIAG_THREADS;
 constexpr int SM_LDT = 20;              // scratch tile of the recursive-doubling inverse (== 4 mod 16)
-constexpr int SM_SMEM_DOUBLES = SB * SM_LDB + 3 * SB * SM_LDD + SB + 16 * SM_LDT;
+constexpr int SM_SMEM_DOUBLES = SB * SM_LDB + 3 * SB * SM_LDD + SB + 16 * SM_LDT + 2;  // + two mbarriers
 constexpr int SM_SMEM_BYTES = SM_SMEM_DOUBLES * 8;  // 100 864 B: two CTAs per SM
 
 __host__ __device__ inline int small_dim(int T) { return ((T + 2 + SB - 1) / SB) * SB; }
@@ -93,10 +93,27 @@ struct SmallSmem {
     double* Inv;  // [2][32][SM_LDD] inverses (lower) of diagonal blocks k (half k & 1) and k - 1
     double* rd;   // [32]          1 / diag
     double* Tmp;  // [16][SM_LDT]  scratch of the inverse
+    unsigned long long* bars;  // [2] mbarriers of the panel loads: whole CTA, product group
     __device__ explicit SmallSmem(double* base)
         : B(base), D(base + SB * SM_LDB), Inv(base + SB * SM_LDB + SB * SM_LDD), rd(base + SB * SM_LDB + 3 * SB * SM_LDD),
-          Tmp(base + SB * SM_LDB + 3 * SB * SM_LDD + SB) {}
+          Tmp(base + SB * SM_LDB + 3 * SB * SM_LDD + SB),
+          bars(reinterpret_cast<unsigned long long*>(base + SB * SM_LDB + 3 * SB * SM_LDD + SB + 16 * SM_LDT)) {}
 };
+
+// Phase parities of the two panel mbarriers, kept per thread (every thread that waits on a barrier flips its copy).
+struct PanelPhase {
+    unsigned parity[2];
+};
+__device__ __forceinline__ unsigned smem_addr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void panel_bars_init(const SmallSmem& sm, PanelPhase& ph) {
+    ph.parity[0] = ph.parity[1] = 0;
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(sm.bars)));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(sm.bars + 1)));
+        asm volatile("fence.mbarrier_init.release.cluster;");
+    }
+    __syncthreads();
+}
 
 // 16 rows x 32 columns of output per warp pass, in DMMA accumulator layout: thread (g = lane / 4, q = lane % 4) holds
 // rows 8 mi + g, columns 8 ni + 2 q and 8 ni + 2 q + 1.
@@ -260,9 +277,16 @@ __device__ __forceinline__ Grp grp_half() {
 }
 #endif
 
-// 32 rows x klen columns (klen a multiple of 2) of a global row-major matrix -> the shared panel, by the threads of
-// group g; the caller synchronises the group
-__device__ __forceinline__ void load_panel(const Grp& g, double* sB, const double* src, int ld, int klen) {
+// 32 rows x klen columns (klen a multiple of 2) of a global row-major matrix -> the shared panel of group g, by TMA:
+// one bulk copy (cp.async.bulk, no tensor map needed: every panel row is one contiguous run of klen * 8 bytes) per row,
+// issued by the 32 lanes of the group's first warp and completed on the group's mbarrier, on which every thread of
+// the group then waits.  The rows being read were written by this CTA's own (generic-proxy) stores, and the panel
+// area itself is also written by ordinary stores between two loads: the issuing lanes order both against the async
+// proxy with fence.proxy.async after the group barrier that precedes every call.
+// (-DBE_SMALL_NO_TMA: the 16-byte cp.async loop of the first version, for A/B.)
+__device__ __forceinline__ void load_panel(const Grp& g, double* sB, const double* src, int ld, int klen, const SmallSmem& sm,
+                                           PanelPhase& ph) {
+#ifdef BE_SMALL_NO_TMA
     const int cpr = klen >> 1;  // 16-byte chunks per row
     const int total = SB * cpr;
     for (int c = g.t; c < total; c += g.n) {
@@ -271,6 +295,31 @@ __device__ __forceinline__ void load_panel(const Grp& g, double* sB, const doubl
     }
     cp_async_commit();
     cp_async_wait<0>();
+#else
+    const int which = g.bar == 0 ? 0 : 1;
+    const unsigned bar = smem_addr(sm.bars + which);
+    if (g.t < 32) {
+        const unsigned bytes = (unsigned)klen * 8u;
+        asm volatile("fence.proxy.async;" ::: "memory");
+        if (g.t == 0) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes * SB) : "memory");
+        __syncwarp();
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                         smem_addr(sB + g.t * SM_LDB)),
+                     "l"(src + (size_t)g.t * ld), "r"(bytes), "r"(bar)
+                     : "memory");
+    }
+    unsigned done = 0;
+    while (!done) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}\n"
+            : "=r"(done)
+            : "r"(bar), "r"(ph.parity[which])
+            : "memory");
+    }
+    ph.parity[which] ^= 1u;
+#endif
 }
 
 // first sub-block (16 rows) >= lo that warp w of nw owns: sub-blocks are dealt round-robin
@@ -446,9 +495,9 @@ __device__ __forceinline__ void diag_inverse32(const Grp& g, const double* sD, c
 //   V[j, i] = -(sum_{p=j}^{i-1} V[j, p] C[i, p]^T) Linv_i^T,  j < i   (the diagonal tile V[i, i] is already in place).
 // Loads the panel C[i, 0:32 i) into sm.B itself; sInv = Linv_i.  Begins and ends with a group barrier on sm.B.
 __device__ __forceinline__ void trtri_column(const Grp& g, double* Vt, const double* Cm, int ld, int i, const double* sInv,
-                                             const SmallSmem& sm) {
+                                             const SmallSmem& sm, PanelPhase& ph) {
     const int ic = SB * i;
-    load_panel(g, sm.B, Cm + (size_t)ic * ld, ld, ic);
+    load_panel(g, sm.B, Cm + (size_t)ic * ld, ld, ic, sm, ph);
     g.sync();
     // row sub-block r contracts K = 32 (i - r / 2) columns: snake deal, so that every warp's total K is about the same
 #pragma unroll 1
@@ -467,8 +516,9 @@ __device__ __forceinline__ void trtri_column(const Grp& g, double* Vt, const dou
 // Early part of the left-looking update of block column kn ("part A": the columns [0, kend) of the factor that are
 // final while the diagonal block kn - 1 is still being factored), by the warps of group g:
 //   Mat[r, kn] -= Mat[r, 0:kend) Mat[kn, 0:kend)^T   for every 16-row sub-block r of block rows >= kn, in place.
-__device__ __forceinline__ void update_early(const Grp& g, double* Mat, int ld, int nb, int kn, int kend, const SmallSmem& sm) {
-    load_panel(g, sm.B, Mat + (size_t)SB * kn * ld, ld, kend);
+__device__ __forceinline__ void update_early(const Grp& g, double* Mat, int ld, int nb, int kn, int kend, const SmallSmem& sm,
+                                             PanelPhase& ph) {
+    load_panel(g, sm.B, Mat + (size_t)SB * kn * ld, ld, kend, sm, ph);
     g.sync();
 #pragma unroll 1
     for (int r = first_owned(2 * kn, g.w, g.nw); r < 2 * nb; r += g.nw) {
@@ -500,10 +550,10 @@ struct CovEpilogue {
     int T;
 };
 __device__ __forceinline__ void lauum_column(const Grp& g, const double* Vb, double* Wb, int n, int nb, int j,
-                                             const CovEpilogue& ep, const SmallSmem& sm) {
+                                             const CovEpilogue& ep, const SmallSmem& sm, PanelPhase& ph) {
     const int lane = g.t & 31, gq = lane >> 2, q = lane & 3;
     const int jc = SB * j, T = ep.T;
-    load_panel(g, sm.B, Vb + (size_t)jc * n + jc, n, n - jc);
+    load_panel(g, sm.B, Vb + (size_t)jc * n + jc, n, n - jc, sm, ph);
     g.sync();
 #pragma unroll 1
     for (int t = g.w; t < 2 * (nb - j) + g.nw; t += g.nw) {
@@ -565,7 +615,7 @@ __device__ __forceinline__ void lauum_column(const Grp& g, const double* Vb, dou
 // On return sm.Inv (ping-pong half (nb - 1) & 1) still holds the inverse of the last diagonal block.
 template <class Extra>
 __device__ __forceinline__ void potrf_small(double* Mat, int ld, int nb, int T, double* Vt, int* info_b, const SmallSmem& sm,
-                                            Extra extra, PhaseClock& clk) {
+                                            Extra extra, PhaseClock& clk, PanelPhase& ph) {
     const Grp cta = grp_cta(), half = grp_half();
     const bool diag_group = in_diag_group();
     {   // diagonal block 0
@@ -591,7 +641,7 @@ __device__ __forceinline__ void potrf_small(double* Mat, int ld, int nb, int T, 
         } else {
             extra(half, k);
             ST_MARK(clk, k, 6);
-            if (k >= 1 && k + 1 < nb) update_early(half, Mat, ld, nb, k + 1, kc, sm);
+            if (k >= 1 && k + 1 < nb) update_early(half, Mat, ld, nb, k + 1, kc, sm, ph);
         }
         ST_MARK(clk, k, 0);  // the group's own work in the window
         __syncthreads();
@@ -663,9 +713,11 @@ __global__ void __launch_bounds__(SM_THREADS, 2)
     // row it lives in: block tb = T / 32 -- the last block, or the one before it when T + 1 is a multiple of 32.
     const int tb = T / SB;
     PhaseClock clk(0);
+    PanelPhase ph;
+    panel_bars_init(sm, ph);
     potrf_small(Mb, n, nb, T, Vb, info + b, sm, [&](const Grp& g, int k) {
-        if (k >= 2 && k - 1 < tb) trtri_column(g, Vb, Mb, n, k - 1, sm.Inv + ((k - 1) & 1) * SB * SM_LDD, sm);
-    }, clk);
+        if (k >= 2 && k - 1 < tb) trtri_column(g, Vb, Mb, n, k - 1, sm.Inv + ((k - 1) & 1) * SB * SM_LDD, sm, ph);
+    }, clk, ph);
     for (int j = threadIdx.x; j < T; j += SM_THREADS) {
         double* p = Mb + (size_t)T * n + j;
         u[(size_t)b * T + j] = *p;
@@ -675,7 +727,7 @@ __global__ void __launch_bounds__(SM_THREADS, 2)
     ST_MARK(clk, 15, 1);
     // the remaining columns (normally just the last one).  Only the inverses of the last two diagonal blocks are still
     // in shared memory, which is all that can be asked for: tb >= nb - 2.
-    for (int i = max(1, tb); i < nb; ++i) trtri_column(grp_cta(), Vb, Mb, n, i, sm.Inv + (i & 1) * SB * SM_LDD, sm);
+    for (int i = max(1, tb); i < nb; ++i) trtri_column(grp_cta(), Vb, Mb, n, i, sm.Inv + (i & 1) * SB * SM_LDD, sm, ph);
     ST_MARK(clk, 15, 2);
 }
 
@@ -693,11 +745,13 @@ __global__ void __launch_bounds__(SM_THREADS, 2)
     const CovEpilogue ep{y_var + (size_t)b * T, mu + (size_t)b * T, var_diag + (size_t)b * T,
                          cov_dense ? cov_dense + (size_t)b * T * T : nullptr, jitter, T};
     PhaseClock clk(1);
-    lauum_column(grp_cta(), Vb, Wb, n, nb, 0, ep, sm);
+    PanelPhase ph;
+    panel_bars_init(sm, ph);
+    lauum_column(grp_cta(), Vb, Wb, n, nb, 0, ep, sm, ph);
     ST_MARK(clk, 15, 3);
     potrf_small(Wb, n, nb, T, nullptr, info + b, sm, [&](const Grp& g, int k) {
-        if (k + 1 < nb) lauum_column(g, Vb, Wb, n, nb, k + 1, ep, sm);
-    }, clk);
+        if (k + 1 < nb) lauum_column(g, Vb, Wb, n, nb, k + 1, ep, sm, ph);
+    }, clk, ph);
 }
 
 }  // namespace be

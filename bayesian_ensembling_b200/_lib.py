@@ -75,6 +75,8 @@ SIGNATURES = {
     "be_dtw_barycenter_averaging_subgradient": (_I, [_P, _P, _I, _I, _I, _I, _D, _D, _D, _P, _P, _P, _P, _P, _Z]),
     "be_perform_dba": (_I, [_P, _P, _I, _I, _I, _I, _P, _P, _P, _Z]),
     "be_dtw_squared": (_I, [_P, _P, _P, _I, _I, _P]),
+    "be_svgp_fit_workspace_bytes": (_Z, [_I, _I, _I, _I, _I]),
+    "be_svgp_fit": (_I, [_P, _P, _P, _I, _I, _I, _I, _P, _I, _D, _D, _I, _D, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _Z]),
     "be_barycentre_fullcov": (_I, [_P, _P, _P, _P, _I, _I, _I, _D, _D, _I, _D, _I, _P, _P, _P, _P, _P, _Z]),
 }
 

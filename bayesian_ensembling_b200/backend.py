@@ -440,6 +440,41 @@ class Backend:
         _lib.check(self.ctx, rc, "be_barycentre_fullcov")
         return mu, S, list(iters), info
 
+    # ------------------------------------------------------------------ SURVEY 8f "next" row 4: the SVGP stage of GPDTW3D
+    def svgp_fit(self, X, Y, Z0, batch_idx, n_steps, gamma=0.5, lr=0.01, train_hypers=True, jitter=DEFAULT_JITTER,
+                 init_variance=1.0, init_lengthscale=1.0, predict_chunk=4096):
+        """X [N, 4+R], Y [N, 2], Z0 [M, 4+R], batch_idx [2*n_steps, batch] int64 -> dict(mu [N], var [N] (+ Y[:,1]),
+        Z, variances [4], lengthscales [4], q_mu [M], q_sqrt [M,M], info)   (ensembles/models.py:357-411)"""
+        X = self._in(X)
+        N, D = X.shape
+        Y = self._in(Y, (N, 2), "Y")
+        Z = self._in(Z0).clone()
+        M = Z.shape[0]
+        if Z.shape[1] != D:
+            raise ValueError(f"Z0: expected {D} columns, got {Z.shape[1]}")
+        idx = torch.as_tensor(batch_idx, dtype=torch.int64, device=self.device).contiguous()
+        if n_steps > 0 and (idx.ndim != 2 or idx.shape[0] < 2 * n_steps):
+            raise ValueError("batch_idx: need [2 * n_steps, minibatch_size] (one minibatch per half-step)")
+        batch = int(idx.shape[1]) if idx.ndim == 2 else 1
+        if n_steps > 0 and (int(idx.min()) < 0 or int(idx.max()) >= N):
+            raise ValueError("batch_idx: index out of range")
+        var = torch.full((4,), float(init_variance), dtype=torch.float64, device=self.device)
+        ls = torch.full((4,), float(init_lengthscale), dtype=torch.float64, device=self.device)
+        q_mu, q_sqrt = self._new(M), self._new(M, M)
+        mu, v = self._new(N), self._new(N)
+        info = self._new(1, dtype=torch.int32)
+        chunk = int(min(predict_chunk, N))
+        nbytes = int(self.lib.be_svgp_fit_workspace_bytes(N, D, M, batch, chunk))
+        if nbytes == 0:
+            raise ValueError(f"svgp_fit: unsupported shape (D = {D} must be 5 .. 36)")
+        ws = self._ws(nbytes)
+        self._sync_stream()
+        rc = self.lib.be_svgp_fit(self.ctx, _ptr(X), _ptr(Y), N, D, M, batch, _ptr(idx), int(n_steps), float(gamma), float(lr),
+                                  int(bool(train_hypers)), float(jitter), chunk, _ptr(Z), _ptr(var), _ptr(ls), _ptr(q_mu),
+                                  _ptr(q_sqrt), _ptr(mu), _ptr(v), _ptr(info), _ptr(ws), nbytes)
+        _lib.check(self.ctx, rc, "be_svgp_fit")
+        return dict(mu=mu, var=v, Z=Z, variances=var, lengthscales=ls, q_mu=q_mu, q_sqrt=q_sqrt, info=info)
+
     # ------------------------------------------------------------------ SURVEY 8f "next" row 1: DTW barycentre averaging
     def dtw_barycenter_averaging_subgradient(self, reals, max_iter=30, initial_step_size=0.05, final_step_size=0.005,
                                              tol=1e-5, init_barycenter=None, want_info=False):

@@ -15,6 +15,7 @@
 #include "sqrtm_kernels.cuh"
 #include "weights_next_kernels.cuh"
 #include "dtw_kernels.cuh"
+#include "svgp_kernels.cuh"
 
 using namespace be;
 
@@ -1195,3 +1196,4 @@ int be_vgp_fit(be_ctx* ctx, const double* X, const double* y_mean, const double*
 
 #include "be_w2_api.cuh"
 #include "be_dtw_api.cuh"
+#include "be_svgp_api.cuh"

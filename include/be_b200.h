@@ -283,6 +283,23 @@ int be_perform_dba(be_ctx* ctx, const double* X, int B, int R, int T, int n_iter
                    int* medoid, void* workspace, size_t workspace_bytes);
 int be_dtw_squared(be_ctx* ctx, const double* A, const double* X, int P, int T, double* sqcost);
 
+/* ---- f-4 (next row): the SVGP stage of GPDTW3D.fit, ensembles/models.py:357-411 --------------------------------
+ * X [N,D] = (x, y, z, t_cont, R realisation columns), D = 4 + R (models.py:270-319); Y [N,2] = (DTW mean, variance).
+ * Kernel = Matern32(active_dims=[3]) + Matern32([0,1]) + Matern32([2]) + Matern32([4..D)) (:358-364): variances /
+ * lengthscales [4] in that order (in: initial values, GPflow's are 1; out: trained).  Z [M,D]: inducing inputs (in:
+ * linspace(min X, max X, M), :370; out: trained -- they are trainable in GPflow).  SVGP(whiten=True, q_mu = 0,
+ * q_sqrt = I, num_data=None: the ELBO is not rescaled) with the heteroskedastic Gaussian likelihood (:142-149).
+ * Step s (n_steps = n_optim_nits * (N / minibatch_size), :393): NaturalGradient(gamma) on minibatch
+ * batch_idx[2s] (:390), then, if train_hypers, Adam(lr) on the kernel parameters and Z on minibatch batch_idx[2s+1]
+ * (:391; the loss closure draws a new batch per call).  batch_idx [2*n_steps, minibatch_size] int64 on the device: the
+ * reference shuffles unseeded, so the caller supplies the order (oracle/svgp.py:batch_indices documents one).
+ * Then predict_f(X, full_cov=False) in chunks of predict_chunk points (:408): mu [N], var [N] = fvar + Y[:,1] (:411).
+ * q_mu [M], q_sqrt [M,M] (lower) are returned for inspection.  info [1]: LAPACK-style report of chol(Kuu). */
+size_t be_svgp_fit_workspace_bytes(int N, int D, int M, int minibatch_size, int predict_chunk);
+int be_svgp_fit(be_ctx* ctx, const double* X, const double* Y, int N, int D, int M, int minibatch_size,
+                const long long* batch_idx, int n_steps, double gamma, double lr, int train_hypers, double jitter,
+                int predict_chunk, double* Z, double* variances, double* lengthscales, double* q_mu, double* q_sqrt,
+                double* mu, double* var, int* info, void* workspace, size_t workspace_bytes);
 
 #ifdef __cplusplus
 }

@@ -272,8 +272,6 @@ def test_gpdtw3d_dtw_to_xarray_and_prep_data(backend):
     assert np.array_equal(X[:, 4:], data[:, t_idx, la_idx, lo_idx].T)
     assert np.array_equal(Y[:, 0], mean_array.values[t_idx, la_idx, lo_idx])
     assert np.array_equal(Y[:, 1], var_array.values[t_idx, la_idx, lo_idx])
-    with pytest.raises(NotImplementedError, match="SVGP"):
-        g3.fit(pm)
     bad = es.ProcessModel(DataArray(data[:, :, 0, 0], ("realisation", "time")), "b")
     with pytest.raises(NotImplementedError, match="4 dimensions"):
         g3.fit(bad)

@@ -1,10 +1,11 @@
 """The SVGP stage of GPDTW3D.fit (ensembles/models.py:357-411) on the device (be_svgp_fit, through
 the C ABI) against the oracle (oracle/svgp.py) on the SAME seeded minibatch order.  Needs a B200: ``-m gpu``.
 
-Tolerance: the natural-gradient half alone reproduces the oracle to ~1e-10; with the Adam half the loop amplifies
-rounding differences through Adam's m / (sqrt(v) + eps) (first steps move every parameter by exactly lr whatever the
-gradient's size), so the bar on the trained parameters and the prediction is 1e-6 after 12 steps -- the same order
-the L2 loop of GPDTW1D is held to."""
+Tolerance: what limits agreement is the conditioning of Kuu, not the step count.  The reference places its inducing
+inputs on ONE line through input space (linspace(min X, max X, M), models.py:370), so neighbouring inducing points are
+nearly identical and cond(Kuu + 1e-6 I) is 4e4 at M = 24, 3e7 at M = 130 and 6e8 at M = 400 (the reference's own
+default): two correct fp64 Cholesky factorisations of such a matrix differ by ~cond x 1e-16.  Observed against the
+oracle: 1e-13 (M = 24), 4e-8 (M = 130), 9e-7 (M = 400).  Bars: 1e-9 / 1e-6 / 1e-5 by M."""
 import numpy as np
 import pytest
 
@@ -42,7 +43,7 @@ def test_svgp_fit_vs_oracle(backend, N, R, M, batch, n_steps, train):
     assert int(out["info"].item()) == 0
     mu_o, var_o, st = svgp.svgp_fit(X, Y, n_steps, n_inducing=M, minibatch_size=batch, seed=11, train_hypers=train,
                                     return_state=True)
-    tol = 1e-6 if train else 1e-9
+    tol = 1e-9 if M <= 24 else (1e-6 if M <= 130 else 1e-5)
     errs = dict(
         mu=rel_err(out["mu"].cpu().numpy(), mu_o), var=rel_err(out["var"].cpu().numpy(), var_o),
         q_mu=rel_err(out["q_mu"].cpu().numpy(), st["q_mu"]), q_sqrt=rel_err(out["q_sqrt"].cpu().numpy(), np.tril(st["q_sqrt"])),

@@ -577,6 +577,57 @@ def measure_reference_api(be, cfg, reals, obs):
                     "holds it on the host"}
 
 
+def measure_svgp(be, with_cpu, n_steps=10):
+    """the SVGP stage of GPDTW3D.fit (models.py:357-411) at the reference's own sizes -- 400 inducing
+    inputs, minibatches of 500, 10 realisation columns -- on N = 20 000 (t, lat, lon) points: ms per optimisation step
+    (natural-gradient half + Adam half) and the prediction over all points; the oracle (NumPy / SciPy, all host BLAS
+    threads) beside it."""
+    import torch
+
+    from bayesian_ensembling_b200.models import GPDTW3D
+
+    rng = np.random.default_rng(20240 + 357)
+    N, R, M, batch = 20000, 10, 400, 500
+    lat, lon, t = rng.uniform(-85, 85, N), rng.uniform(0, 360, N), rng.uniform(-1, 1, N)
+    X = np.column_stack([np.cos(np.radians(lat)) * np.cos(np.radians(lon)), np.cos(np.radians(lat)) * np.sin(np.radians(lon)),
+                         np.sin(np.radians(lat)), t, 0.4 * t[:, None] + 0.1 * rng.standard_normal((N, R))])
+    Y = np.column_stack([0.4 * t + 0.2 * np.sin(np.radians(lat)) + 0.05 * rng.standard_normal(N), rng.uniform(0.005, 0.03, N)])
+    Z0 = np.linspace(X.min(axis=0), X.max(axis=0), M)
+    idx = GPDTW3D.minibatch_order(N, batch, 2 * (n_steps + 1), 1)
+    Xd, Yd, Zd = (torch.as_tensor(a, device=be.device) for a in (X, Y, Z0))
+    be.svgp_fit(Xd, Yd, Zd, idx, 1)  # warm-up (workspace)
+    torch.cuda.synchronize()
+    times = []
+    for k in (1, 1 + n_steps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = be.svgp_fit(Xd, Yd, Zd, idx, k)
+        e1.record()
+        torch.cuda.synchronize()
+        times.append(e0.elapsed_time(e1))
+    ms_step = (times[1] - times[0]) / n_steps
+    res = {"points": N, "inducing": M, "minibatch": batch, "realisation_columns": R, "ms_per_step": ms_step,
+           "ms_predict_all_points_plus_one_step": times[0], "info": int(out["info"].item()),
+           "steps_per_sec": 1e3 / ms_step,
+           "note": "be_svgp_fit: natural-gradient step on one minibatch + Adam step (8 kernel parameters and the 400 x 14 "
+                   "inducing inputs) on the next; M x M factorisations on the blocked DMMA path, rectangular products on a "
+                   "plain FP64 GEMM: launch-bound at these sizes (~90 launches per step)"}
+    if with_cpu:
+        from oracle import svgp as osvgp  # the CPU leg: the oracle is what is timed here, never the product
+
+        _use_all_host_threads()
+        threads, _ = _blas_threads()
+        t0 = time.perf_counter()
+        osvgp.svgp_fit(X, Y, 0, n_inducing=M, minibatch_size=batch, seed=1)
+        t1 = time.perf_counter()
+        osvgp.svgp_fit(X, Y, 2, n_inducing=M, minibatch_size=batch, seed=1)
+        t2 = time.perf_counter()
+        cpu_step = max((t2 - t1) - (t1 - t0), 1e-9) / 2
+        res["cpu"] = {"ms_per_step": cpu_step * 1e3, "cores": threads, "kind": "port", "gpu_over_cpu": cpu_step * 1e3 / ms_step,
+                      "sample": "two steps of the oracle minus its prediction-only run"}
+    return res
+
+
 SIDE_CONFIGS = {"cfg1": 512, "cfg3": 6, "cfg4": 256}  # cells per step per GPU of the short side runs
 
 
@@ -789,6 +840,10 @@ def run_ours(args, cfg):
     if args.dba_iters > 0 and rank == 0:
         dba = measure_dba(be, r_dev, cfg, ms / args.steps, args.dba_iters, world == 1 and not args.no_cpu_baseline)
 
+    svgp_stage = None
+    if rank == 0 and not args.no_svgp:
+        svgp_stage = measure_svgp(be, world == 1 and not args.no_cpu_baseline)
+
     ref_api = None
     if rank == 0 and not args.no_reference_api:
         del r_dev, o_dev, res
@@ -840,6 +895,7 @@ def run_ours(args, cfg):
             "hbm_stages": hbm_stages,
             "factored_posterior": factored,
             "dtw_barycentre_averaging": dba,
+            "svgp_stage": svgp_stage,
             "cpu_baseline": cpu_baseline,
         }
         print(json.dumps(line), flush=True)
@@ -879,6 +935,7 @@ def main():
     ap.add_argument("--no-side-configs", action="store_true", help="skip the cfg1 / cfg3 / cfg4 short runs")
     ap.add_argument("--no-member-sharded", action="store_true", help="skip the member-sharded cell (N > 1)")
     ap.add_argument("--no-reference-api", action="store_true", help="skip the e2e_reference_api measurement")
+    ap.add_argument("--no-svgp", action="store_true", help="skip the svgp_stage measurement (GPDTW3D's SVGP step)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     from bayesian_ensembling_b200 import synthetic

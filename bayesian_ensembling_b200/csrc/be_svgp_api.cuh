@@ -80,6 +80,72 @@ int svgp_conditional_A(be_ctx* ctx, const SvgpBuffers& w, const double* Z, const
     return svgp_gemm<1, 0>(ctx, M, n, M, 1.0, w.Vu, Mp, w.Kuf, n, 0.0, w.A, n);
 }
 
+// One optimisation step (models.py:389-391): natural-gradient half on minibatch 2 * step, Adam half on 2 * step + 1.
+int svgp_iteration(be_ctx* ctx, const SvgpBuffers& w, const double* X, const double* Y, const long long* batch_idx, double* Z,
+                   double* variances, double* lengthscales, const SvgpKernelParams& kp, int D, int M, int n, double gamma,
+                   double lr, int train_hypers, double jitter, int* info) {
+    const int Mp = pad_dim(M);
+    int rc;
+    // ---- natural-gradient step on minibatch 2 * step (models.py:390)
+    k_svgp_gather<<<grid1d((size_t)n * D, 256), 256, 0, ctx->stream>>>(X, Y, batch_idx, w.step, 0, n, D, w.Xb, w.yb,
+                                                                     w.sb);
+    BE_LAUNCHED();
+    if ((rc = svgp_factor_kuu(ctx, w, Z, kp, M, jitter, info)) != BE_OK) return rc;
+    if ((rc = svgp_conditional_A(ctx, w, Z, kp, M, n)) != BE_OK) return rc;
+    k_svgp_scale_cols<<<grid1d((size_t)M * n, 256), 256, 0, ctx->stream>>>(w.A, w.sb, M, n, w.Aw);
+    BE_LAUNCHED();
+    k_gemv_n<<<grid1d((size_t)M * 32, 256), 256, 0, ctx->stream>>>(M, n, w.Aw, n, w.yb, w.n1s);  // nat1* = A D^-1 y
+    BE_LAUNCHED();
+    if ((rc = svgp_gemm<0, 1>(ctx, M, M, n, 1.0, w.Aw, n, w.A, n, 0.0, w.G, M)) != BE_OK) return rc;  // A D^-1 A^T
+    k_svgp_natgrad_update<<<grid1d((size_t)Mp * Mp, 256), 256, 0, ctx->stream>>>(w.P, w.G, w.n1, w.n1s, M, Mp, gamma, w.Wp);
+    BE_LAUNCHED();
+    // S = P^-1 = Vp Vp^T (Vp = chol(P)^-T), q_mu = S nat1, q_sqrt = chol(S)
+    BE_CUDA(cudaMemsetAsync(w.Vp, 0, sizeof(double) * (size_t)Mp * Mp, ctx->stream));
+    if ((rc = potrf_padded(ctx, w.Wp, Mp, M, 1, w.DinvB, w.Pbuf, w.Vp, w.info_tmp)) != BE_OK) return rc;
+    if ((rc = trtri_padded(ctx, w.Vp, w.Wp, Mp, M, 1, w.DinvB, w.Pbuf)) != BE_OK) return rc;
+    if ((rc = svgp_gemm<0, 1>(ctx, M, M, M, 1.0, w.Vp, Mp, w.Vp, Mp, 0.0, w.S, Mp)) != BE_OK) return rc;
+    k_gemv_n<<<grid1d((size_t)M * 32, 256), 256, 0, ctx->stream>>>(M, M, w.S, Mp, w.n1, w.qmu);
+    BE_LAUNCHED();
+    k_svgp_pad_copy<<<grid1d((size_t)Mp * Mp, 256), 256, 0, ctx->stream>>>(w.S, Mp, M, Mp, w.Sq);
+    BE_LAUNCHED();
+    if ((rc = potrf_padded(ctx, w.Sq, Mp, M, 1, w.DinvB, w.Pbuf, nullptr, w.info_tmp)) != BE_OK) return rc;
+    k_copy_out_tri<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(w.Sq, Mp, Mp, M, w.SqD, 1);
+    BE_LAUNCHED();
+    if (train_hypers) {
+    // ---- Adam step on minibatch 2 * step + 1 (models.py:391): same kernel parameters, so Lu / Vu stand
+    k_svgp_gather<<<grid1d((size_t)n * D, 256), 256, 0, ctx->stream>>>(X, Y, batch_idx, w.step, 1, n, D, w.Xb, w.yb,
+                                                                     w.sb);
+    BE_LAUNCHED();
+    if ((rc = svgp_conditional_A(ctx, w, Z, kp, M, n)) != BE_OK) return rc;
+    k_gemv_t<<<grid1d(n, 128), 128, 0, ctx->stream>>>(M, n, w.A, n, w.qmu, w.fmean);  // m = A^T q_mu
+    BE_LAUNCHED();
+    if ((rc = svgp_gemm<1, 0>(ctx, M, n, M, 1.0, w.SqD, M, w.A, n, 0.0, w.W, n)) != BE_OK) return rc;   // W = Sq^T A
+    if ((rc = svgp_gemm<0, 0>(ctx, M, n, M, 1.0, w.SqD, M, w.W, n, 0.0, w.SW, n)) != BE_OK) return rc;  // Sq W
+    k_svgp_point_grads<<<grid1d(n, 128), 128, 0, ctx->stream>>>(w.fmean, w.yb, w.sb, n, w.gm, w.gv);
+    BE_LAUNCHED();
+    k_svgp_abar<<<grid1d((size_t)M * n, 256), 256, 0, ctx->stream>>>(w.A, w.SW, w.qmu, w.gm, w.gv, M, n, w.Abar);
+    BE_LAUNCHED();
+    if ((rc = svgp_gemm<0, 0>(ctx, M, n, M, 1.0, w.Vu, Mp, w.Abar, n, 0.0, w.Kufbar, n)) != BE_OK) return rc;  // Lu^-T Abar
+    if ((rc = svgp_gemm<0, 1>(ctx, M, M, n, 1.0, w.Kufbar, n, w.A, n, 0.0, w.T1, M)) != BE_OK) return rc;      // Kuf_bar A^T
+    k_svgp_neg_tril<<<grid1d((size_t)M * M, 256), 256, 0, ctx->stream>>>(w.T1, M);                            // Lu_bar
+    BE_LAUNCHED();
+    if ((rc = svgp_gemm<1, 0>(ctx, M, M, M, 1.0, w.LuD, M, w.T1, M, 0.0, w.T2, M)) != BE_OK) return rc;  // Lu^T Lu_bar
+    k_svgp_phi<<<grid1d((size_t)M * M, 256), 256, 0, ctx->stream>>>(w.T2, M);
+    BE_LAUNCHED();
+    if ((rc = svgp_gemm<0, 0>(ctx, M, M, M, 1.0, w.Vu, Mp, w.T2, M, 0.0, w.T1, M)) != BE_OK) return rc;  // Lu^-T Phi
+    if ((rc = svgp_gemm<0, 1>(ctx, M, M, M, 1.0, w.T1, M, w.Vu, Mp, 0.0, w.G, M)) != BE_OK) return rc;   // ... Lu^-1
+    BE_CUDA(cudaMemsetAsync(w.g, 0, sizeof(double) * 8, ctx->stream));
+    k_svgp_param_grads<<<M, 128, 0, ctx->stream>>>(Z, w.Xb, w.Kufbar, w.G, w.gv, kp, M, n, w.g, w.gZ);
+    BE_LAUNCHED();
+    k_svgp_adam<<<grid1d(8 + (size_t)M * D, 128), 128, 0, ctx->stream>>>(w.g, w.gZ, M * D, lr, w.u, Z, w.am, w.av, w.step,
+                                                                       variances, lengthscales);
+    BE_LAUNCHED();
+    }
+    k_svgp_step_inc<<<1, 1, 0, ctx->stream>>>(w.step);
+    BE_LAUNCHED();
+    return BE_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -141,63 +207,47 @@ int be_svgp_fit(be_ctx* ctx, const double* X, const double* Y, int N, int D, int
     k_svgp_unconstrain<<<1, 32, 0, ctx->stream>>>(variances, lengthscales, w.u);
     BE_LAUNCHED();
 
-    for (int step = 0; step < n_steps; ++step) {
-        // ---- natural-gradient step on minibatch 2 * step (models.py:390)
-        k_svgp_gather<<<grid1d((size_t)n * D, 256), 256, 0, ctx->stream>>>(X, Y, batch_idx + (size_t)(2 * step) * n, n, D, w.Xb,
-                                                                         w.yb, w.sb);
-        BE_LAUNCHED();
-        if ((rc = svgp_factor_kuu(ctx, w, Z, kp, M, jitter, info)) != BE_OK) return rc;
-        if ((rc = svgp_conditional_A(ctx, w, Z, kp, M, n)) != BE_OK) return rc;
-        k_svgp_scale_cols<<<grid1d((size_t)M * n, 256), 256, 0, ctx->stream>>>(w.A, w.sb, M, n, w.Aw);
-        BE_LAUNCHED();
-        k_gemv_n<<<grid1d((size_t)M * 32, 256), 256, 0, ctx->stream>>>(M, n, w.Aw, n, w.yb, w.n1s);  // nat1* = A D^-1 y
-        BE_LAUNCHED();
-        if ((rc = svgp_gemm<0, 1>(ctx, M, M, n, 1.0, w.Aw, n, w.A, n, 0.0, w.G, M)) != BE_OK) return rc;  // A D^-1 A^T
-        k_svgp_natgrad_update<<<grid1d((size_t)Mp * Mp, 256), 256, 0, ctx->stream>>>(w.P, w.G, w.n1, w.n1s, M, Mp, gamma, w.Wp);
-        BE_LAUNCHED();
-        // S = P^-1 = Vp Vp^T (Vp = chol(P)^-T), q_mu = S nat1, q_sqrt = chol(S)
-        BE_CUDA(cudaMemsetAsync(w.Vp, 0, sizeof(double) * (size_t)Mp * Mp, ctx->stream));
-        if ((rc = potrf_padded(ctx, w.Wp, Mp, M, 1, w.DinvB, w.Pbuf, w.Vp, w.info_tmp)) != BE_OK) return rc;
-        if ((rc = trtri_padded(ctx, w.Vp, w.Wp, Mp, M, 1, w.DinvB, w.Pbuf)) != BE_OK) return rc;
-        if ((rc = svgp_gemm<0, 1>(ctx, M, M, M, 1.0, w.Vp, Mp, w.Vp, Mp, 0.0, w.S, Mp)) != BE_OK) return rc;
-        k_gemv_n<<<grid1d((size_t)M * 32, 256), 256, 0, ctx->stream>>>(M, M, w.S, Mp, w.n1, w.qmu);
-        BE_LAUNCHED();
-        k_svgp_pad_copy<<<grid1d((size_t)Mp * Mp, 256), 256, 0, ctx->stream>>>(w.S, Mp, M, Mp, w.Sq);
-        BE_LAUNCHED();
-        if ((rc = potrf_padded(ctx, w.Sq, Mp, M, 1, w.DinvB, w.Pbuf, nullptr, w.info_tmp)) != BE_OK) return rc;
-        k_copy_out_tri<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(w.Sq, Mp, Mp, M, w.SqD, 1);
-        BE_LAUNCHED();
-        if (!train_hypers) continue;
-        // ---- Adam step on minibatch 2 * step + 1 (models.py:391): same kernel parameters, so Lu / Vu stand
-        k_svgp_gather<<<grid1d((size_t)n * D, 256), 256, 0, ctx->stream>>>(X, Y, batch_idx + (size_t)(2 * step + 1) * n, n, D,
-                                                                         w.Xb, w.yb, w.sb);
-        BE_LAUNCHED();
-        if ((rc = svgp_conditional_A(ctx, w, Z, kp, M, n)) != BE_OK) return rc;
-        k_gemv_t<<<grid1d(n, 128), 128, 0, ctx->stream>>>(M, n, w.A, n, w.qmu, w.fmean);  // m = A^T q_mu
-        BE_LAUNCHED();
-        if ((rc = svgp_gemm<1, 0>(ctx, M, n, M, 1.0, w.SqD, M, w.A, n, 0.0, w.W, n)) != BE_OK) return rc;   // W = Sq^T A
-        if ((rc = svgp_gemm<0, 0>(ctx, M, n, M, 1.0, w.SqD, M, w.W, n, 0.0, w.SW, n)) != BE_OK) return rc;  // Sq W
-        k_svgp_point_grads<<<grid1d(n, 128), 128, 0, ctx->stream>>>(w.fmean, w.yb, w.sb, n, w.gm, w.gv);
-        BE_LAUNCHED();
-        k_svgp_abar<<<grid1d((size_t)M * n, 256), 256, 0, ctx->stream>>>(w.A, w.SW, w.qmu, w.gm, w.gv, M, n, w.Abar);
-        BE_LAUNCHED();
-        if ((rc = svgp_gemm<0, 0>(ctx, M, n, M, 1.0, w.Vu, Mp, w.Abar, n, 0.0, w.Kufbar, n)) != BE_OK) return rc;  // Lu^-T Abar
-        if ((rc = svgp_gemm<0, 1>(ctx, M, M, n, 1.0, w.Kufbar, n, w.A, n, 0.0, w.T1, M)) != BE_OK) return rc;      // Kuf_bar A^T
-        k_svgp_neg_tril<<<grid1d((size_t)M * M, 256), 256, 0, ctx->stream>>>(w.T1, M);                            // Lu_bar
-        BE_LAUNCHED();
-        if ((rc = svgp_gemm<1, 0>(ctx, M, M, M, 1.0, w.LuD, M, w.T1, M, 0.0, w.T2, M)) != BE_OK) return rc;  // Lu^T Lu_bar
-        k_svgp_phi<<<grid1d((size_t)M * M, 256), 256, 0, ctx->stream>>>(w.T2, M);
-        BE_LAUNCHED();
-        if ((rc = svgp_gemm<0, 0>(ctx, M, M, M, 1.0, w.Vu, Mp, w.T2, M, 0.0, w.T1, M)) != BE_OK) return rc;  // Lu^-T Phi
-        if ((rc = svgp_gemm<0, 1>(ctx, M, M, M, 1.0, w.T1, M, w.Vu, Mp, 0.0, w.G, M)) != BE_OK) return rc;   // ... Lu^-1
-        BE_CUDA(cudaMemsetAsync(w.g, 0, sizeof(double) * 8, ctx->stream));
-        k_svgp_param_grads<<<M, 128, 0, ctx->stream>>>(Z, w.Xb, w.Kufbar, w.G, w.gv, kp, M, n, w.g, w.gZ);
-        BE_LAUNCHED();
-        k_svgp_adam<<<grid1d(8 + (size_t)M * D, 128), 128, 0, ctx->stream>>>(w.g, w.gZ, M * D, lr, w.u, Z, w.am, w.av, w.step,
-                                                                           variances, lengthscales);
-        BE_LAUNCHED();
-        k_svgp_step_inc<<<1, 1, 0, ctx->stream>>>(w.step);
-        BE_LAUNCHED();
+    // The training loop: one step (~90 small launches) is captured into a CUDA graph on a private stream and replayed
+    // n_steps times, as be_vgp_fit does; the minibatch offset comes from the device-side step counter.
+    if (n_steps > 0) {
+        cudaStream_t user_stream = ctx->stream, cap;
+        cudaEvent_t fork, join;
+        BE_CUDA(cudaStreamCreateWithFlags(&cap, cudaStreamNonBlocking));
+        BE_CUDA(cudaEventCreateWithFlags(&fork, cudaEventDisableTiming));
+        BE_CUDA(cudaEventCreateWithFlags(&join, cudaEventDisableTiming));
+        BE_CUDA(cudaEventRecord(fork, user_stream));
+        BE_CUDA(cudaStreamWaitEvent(cap, fork, 0));
+        const bool prof = ctx->profiling;
+        const long long launches0 = ctx->launches;
+        ctx->profiling = false;
+        ctx->stream = cap;
+        cudaGraph_t graph = nullptr;
+        cudaGraphExec_t exec = nullptr;
+        cudaError_t ce = cudaStreamBeginCapture(cap, cudaStreamCaptureModeThreadLocal);
+        rc = BE_OK;
+        if (ce == cudaSuccess) {
+            rc = svgp_iteration(ctx, w, X, Y, batch_idx, Z, variances, lengthscales, kp, D, M, n, gamma, lr, train_hypers, jitter,
+                                info);
+            ce = cudaStreamEndCapture(cap, &graph);
+        }
+        const long long per_iter = ctx->launches - launches0;
+        if (ce == cudaSuccess && rc == BE_OK) ce = cudaGraphInstantiate(&exec, graph, 0);
+        if (ce == cudaSuccess && rc == BE_OK) {
+            for (int it = 0; it < n_steps && ce == cudaSuccess; ++it) ce = cudaGraphLaunch(exec, cap);
+            ctx->launches = launches0 + per_iter * n_steps;
+        }
+        if (exec) cudaGraphExecDestroy(exec);
+        if (graph) cudaGraphDestroy(graph);
+        ctx->stream = user_stream;
+        ctx->profiling = prof;
+        cudaError_t ce2 = cudaEventRecord(join, cap);
+        if (ce2 == cudaSuccess) ce2 = cudaStreamWaitEvent(user_stream, join, 0);
+        cudaEventDestroy(fork);
+        cudaEventDestroy(join);
+        cudaStreamDestroy(cap);
+        if (rc != BE_OK) return rc;
+        if (ce != cudaSuccess) return cuda_fail(ctx, ce, "svgp graph");
+        if (ce2 != cudaSuccess) return cuda_fail(ctx, ce2, "svgp join");
     }
     // ---- predict_f(X, full_cov=False) at the final parameters (models.py:408), + Y[:, 1] (models.py:411)
     if ((rc = svgp_factor_kuu(ctx, w, Z, kp, M, jitter, info)) != BE_OK) return rc;

@@ -3,8 +3,8 @@
 // by alternating a natural-gradient step on (q_mu, q_sqrt) and an Adam step on the kernel parameters AND the
 // inducing inputs, each on its own minibatch (500 points).  Every matrix here is at most M x M or M x batch
 // (400 x 500): the M x M factorisations run on the blocked DMMA path of be_kernels.cuh (one problem), the
-// rectangular products on a plain shared-memory-tiled FP64 GEMM -- at these sizes a step is launch-bound, not
-// pipe-bound, and the stage is a "next" row of the hot-path table, not the headline.
+// rectangular products on a plain shared-memory-tiled FP64 GEMM -- at these sizes a step is bound by the latency of the
+// single-problem factorisation kernels, not by the FP64 pipe, and the stage is a "next" row, not the headline.
 // The arithmetic follows oracle/svgp.py line by line (GPflow 2.1.5's SVGP with whiten=True, num_data=None).
 #pragma once
 #include <math.h>
@@ -135,12 +135,15 @@ __global__ void k_gemv_t(int m, int n, const double* __restrict__ A, int lda, co
 }
 
 // minibatch gather: Xb [n, D], yb [n], sb [n] from X [N, D], Y [N, 2] (columns: DTW mean, variance; models.py:180)
+// The minibatch is row (2 * *step + half) of idx [2 * n_steps, n]: the step counter lives on the device so that one
+// optimisation step can be captured in a CUDA graph and replayed.
 __global__ void k_svgp_gather(const double* __restrict__ X, const double* __restrict__ Y, const long long* __restrict__ idx,
-                              int n, int D, double* __restrict__ Xb, double* __restrict__ yb, double* __restrict__ sb) {
+                              const int* __restrict__ step, int half, int n, int D, double* __restrict__ Xb,
+                              double* __restrict__ yb, double* __restrict__ sb) {
     const int gid = blockIdx.x * blockDim.x + threadIdx.x;
     if (gid >= n * D) return;
     const int i = gid / D, d = gid % D;
-    const long long src = idx[i];
+    const long long src = idx[(size_t)(2 * *step + half) * n + i];
     Xb[gid] = X[(size_t)src * D + d];
     if (d == 0) {
         yb[i] = Y[(size_t)src * 2];

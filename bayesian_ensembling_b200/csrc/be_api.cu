@@ -162,7 +162,7 @@ int ensure_kernel_attrs(be_ctx* ctx) {
     BE_CUDA(cudaFuncSetAttribute(k_loglik_weights_mvn_tab<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WEIGHT_STAGE_MAX_BYTES + 16384 + 128));
     BE_CUDA(cudaFuncSetAttribute(k_loglik_weights_normal, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WEIGHT_STAGE_MAX_BYTES));
     BE_CUDA(cudaFuncSetAttribute(k_mvn_logprob_vectors, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    BE_CUDA(cudaFuncSetAttribute(k_crps_weights, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WEIGHT_STAGE_MAX_BYTES));
+    BE_CUDA(cudaFuncSetAttribute(k_crps_weights, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WEIGHT_STAGE_MAX_BYTES + 16384));
     BE_CUDA(cudaFuncSetAttribute(k_ksd_weights, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WEIGHT_STAGE_MAX_BYTES));
     BE_CUDA(cudaFuncSetAttribute(k_w2_collapse, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WEIGHT_STAGE_MAX_BYTES));
     BE_CUDA(cudaFuncSetAttribute(k_similarity_pointwise, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WEIGHT_STAGE_MAX_BYTES));

@@ -340,10 +340,11 @@ int be_crps_weights(be_ctx* ctx, const double* loc, const double* scale, const d
     if (Ro <= 0) return -7;
     if (N <= 0) return -8;
     if (!weights) return -9;
-    const int wb = weight_stage_block(M);
-    const size_t wsm = weight_stage_bytes(M);
-    k_crps_weights<<<grid1d((size_t)C * N, wb), wb, wsm, ctx->stream>>>(loc, scale, obs, C, M, Ro, N, weights, crps_mean,
-                                                                       wsm > 0);
+    const int wb = 128;
+    const size_t osm = in_stage_bytes(Ro, wb);
+    const size_t tab_bytes = (size_t)2 * (CRPS_TAB_N + 1) * sizeof(double);  // the (G, E) table ahead of the observations
+    k_crps_weights<<<grid1d((size_t)C * N, wb), wb, tab_bytes + osm, ctx->stream>>>(loc, scale, obs, C, M, Ro, N, weights,
+                                                                                   crps_mean, osm > 0);
     BE_LAUNCHED();
     return BE_OK;
 }
@@ -360,10 +361,10 @@ int be_ksd_weights(be_ctx* ctx, const double* loc, const double* scale, const do
     if (Ro <= 0) return -7;
     if (N <= 0) return -8;
     if (!weights) return -9;
-    const int wb = weight_stage_block(M);
-    const size_t wsm = weight_stage_bytes(M);
-    k_ksd_weights<<<grid1d((size_t)C * N, wb), wb, wsm, ctx->stream>>>(loc, scale, obs, C, M, Ro, N, weights, ksd,
-                                                                      wsm > 0);
+    const int wb = 128;
+    const size_t osm = in_stage_bytes(Ro, wb);
+    k_ksd_weights<<<grid1d((size_t)C * N, wb), wb, osm, ctx->stream>>>(loc, scale, obs, C, M, Ro, N, weights, ksd,
+                                                                      osm > 0);
     BE_LAUNCHED();
     return BE_OK;
 }
@@ -392,10 +393,10 @@ int be_similarity_weights_pointwise(be_ctx* ctx, const double* mean, const doubl
     if (M <= 0) return -5;
     if (N <= 0) return -6;
     if (!weights) return -7;
-    const int wb = weight_stage_block(M);
-    const size_t wsm = weight_stage_bytes(M);
-    k_similarity_pointwise<<<grid1d((size_t)C * N, wb), wb, wsm, ctx->stream>>>(mean, var, C, M, N, weights, w2_out,
-                                                                               wsm > 0);
+    const int wb = 128;
+    const size_t msm = in_stage_bytes(M, wb);
+    k_similarity_pointwise<<<grid1d((size_t)C * N, wb), wb, msm, ctx->stream>>>(mean, var, C, M, N, weights, w2_out,
+                                                                               msm > 0);
     BE_LAUNCHED();
     return BE_OK;
 }

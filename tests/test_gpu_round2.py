@@ -246,3 +246,37 @@ def test_small_t_member_kernels_many_problems_and_non_pd_report(backend):
         mu_o, cov_o = rp.gp_posterior_closed_form(Xo, yo, so, 0.5, 6.0)
         assert rel_err(a.mu[k].cpu().numpy(), mu_o) <= 1e-8
         assert rel_err(a.var_diag[k].cpu().numpy(), np.diag(cov_o)) <= 1e-8
+
+
+def test_crps_kernel_table_step_against_exact_values(backend):
+    """k_crps_weights evaluates z (2 Phi(z) - 1) + 2 phi(z) by a Taylor step from a 513-entry table
+    (weights_next_kernels.cuh).  Swept over |z| from 1e-12 to beyond the table's end -- on the grid points, at the
+    half-way points where the nearest grid point changes, and at random -- against a 50-digit evaluation and
+    against the oracle's erf / exp form (properscoring.crps_gaussian, weights.py:469-471)."""
+    import mpmath as mp
+
+    mp.mp.dps = 50
+    rng = np.random.default_rng(12)
+    k = np.arange(0, 600)
+    z = np.concatenate([k / 64.0, k / 64.0 + 1.0 / 128.0, np.nextafter(k / 64.0 + 1.0 / 128.0, 0.0),
+                        rng.uniform(0.0, 8.5, 3000), 10.0 ** rng.uniform(-12, 0, 500), [8.0, np.nextafter(8.0, 0.0), 37.5, 1e6]])
+    z = np.concatenate([z, -z])
+    N = z.size
+    loc = np.zeros((1, 2, N))
+    scale = np.ones((1, 2, N))
+    _, cm = backend.crps_weights(_t(backend, loc), _t(backend, scale), _t(backend, z[None, None, :]), want_crps=True)
+    got = cm[0, 0].cpu().numpy()
+    assert rel_err(got, rp.crps_gaussian(z, 0.0, 1.0)) < 2e-15
+    worst = 0.0
+    for zi, gi in zip(z[::7], got[::7]):
+        zz = mp.mpf(float(zi))
+        G = zz * mp.erf(zz / mp.sqrt(2)) + mp.sqrt(2 / mp.pi) * mp.exp(-zz * zz / 2)
+        worst = max(worst, float(abs(mp.mpf(float(gi)) - (G - 1 / mp.sqrt(mp.pi))) / G))
+    assert worst < 5e-16, worst  # G to 2.9e-16 (tools/make_crps_table.py --check) and the rounding of the subtraction
+    # infinities and NaN come out as the closed form gives them
+    zs = np.array([np.inf, -np.inf, np.nan, 0.0])
+    _, cm = backend.crps_weights(_t(backend, np.zeros((1, 2, 4))), _t(backend, np.ones((1, 2, 4))),
+                                 _t(backend, zs[None, None, :]), want_crps=True)
+    got = cm[0, 0].cpu().numpy()
+    assert got[0] == np.inf and got[1] == np.inf and np.isnan(got[2])
+    assert abs(got[3] - (np.sqrt(2.0) - 1.0) / np.sqrt(np.pi)) < 1e-16

@@ -404,13 +404,9 @@ int gp_posterior_small(be_ctx* ctx, const double* X, const double* y_mean, const
         // potrf (T^3/3) + triangular inverse (T^3/3); one pass over M and V in global memory (L2-resident)
         NvtxRange nv("be:small:factor_inverse");
         Prof pr(ctx, F_SMALL_A, dB * 2.0 / 3.0 * dT * dT * dT, dB * 1.5 * dT * dT * 8);
-        k_small_factor_inverse<<<B, SM_THREADS, SM_SMEM_BYTES, ctx->stream>>>(Mw, Vw, u, info_fit, n, T);
-        BE_LAUNCHED();
-    }
-    {
-        NvtxRange nv("be:small:mean");
-        Prof pr(ctx, F_MEAN, dB * dT * dT, dB * (0.5 * dT * dT + 4.0 * dT) * 8);
-        k_posterior_mean<<<grid1d((size_t)B * T, 8), 256, 0, ctx->stream>>>(Vw, n, n, T, u, y_mean, y_var, jitter, mu, B);
+        // ... and the posterior mean mu = y - E V u in the kernel's tail (V is L2-hot there)
+        k_small_factor_inverse<<<B, SM_THREADS, SM_SMEM_BYTES, ctx->stream>>>(Mw, Vw, u, info_fit, n, T, y_mean, y_var,
+                                                                            jitter, mu);
         BE_LAUNCHED();
     }
     {

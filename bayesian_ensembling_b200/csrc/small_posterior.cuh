@@ -7,11 +7,12 @@
 // trips) are covered by the other CTA's tensor work:
 //
 //   k_small_factor_inverse :  M = C C^T (left-looking, 32-column block steps)  ->  u = C^-1 y (rides along as row T)
-//                             ->  V = C^-T (upper, row-major)
+//                             ->  V = C^-T (upper, row-major)  ->  the posterior mean mu = y - E V u (kernel tail)
 //   k_small_cov_factor     :  cov = D + E - E (V V^T) E  (lauum + the posterior epilogue of be_kernels.cuh)
 //                             ->  scale_tri = chol(cov) with the rows (1, mu) riding along (data.py:38-39)
 //
-// (the posterior mean between the two is k_posterior_mean, the Matern gram in front is k_matern32<1>: both unchanged).
+// (the Matern gram in front is k_matern32<1>, unchanged; the blocked path's k_posterior_mean pass over V is fused into
+// the first kernel's tail.)
 //
 // Data stays in the per-problem workspace in global memory -- 2 x 512 KB per problem, L2-resident while the CTA works
 // on it (296 CTAs x 1 MB is of the order of the 126 MB L2) -- and every stage is the same device routine: a "tall
@@ -698,12 +699,70 @@ __device__ __forceinline__ void potrf_small(double* Mat, int ld, int nb, int T, 
     }
 }
 
+// mu_i = y_i - E_i sum_{k >= i} V[i, k] u[k]  (V = C^-T upper, rows k-contiguous; E = y_var + jitter).  One warp per row,
+// FOUR rows of a warp in flight at a time (the rows are short -- T - i elements -- so one row at a time is a chain of
+// L2 round trips and five shuffles: ~40 k cycles per CTA).  u is staged in the panel buffer,
+// free at this point: every bulk copy into it was waited for by the product that used it.  Not inlined: the kernel body
+// sits at the 128-register cap.
+__device__ __noinline__ void small_posterior_mean(const double* __restrict__ Vb, int n, int T, const double* __restrict__ u,
+                                                  const double* __restrict__ y_mean, const double* __restrict__ y_var,
+                                                  double jitter, double* __restrict__ mu, double* us) {
+    for (int j = threadIdx.x; j < T; j += SM_THREADS) us[j] = u[j];
+    __syncthreads();
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    constexpr int NW = SM_THREADS / 32;
+    for (int i0 = w; i0 < T; i0 += 4 * NW) {
+        // all sixteen 16-byte loads of the four rows are issued before the first use (T <= 254: at most four chunks of
+        // 64 per row); written as loops over k they would be four dependent L2 round trips per row, one row after another
+        double2 v[4][4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const int i = i0 + r * NW;
+            const double* row = Vb + (size_t)min(i, T - 1) * n;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const int k = (i & ~1) + 2 * lane + 64 * c;  // aligned start; element k < i (if any) is an explicit zero
+                v[r][c] = (i < T && k < T) ? *reinterpret_cast<const double2*>(row + k) : make_double2(0.0, 0.0);
+            }
+        }
+        double sum[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const int i = i0 + r * NW;
+            double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const int k = (i & ~1) + 2 * lane + 64 * c;
+                if (i < T && k < T) {
+                    if (k >= i) s0 += v[r][c].x * us[k];
+                    if (k + 1 < T && k + 1 >= i) s1 += v[r][c].y * us[k + 1];
+                }
+            }
+            sum[r] = s0 + s1;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+            for (int r = 0; r < 4; ++r) sum[r] += __shfl_xor_sync(0xffffffffu, sum[r], o);
+        }
+        if (lane < 4) {
+            const int i = i0 + lane * NW;
+            if (i < T) {
+                const double s = lane == 0 ? sum[0] : lane == 1 ? sum[1] : lane == 2 ? sum[2] : sum[3];
+                mu[i] = y_mean[i] - (y_var[i] + jitter) * s;
+            }
+        }
+    }
+}
+
 // ---- kernel A: M = C C^T, u = C^-1 y (row T), V = C^-T ------------------------------------------------------
 // Mat [B][n][n] holds the lower tiles of M = K + diag(y_var + jitter) with row T = y_mean (k_matern32<1>); on return
 // it holds C (row T zeroed), Vt holds C^-T, u [B][T] the forward-substituted right-hand side.  The triangular
 // inverse's column k - 1 runs in the window of diagonal block k; its last column after the loop.
 __global__ void __launch_bounds__(SM_THREADS, 2)
-    k_small_factor_inverse(double* Mat, double* Vt, double* u, int* info, int n, int T) {
+    k_small_factor_inverse(double* Mat, double* Vt, double* u, int* info, int n, int T,
+                           const double* __restrict__ y_mean, const double* __restrict__ y_var, double jitter,
+                           double* __restrict__ mu) {
     extern __shared__ __align__(16) double small_smem[];
     const SmallSmem sm(small_smem);
     const int b = blockIdx.x, nb = n / SB;
@@ -729,6 +788,14 @@ __global__ void __launch_bounds__(SM_THREADS, 2)
     // in shared memory, which is all that can be asked for: tb >= nb - 2.
     for (int i = max(1, tb); i < nb; ++i) trtri_column(grp_cta(), Vb, Mb, n, i, sm.Inv + (i & 1) * SB * SM_LDD, sm, ph);
     ST_MARK(clk, 15, 2);
+    // ---- posterior mean  mu = y - E (V u): the arithmetic (and its order) of k_posterior_mean, which cost a launch and a
+    // pass over V of its own (0.85 ms = 4.4 % of the cfg4 step).  Here it costs ~0.55 ms of this kernel (r02D/E: its ~60
+    // FP64 additions and products per warp and row group queue behind the other CTA's DMMAs like everything else on
+    // the shared FP64 pipe; an L2 prefetch of V under the last column changed nothing, so it is not the memory).
+    __syncthreads();
+    small_posterior_mean(Vb, n, T, u + (size_t)b * T, y_mean + (size_t)b * T, y_var + (size_t)b * T, jitter,
+                         mu + (size_t)b * T, sm.B);
+    ST_MARK(clk, 15, 3);
 }
 
 // ---- kernel B: cov = D + E - E (V V^T) E, then scale_tri = chol(cov) with (1, mu) riding along ---------------------

@@ -7,8 +7,7 @@ namespace {
 template <int TA, int TB>
 int svgp_gemm(be_ctx* ctx, int m, int n, int k, double alpha, const double* A, int lda, const double* Bm, int ldb, double beta,
               double* C, int ldc) {
-    dim3 grid((n + 63) / 64, (m + 63) / 64);
-    k_dgemm<TA, TB><<<grid, 256, 0, ctx->stream>>>(m, n, k, alpha, A, lda, Bm, ldb, beta, C, ldc);
+    k_dgemm<TA, TB><<<dgemm_grid(m, n), 128, 0, ctx->stream>>>(m, n, k, alpha, A, lda, Bm, ldb, beta, C, ldc);
     BE_LAUNCHED();
     return BE_OK;
 }
@@ -117,7 +116,7 @@ int svgp_iteration(be_ctx* ctx, const SvgpBuffers& w, const double* X, const dou
                                                                      w.sb);
     BE_LAUNCHED();
     if ((rc = svgp_conditional_A(ctx, w, Z, kp, M, n)) != BE_OK) return rc;
-    k_gemv_t<<<grid1d(n, 128), 128, 0, ctx->stream>>>(M, n, w.A, n, w.qmu, w.fmean);  // m = A^T q_mu
+    k_gemv_t<<<grid1d(n, 32), 256, 0, ctx->stream>>>(M, n, w.A, n, w.qmu, w.fmean);  // m = A^T q_mu
     BE_LAUNCHED();
     if ((rc = svgp_gemm<1, 0>(ctx, M, n, M, 1.0, w.SqD, M, w.A, n, 0.0, w.W, n)) != BE_OK) return rc;   // W = Sq^T A
     if ((rc = svgp_gemm<0, 0>(ctx, M, n, M, 1.0, w.SqD, M, w.W, n, 0.0, w.SW, n)) != BE_OK) return rc;  // Sq W
@@ -256,7 +255,7 @@ int be_svgp_fit(be_ctx* ctx, const double* X, const double* Y, int N, int D, int
         k_svgp_gather_rows<<<grid1d((size_t)nc * D, 256), 256, 0, ctx->stream>>>(X, Y, c0, nc, D, w.Xb, w.sb);
         BE_LAUNCHED();
         if ((rc = svgp_conditional_A(ctx, w, Z, kp, M, nc)) != BE_OK) return rc;
-        k_gemv_t<<<grid1d(nc, 128), 128, 0, ctx->stream>>>(M, nc, w.A, nc, w.qmu, mu + c0);
+        k_gemv_t<<<grid1d(nc, 32), 256, 0, ctx->stream>>>(M, nc, w.A, nc, w.qmu, mu + c0);
         BE_LAUNCHED();
         if ((rc = svgp_gemm<1, 0>(ctx, M, nc, M, 1.0, w.SqD, M, w.A, nc, 0.0, w.W, nc)) != BE_OK) return rc;
         k_svgp_predict_var<<<grid1d(nc, 128), 128, 0, ctx->stream>>>(w.A, w.W, variances, w.sb, M, nc, var + c0);

@@ -3,8 +3,9 @@
 // by alternating a natural-gradient step on (q_mu, q_sqrt) and an Adam step on the kernel parameters AND the
 // inducing inputs, each on its own minibatch (500 points).  Every matrix here is at most M x M or M x batch
 // (400 x 500): the M x M factorisations run on the blocked DMMA path of be_kernels.cuh (one problem), the
-// rectangular products on a plain shared-memory-tiled FP64 GEMM -- at these sizes a step is bound by the latency of the
-// single-problem factorisation kernels, not by the FP64 pipe, and the stage is a "next" row, not the headline.
+// rectangular products on a warp-per-tile DMMA GEMM that reads its fragments straight from global memory (k_dgemm) -- at
+// these sizes a step is bound by the latency of the single-problem factorisation kernels, not by the FP64 pipe, and the
+// stage is a "next" row, not the headline.
 // The arithmetic follows oracle/svgp.py line by line (GPflow 2.1.5's SVGP with whiten=True, num_data=None).
 #pragma once
 #include <math.h>
@@ -67,53 +68,71 @@ __global__ void k_svgp_kernel(const double* __restrict__ A, int na, const double
     }
 }
 
-// Plain FP64 GEMM for the rectangular products: C [m, n] = alpha op(A) op(B) + beta C, row-major, 64 x 64 tiles,
-// 256 threads, 4 x 4 outputs per thread.  op(A) [m, k]: A[i * lda + kk] (ta = 0) or A[kk * lda + i] (ta = 1).
+// FP64 GEMM for the rectangular products of the step (every dimension <= ~500, any of the three layouts):
+//   C [m, n] = alpha op(A) op(B) + beta C, row-major;  op(A) [m, k]: A[i * lda + kk] (TA = 0) or A[kk * lda + i] (TA = 1),
+//   op(B) [k, n]: B[kk * ldb + j] (TB = 0) or B[j * ldb + kk] (TB = 1).
+// One WARP per 16 x 32 output tile, DMMA m8n8k4 fragments read straight from global memory (the operands are L2 /
+// L1-resident at these sizes; each 8-byte lane load is one fragment element, so any layout costs the same), four
+// k-steps per register group and the next group's 24 loads in flight under the current group's 32 DMMAs.  No shared
+// memory, no barrier: the first version (64 x 64 shared-memory tiles, 4 x 4 outputs per thread) put 56 CTAs on 148 SMs
+// and took ~140 us per product (1.1 TFLOP/s, 48 % of the step); 400 independent warps are spread over all of them.
+// Sums run over k in order within a lane's accumulator, as DMMA does: deterministic.
 template <int TA, int TB>
-__global__ void __launch_bounds__(256) k_dgemm(int m, int n, int k, double alpha, const double* __restrict__ A, int lda,
+__global__ void __launch_bounds__(128) k_dgemm(int m, int n, int k, double alpha, const double* __restrict__ A, int lda,
                                                const double* __restrict__ Bm, int ldb, double beta, double* __restrict__ C, int ldc) {
-    __shared__ double As[16][65], Bs[16][65];
-    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-    const int i0 = blockIdx.y * 64, j0 = blockIdx.x * 64;
-    double acc[4][4] = {};
-    for (int k0 = 0; k0 < k; k0 += 16) {
-        for (int e = threadIdx.x; e < 16 * 64; e += 256) {
-            int kk, ii;
-            if (TA) { ii = e & 63; kk = e >> 6; } else { kk = e & 15; ii = e >> 4; }
-            const int gi = i0 + ii, gk = k0 + kk;
-            As[kk][ii] = (gi < m && gk < k) ? (TA ? A[(size_t)gk * lda + gi] : A[(size_t)gi * lda + gk]) : 0.0;
-            int kb, jj;
-            if (TB) { kb = e & 15; jj = e >> 4; } else { jj = e & 63; kb = e >> 6; }
-            const int gj = j0 + jj, gkb = k0 + kb;
-            Bs[kb][jj] = (gj < n && gkb < k) ? (TB ? Bm[(size_t)gj * ldb + gkb] : Bm[(size_t)gkb * ldb + gj]) : 0.0;
-        }
-        __syncthreads();
+    const int lane = threadIdx.x & 31, g = lane >> 2, q = lane & 3;
+    const int tiles_n = (n + 31) / 32, tiles_m = (m + 15) / 16;
+    const int wt = blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (wt >= tiles_m * tiles_n) return;
+    const int i0 = (wt / tiles_n) * 16, j0 = (wt % tiles_n) * 32;
+    constexpr int U = 4;  // k-steps (of 4) per register group
+    double acc[2][4][2] = {};
+    double a0[U][2], b0[U][4], a1[U][2], b1[U][4];
+    auto load_group = [&](double (&a)[U][2], double (&b)[U][4], int k0) {
 #pragma unroll
-        for (int kk = 0; kk < 16; ++kk) {
-            double a[4], b[4];
+        for (int u = 0; u < U; ++u) {
+            const int kk = k0 + 4 * u + q;
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                a[u] = As[kk][ty * 4 + u];
-                b[u] = Bs[kk][tx * 4 + u];
+            for (int mi = 0; mi < 2; ++mi) {
+                const int i = i0 + 8 * mi + g;
+                a[u][mi] = (i < m && kk < k) ? (TA ? A[(size_t)kk * lda + i] : A[(size_t)i * lda + kk]) : 0.0;
             }
 #pragma unroll
-            for (int u = 0; u < 4; ++u)
-#pragma unroll
-                for (int v = 0; v < 4; ++v) acc[u][v] = fma(a[u], b[v], acc[u][v]);
+            for (int ni = 0; ni < 4; ++ni) {
+                const int j = j0 + 8 * ni + g;
+                b[u][ni] = (j < n && kk < k) ? (TB ? Bm[(size_t)j * ldb + kk] : Bm[(size_t)kk * ldb + j]) : 0.0;
+            }
         }
-        __syncthreads();
+    };
+    auto mma_group = [&](const double (&a)[U][2], const double (&b)[U][4]) {
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+#pragma unroll
+            for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+                for (int ni = 0; ni < 4; ++ni) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[u][mi], b[u][ni]);
+    };
+    load_group(a0, b0, 0);
+    for (int k0 = 0; k0 < k; k0 += 8 * U) {
+        load_group(a1, b1, k0 + 4 * U);  // out-of-range k loads nothing and contributes zeros
+        mma_group(a0, b0);
+        load_group(a0, b0, k0 + 8 * U);
+        mma_group(a1, b1);
     }
 #pragma unroll
-    for (int u = 0; u < 4; ++u)
+    for (int mi = 0; mi < 2; ++mi)
 #pragma unroll
-        for (int v = 0; v < 4; ++v) {
-            const int gi = i0 + ty * 4 + u, gj = j0 + tx * 4 + v;
-            if (gi < m && gj < n) {
-                double* c = C + (size_t)gi * ldc + gj;
-                *c = beta == 0.0 ? alpha * acc[u][v] : fma(alpha, acc[u][v], beta * *c);
+        for (int ni = 0; ni < 4; ++ni)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int gi = i0 + 8 * mi + g, gj = j0 + 8 * ni + 2 * q + e;
+                if (gi < m && gj < n) {
+                    double* c = C + (size_t)gi * ldc + gj;
+                    *c = beta == 0.0 ? alpha * acc[mi][ni][e] : fma(alpha, acc[mi][ni][e], beta * *c);
+                }
             }
-        }
 }
+inline unsigned dgemm_grid(int m, int n) { return (unsigned)((((m + 15) / 16) * ((n + 31) / 32) + 3) / 4); }
 
 // y [m] = A [m, k] x  (warp per row)
 __global__ void k_gemv_n(int m, int k, const double* __restrict__ A, int lda, const double* __restrict__ x, double* __restrict__ y) {
@@ -125,13 +144,24 @@ __global__ void k_gemv_n(int m, int k, const double* __restrict__ A, int lda, co
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
     if (lane == 0) y[row] = s;
 }
-// y [n] = A^T x, A [m, n]  (thread per column)
-__global__ void k_gemv_t(int m, int n, const double* __restrict__ A, int lda, const double* __restrict__ x, double* __restrict__ y) {
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= n) return;
+// y [n] = A^T x, A [m, n]: 32 columns per CTA, the rows dealt over 8 row groups (a thread per column walking all m rows
+// was a chain of m dependent loads: 89 us at m = 400), partial sums combined in a fixed order.  Launch with 256 threads.
+__global__ void __launch_bounds__(256) k_gemv_t(int m, int n, const double* __restrict__ A, int lda,
+                                                const double* __restrict__ x, double* __restrict__ y) {
+    __shared__ double part[8][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int j = blockIdx.x * 32 + tx;
     double s = 0.0;
-    for (int i = 0; i < m; ++i) s = fma(A[(size_t)i * lda + j], x[i], s);
-    y[j] = s;
+    if (j < n)
+        for (int i = ty; i < m; i += 8) s = fma(A[(size_t)i * lda + j], x[i], s);
+    part[ty][tx] = s;
+    __syncthreads();
+    if (ty == 0 && j < n) {
+        double t = part[0][tx];
+#pragma unroll
+        for (int r = 1; r < 8; ++r) t += part[r][tx];
+        y[j] = t;
+    }
 }
 
 // minibatch gather: Xb [n, D], yb [n], sb [n] from X [N, D], Y [N, 2] (columns: DTW mean, variance; models.py:180)

@@ -611,7 +611,7 @@ def measure_svgp(be, with_cpu, n_steps=10):
            "steps_per_sec": 1e3 / ms_step,
            "note": "be_svgp_fit: natural-gradient step on one minibatch + Adam step (8 kernel parameters and the 400 x 14 "
                    "inducing inputs) on the next; M x M factorisations on the blocked DMMA path, rectangular products on a "
-                   "plain FP64 GEMM; one step is replayed from a CUDA graph and is bound by the latency of ONE-problem factorisation kernels (twelve 128-wide diagonal blocks per step at ~90 us each), not by launches"}
+                   "warp-per-tile DMMA GEMM reading its fragments from global memory; one step is replayed from a CUDA graph and is bound by the latency of ONE-problem factorisation kernels (thirteen 128-wide diagonal blocks per step), not by launches"}
     if with_cpu:
         from oracle import svgp as osvgp  # the CPU leg: the oracle is what is timed here, never the product
 

@@ -152,7 +152,7 @@ int ensure_kernel_attrs(be_ctx* ctx) {
     BE_CUDA(cudaFuncSetAttribute(k_gemm_nt<EpiNatP>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
     BE_CUDA(cudaFuncSetAttribute(k_gemm_nt<EpiLbarT>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
     BE_CUDA(cudaFuncSetAttribute(k_gemm_nt<EpiPhi>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
-    BE_CUDA(cudaFuncSetAttribute(k_gemm_nt<EpiKbarGrad>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
+    BE_CUDA(cudaFuncSetAttribute(k_kbar_grad, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     BE_CUDA(cudaFuncSetAttribute(k_gemm_nt<EpiCov>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
     BE_CUDA(cudaFuncSetAttribute(k_gemm_nt<EpiDB>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
     BE_CUDA(cudaFuncSetAttribute(k_gemm_nt<EpiSym>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
@@ -351,15 +351,16 @@ int vgp_iteration(be_ctx* ctx, const VgpBuffers& w, const double* X, const doubl
         e.out = w.Wt; e.sub = nullptr; e.ld = ld; e.Tp = Tp; e.T = T; e.pad_diag = 0.0; e.mirror = 0;
         if ((rc = launch_gemm(ctx, gemm_args(w.VL, w.M2, Tp, B, SHAPE_UPPER, KLO_TA, KHI_TB, T), e)) != BE_OK) return rc;
     }
-    // g = sum Kbar_u .* dK/dtheta with Kbar_u = VL YT^T
-    const int ctas = nblk * nblk * 2;
-    BE_CUDA(cudaMemsetAsync(w.partial, 0, sizeof(double) * 2 * (size_t)B * ctas, ctx->stream));
+    // g = sum Kbar_u .* dK/dtheta with Kbar_u = VL YT^T  (into Zt: LbarT is no longer needed), reduced by k_kbar_grad
+    const int ctas = nblk * nblk;
     {
-        EpiKbarGrad e;
-        e.X = X; e.variance = variance; e.lengthscale = lengthscale; e.partial = w.partial; e.T = T; e.R = R;
-        e.ctas_per_problem = ctas; e.g0 = 0.0; e.g1 = 0.0;
+        EpiStore e;
+        e.out = w.Zt; e.sub = nullptr; e.ld = ld; e.Tp = Tp; e.T = T; e.pad_diag = 0.0; e.mirror = 0;
         if ((rc = launch_gemm(ctx, gemm_args(w.VL, w.Wt, Tp, B, SHAPE_FULL, KLO_MAX, KHI_END, T), e)) != BE_OK) return rc;
     }
+    k_kbar_grad<<<(unsigned)((size_t)ctas * B), 256, matern_smem(R), ctx->stream>>>(w.Zt, ld, Tp, X, B, T, R, variance,
+                                                                                  lengthscale, w.partial, nblk);
+    BE_LAUNCHED();
     k_vgp_adam<<<grid1d(B, 128), 128, 0, ctx->stream>>>(w.partial, ctas, B, lr, 0.9, 0.999, 1e-7, w.u, w.am, w.av, w.step,
                                                        variance, lengthscale);
     BE_LAUNCHED();

@@ -161,64 +161,108 @@ struct EpiPhi : EpiBase {
     }
 };
 
-// g_theta = sum_{a,b} Kbar_u[a,b] dK[a,b]/dtheta for theta = (variance, lengthscale); per-CTA
-// partial sums go to partial[b][cta][2] and are added in a fixed order by k_vgp_adam.
-struct EpiKbarGrad {
-    const double* X;
-    const double* variance;
-    const double* lengthscale;
-    double* partial;
-    int T, R, ctas_per_problem;
-    double g0, g1;
-    __device__ void operator()(int b, int gr, int gc, double v0, double v1) {
-        if (gr >= T) return;
-        const double ls = lengthscale[b], var = variance[b];
-        const double* xa = X + ((size_t)b * T + gr) * R;
-        double v[2] = {v0, v1};
-#pragma unroll
-        for (int e = 0; e < 2; ++e) {
-            int c = gc + e;
-            if (c >= T) continue;
-            const double* xb = X + ((size_t)b * T + c) * R;
-            double dot = 0.0, sa = 0.0, sb = 0.0;
+// g_theta = sum_{a,b} Kbar_u[a,b] dK[a,b]/dtheta for theta = (variance, lengthscale).  Kbar_u (a plain GEMM result,
+// padded [Tp, ld]) is read once; the Matern terms are recomputed from X exactly as k_matern32 computes the gram
+// (same staging: the tile's rows and columns of X / l k-major in shared memory with their squared norms, 2 x 2 entries
+// at a time, branch-free sqrt_pos / exp_neg).  One CTA per 128 x 128 tile and problem; per-CTA partial sums go to
+// partial[b][tile][2] and are added in a fixed order by k_vgp_adam.
+// Round 1 did this in the EPILOGUE of the GEMM that forms Kbar_u (so that Kbar_u was never stored): there every
+// element divided both points' coordinates by l and called the library sqrt and exp (~600 instructions per element
+// at R = 10) in a kernel that keeps 8 warps per SM -- 36 % of an L2 iteration at T = 251 and 12 % at T = 3012 (ncu launch
+// lists profiles/r02F_vgp_small_launches.md, r02G_vgp_cfg2_launches.md).  Storing Kbar_u costs 16 T^2 bytes of traffic
+// per member and iteration, a fraction of a percent of the iteration.
+__global__ void __launch_bounds__(256, BE_MATERN_CTAS)
+    k_kbar_grad(const double* __restrict__ Kb, int ld, int Tp, const double* __restrict__ X, int B, int T, int R,
+                const double* __restrict__ variance, const double* __restrict__ lengthscale,
+                double* __restrict__ partial, int nt) {
+    extern __shared__ __align__(16) double sm[];
+    double* xi = sm;              // [R][128]  rows of the tile, k-major
+    double* xj = xi + NB * R;     // [R][128]  columns of the tile
+    double* si = xj + NB * R;     // |x_i / l|^2
+    double* sj = si + NB;
+    __shared__ double red[8][2];
+    const int tile = blockIdx.x / B, b = blockIdx.x % B;
+    const int ti = tile / nt, tj = tile % nt;
+    const double ls = lengthscale[b];
+    const double* Xb = X + (size_t)b * T * R;
+    for (int e = threadIdx.x; e < NB * R; e += blockDim.x) {
+        int r = e / R, k = e % R;
+        int gi = ti * NB + r, gj = tj * NB + r;
+        xi[k * NB + r] = gi < T ? Xb[(size_t)gi * R + k] / ls : 0.0;
+        xj[k * NB + r] = gj < T ? Xb[(size_t)gj * R + k] / ls : 0.0;
+    }
+    __syncthreads();
+    {
+        const double* src = threadIdx.x < NB ? xi : xj;
+        const int r = threadIdx.x & (NB - 1);
+        double q = 0.0;
+        for (int k = 0; k < R; ++k) q += src[k * NB + r] * src[k * NB + r];
+        (threadIdx.x < NB ? si : sj)[r] = q;
+    }
+    __syncthreads();
+    const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
+    const double* kb = Kb + (size_t)b * Tp * ld;
+    double g0 = 0.0, g1 = 0.0;
+#pragma unroll 1
+    for (int ip = 0; ip < 4; ++ip) {
+        const int lr = ty * 8 + 2 * ip;
+        const int gi0 = ti * NB + lr;
+        const double2 si2 = *reinterpret_cast<const double2*>(si + lr);
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+            const int lc = 2 * tx + 32 * c;
+            const int gj = tj * NB + lc;
+            if (gi0 >= T || gj >= T) continue;
+            double acc[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
             for (int k = 0; k < R; ++k) {
-                double pa = xa[k] / ls, pb = xb[k] / ls;
-                dot += pa * pb;
-                sa += pa * pa;
-                sb += pb * pb;
+                const double2 a2 = *reinterpret_cast<const double2*>(xi + k * NB + lr);
+                const double2 b2 = *reinterpret_cast<const double2*>(xj + k * NB + lc);
+                acc[0][0] = fma(a2.x, b2.x, acc[0][0]);
+                acc[0][1] = fma(a2.x, b2.y, acc[0][1]);
+                acc[1][0] = fma(a2.y, b2.x, acc[1][0]);
+                acc[1][1] = fma(a2.y, b2.y, acc[1][1]);
             }
-            double r2 = (-2.0 * dot + sa) + sb;
-            double rr = sqrt(fmax(r2, 1e-36));
-            double ex = exp(-SQRT3 * rr);
-            g0 += v[e] * (1.0 + SQRT3 * rr) * ex;
-            if (r2 > 1e-36) g1 += v[e] * (3.0 * var * rr * rr * ex / ls);
-        }
-    }
-    __device__ void finish(int b, int cta, double* red) {
-        __syncthreads();
-        double a0 = g0, a1 = g1;
+            const double2 sj2 = *reinterpret_cast<const double2*>(sj + lc);
+            // the padded buffer has zeros beyond T (EpiStore), so the pair loads need no column guard
+            const double2 k0 = *reinterpret_cast<const double2*>(kb + (size_t)gi0 * ld + gj);
+            const double2 k1 = gi0 + 1 < T ? *reinterpret_cast<const double2*>(kb + (size_t)(gi0 + 1) * ld + gj)
+                                           : make_double2(0.0, 0.0);
+            const double kv[2][2] = {{k0.x, k0.y}, {k1.x, k1.y}};
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            a0 += __shfl_xor_sync(0xffffffffu, a0, o);
-            a1 += __shfl_xor_sync(0xffffffffu, a1, o);
-        }
-        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-        if (lane == 0) {
-            red[2 * warp] = a0;
-            red[2 * warp + 1] = a1;
-        }
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            double s0 = 0, s1 = 0;
-            for (int w = 0; w < GEMM_THREADS / 32; ++w) {
-                s0 += red[2 * w];
-                s1 += red[2 * w + 1];
-            }
-            partial[((size_t)b * ctas_per_problem + cta) * 2] = s0;
-            partial[((size_t)b * ctas_per_problem + cta) * 2 + 1] = s1;
+            for (int i = 0; i < 2; ++i)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    if (gi0 + i >= T || gj + e >= T) continue;
+                    const double r2 = (-2.0 * acc[i][e] + (i ? si2.y : si2.x)) + (e ? sj2.y : sj2.x);
+                    const double x = SQRT3 * sqrt_pos(fmax(r2, 1e-36));
+                    const double ex = x <= 700.0 ? exp_neg(x) : exp(-x);
+                    g0 = fma(kv[i][e], (1.0 + x) * ex, g0);
+                    if (r2 > 1e-36) g1 = fma(kv[i][e], (x * x) * ex, g1);  // x = sqrt3 r: 3 r^2 e^(-sqrt3 r)
+                }
         }
     }
-};
+    g1 *= variance[b] / ls;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        g0 += __shfl_xor_sync(0xffffffffu, g0, o);
+        g1 += __shfl_xor_sync(0xffffffffu, g1, o);
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) {
+        red[warp][0] = g0;
+        red[warp][1] = g1;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s0 = 0.0, s1 = 0.0;
+        for (int w = 0; w < 8; ++w) {
+            s0 += red[w][0];
+            s1 += red[w][1];
+        }
+        partial[((size_t)b * nt * nt + tile) * 2] = s0;
+        partial[((size_t)b * nt * nt + tile) * 2 + 1] = s1;
+    }
+}
 
 // cov = K + AT (S - I) AT^T + D   (predict_f full_cov + models.py:220), lower tiles, mirrored
 struct EpiCov : EpiBase {

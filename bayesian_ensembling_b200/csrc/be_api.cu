@@ -150,8 +150,7 @@ int ensure_kernel_attrs(be_ctx* ctx) {
     BE_CUDA(cudaFuncSetAttribute(k_matern32<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     BE_CUDA(cudaFuncSetAttribute(k_gemm_nt<EpiStore>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
     BE_CUDA(cudaFuncSetAttribute(k_gemm_nt<EpiNatP>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
-    BE_CUDA(cudaFuncSetAttribute(k_gemm_nt<EpiLbarT>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
-    BE_CUDA(cudaFuncSetAttribute(k_gemm_nt<EpiPhi>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
+    BE_CUDA(cudaFuncSetAttribute(k_gemm_nt<EpiPhiGS>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
     BE_CUDA(cudaFuncSetAttribute(k_kbar_grad, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     BE_CUDA(cudaFuncSetAttribute(k_gemm_nt<EpiCov>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
     BE_CUDA(cudaFuncSetAttribute(k_gemm_nt<EpiDB>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
@@ -285,7 +284,7 @@ inline GemmArgs gemm_args(const double* A, const double* Bm, int Tp, int B, int 
 struct VgpBuffers {
     double *Mk, *Ut, *Wt, *P, *M2, *VP, *VL, *S, *Zt;  // [B][Tp][Tp] each
     double *DinvL, *DinvP, *Pbuf;
-    double *n1, *qmu, *r, *zeros;  // [B][T]
+    double *n1, *qmu, *r, *v, *zeros;  // [B][T]
     double *u, *am, *av, *partial;
     int *step, *info_tmp;
 };
@@ -314,7 +313,7 @@ int vgp_iteration(be_ctx* ctx, const VgpBuffers& w, const double* X, const doubl
     // P <- (1-gamma) P + gamma (I + L^T D^-1 L)
     {
         EpiNatP e;
-        e.P = w.P; e.work = w.M2; e.ld = ld; e.Tp = Tp; e.T = T; e.gamma = gamma;
+        e.P = w.P; e.work = w.M2; e.G = train ? w.Zt : nullptr; e.ld = ld; e.Tp = Tp; e.T = T; e.gamma = gamma;
         if ((rc = launch_gemm(ctx, gemm_args(w.Wt, w.Ut, Tp, B, SHAPE_LOWER, KLO_TA, KHI_END, T), e)) != BE_OK) return rc;
     }
     // S = P^-1 (potrf, trtri, lauum), q_mu = S theta_1
@@ -331,17 +330,14 @@ int vgp_iteration(be_ctx* ctx, const VgpBuffers& w, const double* X, const doubl
     // r = D^-1 (y - L q_mu)
     k_rowdot<<<rows_grid, 256, 0, ctx->stream>>>(w.Mk, ld, Tp, T, 1, 2, w.qmu, y_mean, y_var, 0.0, w.r, B);
     BE_LAUNCHED();
-    // LbarT = q_mu r^T - (S L^T) D^-1
+    // v = L^T r;  Phi = tril(v q_mu^T - G S), halved diagonal, G = L^T D^-1 L kept by the natural-gradient half in Zt
+    // (M2 is free again)
+    k_rowdot<<<rows_grid, 256, 0, ctx->stream>>>(w.Ut, ld, Tp, T, 2, 0, w.r, nullptr, nullptr, 0.0, w.v, B);
+    BE_LAUNCHED();
     {
-        EpiLbarT e;
-        e.out = w.Zt; e.q_mu = w.qmu; e.r = w.r; e.y_var = y_var; e.ld = ld; e.Tp = Tp; e.T = T;
-        if ((rc = launch_gemm(ctx, gemm_args(w.S, w.Mk, Tp, B, SHAPE_FULL, KLO_ZERO, KHI_TB, T), e)) != BE_OK) return rc;
-    }
-    // Phi = tril(L^T Lbar), halved diagonal  (M2 is free again)
-    {
-        EpiPhi e;
-        e.out = w.M2; e.ld = ld; e.Tp = Tp; e.T = T;
-        if ((rc = launch_gemm(ctx, gemm_args(w.Ut, w.Zt, Tp, B, SHAPE_LOWER, KLO_TA, KHI_END, T), e)) != BE_OK) return rc;
+        EpiPhiGS e;
+        e.out = w.M2; e.v = w.v; e.q_mu = w.qmu; e.ld = ld; e.Tp = Tp; e.T = T;
+        if ((rc = launch_gemm(ctx, gemm_args(w.Zt, w.S, Tp, B, SHAPE_LOWER, KLO_ZERO, KHI_END, T), e)) != BE_OK) return rc;
     }
     // VL = L^-T
     if ((rc = trtri_padded(ctx, w.VL, w.Mk, Tp, T, B, w.DinvL, w.Pbuf)) != BE_OK) return rc;
@@ -351,7 +347,7 @@ int vgp_iteration(be_ctx* ctx, const VgpBuffers& w, const double* X, const doubl
         e.out = w.Wt; e.sub = nullptr; e.ld = ld; e.Tp = Tp; e.T = T; e.pad_diag = 0.0; e.mirror = 0;
         if ((rc = launch_gemm(ctx, gemm_args(w.VL, w.M2, Tp, B, SHAPE_UPPER, KLO_TA, KHI_TB, T), e)) != BE_OK) return rc;
     }
-    // g = sum Kbar_u .* dK/dtheta with Kbar_u = VL YT^T  (into Zt: LbarT is no longer needed), reduced by k_kbar_grad
+    // g = sum Kbar_u .* dK/dtheta with Kbar_u = VL YT^T  (into Zt: G is no longer needed), reduced by k_kbar_grad
     const int ctas = nblk * nblk;
     {
         EpiStore e;
@@ -1037,7 +1033,7 @@ size_t be_vgp_fit_workspace_bytes(int B, int T, int R) {
     size_t mat = align_up(padded_matrix_doubles(B, T) * 8, 256);
     size_t vec = align_up((size_t)B * T * 8, 256);
     size_t ctas = (size_t)num_blocks((int)Tp) * num_blocks((int)Tp) * 2;
-    return 9 * mat + 2 * align_up(dinv_doubles(B, T) * 8, 256) + align_up(pbuf_doubles(B, T) * 8, 256) + 4 * vec +
+    return 9 * mat + 2 * align_up(dinv_doubles(B, T) * 8, 256) + align_up(pbuf_doubles(B, T) * 8, 256) + 5 * vec +
            3 * align_up((size_t)B * 2 * 8, 256) + align_up((size_t)B * ctas * 2 * 8, 256) +
            2 * align_up((size_t)B * 4, 256) + 4096;
 }
@@ -1076,7 +1072,7 @@ int be_vgp_fit(be_ctx* ctx, const double* X, const double* y_mean, const double*
     w.DinvL = cv.take<double>(dinv_doubles(B, T)); w.DinvP = cv.take<double>(dinv_doubles(B, T));
     w.Pbuf = cv.take<double>(pbuf_doubles(B, T));
     w.n1 = cv.take<double>((size_t)B * T); w.qmu = cv.take<double>((size_t)B * T); w.r = cv.take<double>((size_t)B * T);
-    w.zeros = cv.take<double>((size_t)B * T);
+    w.zeros = cv.take<double>((size_t)B * T); w.v = cv.take<double>((size_t)B * T);
     w.u = cv.take<double>((size_t)B * 2); w.am = cv.take<double>((size_t)B * 2); w.av = cv.take<double>((size_t)B * 2);
     w.partial = cv.take<double>((size_t)B * nblk * nblk * 2 * 2);
     w.step = cv.take<int>(B); w.info_tmp = cv.take<int>(B);

@@ -105,9 +105,13 @@ struct EpiStore : EpiBase {
 
 // natural-gradient step on theta_2 (models.py:209):  P <- (1-gamma) P + gamma (I + L^T D^-1 L),
 // lower tiles; also copied to `work`, the buffer the next factorisation destroys.
+// If G != nullptr the accumulators G = L^T D^-1 L themselves are kept as a full symmetric padded matrix (zero padding)
+// for the Adam half's G S product: written from the positions at or below the diagonal only, with their mirror --
+// (L_ki / s_k) L_kj and (L_kj / s_k) L_ki round differently, so the two triangles of a diagonal tile would race.
 struct EpiNatP : EpiBase {
     double* P;
     double* work;
+    double* G;
     int ld, Tp, T;
     double gamma;
     __device__ void operator()(int b, int gr, int gc, double v0, double v1) {
@@ -122,40 +126,38 @@ struct EpiNatP : EpiBase {
             } else {
                 o[e] = eye;
             }
+            if (G && c <= gr) {
+                const double gval = (gr < T && c < T) ? v[e] : 0.0;
+                double* gb = G + (size_t)b * Tp * ld;
+                gb[(size_t)gr * ld + c] = gval;
+                gb[(size_t)c * ld + gr] = gval;
+            }
         }
         *reinterpret_cast<double2*>(P + off) = make_double2(o[0], o[1]);
         *reinterpret_cast<double2*>(work + off) = make_double2(o[0], o[1]);
     }
 };
 
-// LbarT[b_, i] = q_mu[b_] r[i] - (S L^T)[b_, i] / s[i]        (d ELBO / d L, transposed)
-struct EpiLbarT : EpiBase {
+// Phi = tril(L^T Lbar) with the diagonal halved (Cholesky reverse-mode, Murray 2016), Lbar = r q_mu^T - D^-1 L S
+// (d ELBO / d L).  L^T Lbar = (L^T r) q_mu^T - (L^T D^-1 L) S = v q_mu^T - G S with the G the natural-gradient half
+// formed anyway (EpiNatP): ONE symmetric-by-symmetric product on the lower tiles (T^3 flops) where round 1 formed
+// S L^T (T^3) and then L^T Lbar (T^3 / 3).  The accumulators are (G S)[gr, c].
+struct EpiPhiGS : EpiBase {
     double* out;
-    const double* q_mu;
-    const double* r;
-    const double* y_var;
+    const double* v;     // L^T r  [B, T]
+    const double* q_mu;  // [B, T]
     int ld, Tp, T;
-    __device__ void operator()(int b, int gr, int gc, double v0, double v1) {
-        double v[2] = {v0, v1}, o[2];
+    __device__ void operator()(int b, int gr, int gc, double a0, double a1) {
+        double a[2] = {a0, a1}, o[2];
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
             int c = gc + e;
-            o[e] = (gr < T && c < T) ? q_mu[(size_t)b * T + gr] * r[(size_t)b * T + c] - v[e] / y_var[(size_t)b * T + c] : 0.0;
-        }
-        *reinterpret_cast<double2*>(out + (size_t)b * Tp * ld + (size_t)gr * ld + gc) = make_double2(o[0], o[1]);
-    }
-};
-
-// Phi = tril(L^T Lbar) with the diagonal halved (Cholesky reverse-mode, Murray 2016)
-struct EpiPhi : EpiBase {
-    double* out;
-    int ld, Tp, T;
-    __device__ void operator()(int b, int gr, int gc, double v0, double v1) {
-        double v[2] = {v0, v1}, o[2];
-#pragma unroll
-        for (int e = 0; e < 2; ++e) {
-            int c = gc + e;
-            o[e] = (gr < T && c < T && c <= gr) ? (c == gr ? 0.5 * v[e] : v[e]) : 0.0;
+            if (gr < T && c < T && c <= gr) {
+                const double f = v[(size_t)b * T + gr] * q_mu[(size_t)b * T + c] - a[e];
+                o[e] = c == gr ? 0.5 * f : f;
+            } else {
+                o[e] = 0.0;
+            }
         }
         *reinterpret_cast<double2*>(out + (size_t)b * Tp * ld + (size_t)gr * ld + gc) = make_double2(o[0], o[1]);
     }

@@ -785,9 +785,9 @@ def run_ours(args, cfg):
               "cells_per_sec_at_2000_iterations": 1e3 / (t_it[0] - ms_iter + 2000 * ms_iter),
               "note": "be_vgp_fit on one cell (24 members batched): natural-gradient step + Adam step per iteration, "
                       "CUDA-graph replay; 2000 iterations is what experiments/full_experiment_script.py:87-113 uses"}
-        # algorithmic flops of one iteration per member, on the real T: chol(K) 1/3, L^T D^-1 L 1/3, S = P^-1 (potrf,
-        # trtri, lauum) 1, S L^T 1, tril(L^T Lbar) 1/3, L^-1 1/3, L^-T Phi^T 1/3, Kbar (triangular x triangular, full) 2/3
-        l2_flops = 13.0 / 3.0 * float(cfg.steps) ** 3 * Bm
+        # algorithmic flops of one iteration per member, on the real T: chol(K) 1/3, G = L^T D^-1 L 1/3, S = P^-1 (potrf,
+        # trtri, lauum) 1, tril(G S) 1, L^-1 1/3, L^-T Phi^T 1/3, Kbar (triangular x triangular, full) 2/3  = 4 T^3
+        l2_flops = 4.0 * float(cfg.steps) ** 3 * Bm
         l2["algorithmic_flops_per_iteration"] = l2_flops
         l2["tflops"] = l2_flops / (ms_iter * 1e-3) / 1e12
         l2["frac_of_fp64_tensor_peak"] = l2["tflops"] / FP64_PEAK_TFLOPS

@@ -41,18 +41,22 @@ __device__ __forceinline__ unsigned dtw_row(double ai, const double (&xj)[W], do
         const double diff = __dsub_rn(ai, xj[k]);
         const double d = __dmul_rn(diff, diff);
         const double top = up[k];
-        double m;
+        // Branch-free: under either tie rule the VALUE is min(diag, top, left) (equal candidates are the same double:
+        // the table holds no NaN and no negative zero), only the 2-bit code depends on the rule.  Written with
+        // nested if / else the dtwa.py rule compiled to a divergent branch per cell (BSSY / BRA / BSYNC, both arms
+        // executed whenever the lanes of a warp disagreed); the tslearn rule was already predicated, and its time did
+        // not change (cfg2: 265 ms per 50 iterations before and after, r02K).  Two compare-and-select pairs, not fmin:
+        // sm_100a has no FP64 min instruction, fmin() expands to ~8 instructions with its NaN handling.
+        const bool top_lt_diag = top < diag;
+        const double m1 = top_lt_diag ? top : diag;
+        const bool left_lt_m1 = left < m1;
+        const double m = left_lt_m1 ? left : m1;
         unsigned code;
-        if (TIE == DTW_TIE_TSLEARN) {
-            m = diag; code = 0;
-            if (top < m) { m = top; code = 1; }
-            if (left < m) { m = left; code = 2; }
-        } else {
-            if (diag <= left) {
-                if (diag <= top) { m = diag; code = 0; } else { m = top; code = 1; }
-            } else {
-                if (left <= top) { m = left; code = 2; } else { m = top; code = 1; }
-            }
+        if (TIE == DTW_TIE_TSLEARN) {  // argmin([diag, top, left]), first minimum wins
+            code = left_lt_m1 ? 2u : (top_lt_diag ? 1u : 0u);
+        } else {                       // ensembles/dtwa.py:113-129 (diag <= top is !(top < diag): no NaN in the table)
+            const unsigned c_diag = top_lt_diag ? 1u : 0u, c_left = left <= top ? 2u : 1u;
+            code = diag <= left ? c_diag : c_left;
         }
         const double cur = __dadd_rn(m, d);
         diag = top;
@@ -66,8 +70,13 @@ __device__ __forceinline__ unsigned dtw_row(double ai, const double (&xj)[W], do
 // resident CTAs per SM the DP kernel is compiled for: the kernel is issue-bound, so what matters is that
 // the register budget leaves no spill and that the CTAs of a launch fill the SMs without a long tail
 // (T = 3012: 14 columns x 7 warps -> 94 registers x 224 threads -> 3 CTAs per SM)
+// (W = 14 x 7 warps at 3 CTAs per SM spills nine of the x_j to local memory -- 80 registers; at 2 CTAs per SM nothing
+// spills -- 110 registers -- and the kernel measured 2 % faster at cfg2, equal at cfg3 / cfg4: r02K.  3 stays.)
+#ifndef BE_DTW_CTAS_W14
+#define BE_DTW_CTAS_W14 3
+#endif
 __host__ __device__ constexpr int dtw_min_ctas(int W, int NWARPS) {
-    return NWARPS == 1 ? 4 : (NWARPS == 7 || W <= 8) ? 3 : 2;
+    return NWARPS == 1 ? 4 : NWARPS == 7 ? BE_DTW_CTAS_W14 : W <= 8 ? 3 : 2;
 }
 
 // (A barrier-free variant was tried for the multi-warp form: neighbouring warps decoupled through a 64-row

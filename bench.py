@@ -791,6 +791,28 @@ def run_ours(args, cfg):
         l2["algorithmic_flops_per_iteration"] = l2_flops
         l2["tflops"] = l2_flops / (ms_iter * 1e-3) / 1e12
         l2["frac_of_fp64_tensor_peak"] = l2["tflops"] / FP64_PEAK_TFLOPS
+        # the same loop at the small-T shape (cfg4 members, T = 251: the size of the reference's own per-member fits)
+        cfg_s = synthetic.CONFIGS["cfg4"]
+        rs, _ = synthetic.make_cells(cfg_s, n_cells=16)
+        rs_dev = torch.as_tensor(rs, device=be.device)
+        Xs, yms, yvs = be.gpdtw1d_inputs(rs_dev.reshape(-1, cfg_s.realisations, cfg_s.steps))
+        be.vgp_fit(Xs, yms, yvs, 1, want_scale_tri=False)
+        torch.cuda.synchronize()
+        ts_it, n_small = [], 10
+        for n_it in (1, 1 + n_small):
+            f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            f0.record()
+            be.vgp_fit(Xs, yms, yvs, n_it, want_scale_tri=False)
+            f1.record()
+            torch.cuda.synchronize()
+            ts_it.append(f0.elapsed_time(f1))
+        ms_small = (ts_it[1] - ts_it[0]) / n_small
+        nm = int(Xs.shape[0])
+        l2["small_t"] = {"members": nm, "time_steps": cfg_s.steps, "ms_per_iteration": ms_small,
+                         "member_iterations_per_sec": nm / ms_small * 1e3,
+                         "tflops": 4.0 * float(cfg_s.steps) ** 3 * nm / (ms_small * 1e-3) / 1e12,
+                         "note": "640 cfg4 members batched; the loop runs on the blocked path at every T (DESIGN 10 item 4)"}
+        del rs_dev, Xs, yms, yvs
         if rank == 0 and world == 1 and not args.no_cpu_baseline:
             # the same iteration in the oracle (NumPy/SciPy, all host BLAS threads): ONE member, (fit with one
             # iteration) - (fit with none), scaled to the cell's members

@@ -281,6 +281,12 @@ inline GemmArgs gemm_args(const double* A, const double* Bm, int Tp, int B, int 
     return g;
 }
 
+// The L2 loop's padded dimension: at the small-T sizes it is the small-T kernels' (a multiple of 32), so that the two
+// factor-and-invert steps of an iteration can run in k_small_factor_inverse (small_posterior.cuh); every other kernel
+// of the loop takes the padded dimension as an argument.
+inline bool small_path(int T);
+inline int vgp_pad(int T) { return small_path(T) ? small_dim(T) : pad_dim(T); }
+
 struct VgpBuffers {
     double *Mk, *Ut, *Wt, *P, *M2, *VP, *VL, *S, *Zt;  // [B][Tp][Tp] each
     double *DinvL, *DinvP, *Pbuf;
@@ -293,7 +299,8 @@ struct VgpBuffers {
 int vgp_iteration(be_ctx* ctx, const VgpBuffers& w, const double* X, const double* y_mean, const double* y_var,
                   double* variance, double* lengthscale, double jitter, double gamma, double lr, int train, int B, int T,
                   int R, int* info_fit) {
-    const int Tp = pad_dim(T), ld = Tp, nblk = num_blocks(Tp);
+    const int Tp = vgp_pad(T), ld = Tp, nblk = num_blocks(Tp);
+    const bool small = small_path(T);
     const int ntl = nblk * (nblk + 1) / 2;
     const int nt32 = (Tp + 31) / 32;
     const unsigned rows_grid = grid1d((size_t)B * T, 8);
@@ -303,7 +310,16 @@ int vgp_iteration(be_ctx* ctx, const VgpBuffers& w, const double* X, const doubl
                                                                                    w.zeros, w.zeros, jitter, w.Mk, Tp,
                                                                                    ld, ntl);
     BE_LAUNCHED();
-    if ((rc = potrf_padded(ctx, w.Mk, Tp, T, B, w.DinvL, w.Pbuf, w.VL, info_fit)) != BE_OK) return rc;
+    if (small) {
+        // L = chol(K + jitter I) AND VL = L^-T in one per-problem kernel (its right-hand-side row is zero here and its
+        // posterior-mean tail writes scratch); the lower 32-blocks of VL inside the 128-tiles were zeroed once, before
+        // the loop, and nothing writes them
+        k_small_factor_inverse<<<B, SM_THREADS, SM_SMEM_BYTES, ctx->stream>>>(w.Mk, w.VL, w.r, info_fit, Tp, T, w.zeros,
+                                                                            w.zeros, 0.0, w.v);
+        BE_LAUNCHED();
+    } else if ((rc = potrf_padded(ctx, w.Mk, Tp, T, B, w.DinvL, w.Pbuf, w.VL, info_fit)) != BE_OK) {
+        return rc;
+    }
     // Ut = L^T, Wt = L^T D^-1
     k_transpose<<<(unsigned)((size_t)nt32 * nt32 * B), 256, 0, ctx->stream>>>(w.Mk, ld, Tp, T, 1, w.Ut, w.Wt, y_var, B);
     BE_LAUNCHED();
@@ -317,8 +333,14 @@ int vgp_iteration(be_ctx* ctx, const VgpBuffers& w, const double* X, const doubl
         if ((rc = launch_gemm(ctx, gemm_args(w.Wt, w.Ut, Tp, B, SHAPE_LOWER, KLO_TA, KHI_END, T), e)) != BE_OK) return rc;
     }
     // S = P^-1 (potrf, trtri, lauum), q_mu = S theta_1
-    if ((rc = potrf_padded(ctx, w.M2, Tp, T, B, w.DinvP, w.Pbuf, w.VP, w.info_tmp)) != BE_OK) return rc;
-    if ((rc = trtri_padded(ctx, w.VP, w.M2, Tp, T, B, w.DinvP, w.Pbuf)) != BE_OK) return rc;
+    if (small) {
+        k_small_factor_inverse<<<B, SM_THREADS, SM_SMEM_BYTES, ctx->stream>>>(w.M2, w.VP, w.r, w.info_tmp, Tp, T, w.zeros,
+                                                                            w.zeros, 0.0, w.v);
+        BE_LAUNCHED();
+    } else {
+        if ((rc = potrf_padded(ctx, w.M2, Tp, T, B, w.DinvP, w.Pbuf, w.VP, w.info_tmp)) != BE_OK) return rc;
+        if ((rc = trtri_padded(ctx, w.VP, w.M2, Tp, T, B, w.DinvP, w.Pbuf)) != BE_OK) return rc;
+    }
     {
         EpiStore e;
         e.out = w.S; e.sub = nullptr; e.ld = ld; e.Tp = Tp; e.T = T; e.pad_diag = 1.0; e.mirror = 1;
@@ -339,8 +361,8 @@ int vgp_iteration(be_ctx* ctx, const VgpBuffers& w, const double* X, const doubl
         e.out = w.M2; e.v = w.v; e.q_mu = w.qmu; e.ld = ld; e.Tp = Tp; e.T = T;
         if ((rc = launch_gemm(ctx, gemm_args(w.Zt, w.S, Tp, B, SHAPE_LOWER, KLO_ZERO, KHI_END, T), e)) != BE_OK) return rc;
     }
-    // VL = L^-T
-    if ((rc = trtri_padded(ctx, w.VL, w.Mk, Tp, T, B, w.DinvL, w.Pbuf)) != BE_OK) return rc;
+    // VL = L^-T  (the small-T kernel formed it with L)
+    if (!small && (rc = trtri_padded(ctx, w.VL, w.Mk, Tp, T, B, w.DinvL, w.Pbuf)) != BE_OK) return rc;
     // YT = VL Phi^T  (block upper), into Wt
     {
         EpiStore e;
@@ -1029,11 +1051,12 @@ int be_barycentre_1d_finish(be_ctx* ctx, const double* partial, int C, int N, do
 
 size_t be_vgp_fit_workspace_bytes(int B, int T, int R) {
     (void)R;
-    size_t Tp = pad_dim(T);
-    size_t mat = align_up(padded_matrix_doubles(B, T) * 8, 256);
+    size_t Tp = vgp_pad(T);
+    size_t mat = align_up((size_t)B * Tp * Tp * 8, 256);
     size_t vec = align_up((size_t)B * T * 8, 256);
     size_t ctas = (size_t)num_blocks((int)Tp) * num_blocks((int)Tp) * 2;
-    return 9 * mat + 2 * align_up(dinv_doubles(B, T) * 8, 256) + align_up(pbuf_doubles(B, T) * 8, 256) + 5 * vec +
+    size_t dinv = align_up((size_t)B * num_blocks((int)Tp) * NB * NB * 8, 256), pbuf = align_up((size_t)B * Tp * NB * 8, 256);
+    return 9 * mat + 2 * dinv + pbuf + 5 * vec +
            3 * align_up((size_t)B * 2 * 8, 256) + align_up((size_t)B * ctas * 2 * 8, 256) +
            2 * align_up((size_t)B * 4, 256) + 4096;
 }
@@ -1062,15 +1085,16 @@ int be_vgp_fit(be_ctx* ctx, const double* X, const double* y_mean, const double*
     if (!info_fit) return -20;
     if (!info_dist) return -21;
     if (!workspace || workspace_bytes < be_vgp_fit_workspace_bytes(B, T, R)) return BE_ERR_WORKSPACE;
-    const int Tp = pad_dim(T), ld = Tp, nblk = num_blocks(Tp);
-    const size_t nm = padded_matrix_doubles(B, T);
+    const int Tp = vgp_pad(T), ld = Tp, nblk = num_blocks(Tp);
+    const size_t nm = (size_t)B * Tp * Tp;
+    const size_t n_dinv = (size_t)B * nblk * NB * NB, n_pbuf = (size_t)B * Tp * NB;
     Carver cv(workspace, workspace_bytes);
     VgpBuffers w;
     w.Mk = cv.take<double>(nm); w.Ut = cv.take<double>(nm); w.Wt = cv.take<double>(nm); w.P = cv.take<double>(nm);
     w.M2 = cv.take<double>(nm); w.VP = cv.take<double>(nm); w.VL = cv.take<double>(nm); w.S = cv.take<double>(nm);
     w.Zt = cv.take<double>(nm);
-    w.DinvL = cv.take<double>(dinv_doubles(B, T)); w.DinvP = cv.take<double>(dinv_doubles(B, T));
-    w.Pbuf = cv.take<double>(pbuf_doubles(B, T));
+    w.DinvL = cv.take<double>(n_dinv); w.DinvP = cv.take<double>(n_dinv);
+    w.Pbuf = cv.take<double>(n_pbuf);
     w.n1 = cv.take<double>((size_t)B * T); w.qmu = cv.take<double>((size_t)B * T); w.r = cv.take<double>((size_t)B * T);
     w.zeros = cv.take<double>((size_t)B * T); w.v = cv.take<double>((size_t)B * T);
     w.u = cv.take<double>((size_t)B * 2); w.am = cv.take<double>((size_t)B * 2); w.av = cv.take<double>((size_t)B * 2);
@@ -1088,6 +1112,12 @@ int be_vgp_fit(be_ctx* ctx, const double* X, const double* y_mean, const double*
     BE_CUDA(cudaMemsetAsync(w.am, 0, sizeof(double) * B * 2, user_stream));
     BE_CUDA(cudaMemsetAsync(w.av, 0, sizeof(double) * B * 2, user_stream));
     BE_CUDA(cudaMemsetAsync(w.step, 0, sizeof(int) * B, user_stream));
+    if (small_path(T)) {
+        // k_small_factor_inverse writes the 32-blocks of V on and above the diagonal only; the tile products read whole
+        // 128-tiles, so the blocks below it have to be zero (once: nothing else writes them inside the loop)
+        BE_CUDA(cudaMemsetAsync(w.VL, 0, sizeof(double) * nm, user_stream));
+        BE_CUDA(cudaMemsetAsync(w.VP, 0, sizeof(double) * nm, user_stream));
+    }
     k_set_identity<<<ctx->sm_count * 8, 256, 0, user_stream>>>(w.P, ld, Tp, B);  // q_sqrt = I
     BE_LAUNCHED();
     k_set_identity<<<ctx->sm_count * 8, 256, 0, user_stream>>>(w.S, ld, Tp, B);

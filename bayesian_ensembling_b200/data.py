@@ -1,6 +1,8 @@
-"""Host-side mirror of the reference's data containers (ensembles/data.py), restricted to what
-the fit -> weight -> barycentre path uses.  Same names, argument meaning and error behaviour;
-plotting, anomaly/climatology and pickling are out of scope.
+"""Host-side containers with the reference's public names (ensembles/data.py: ``Distribution``, ``ProcessModel``,
+``ModelCollection``), restricted to what the fit -> weight -> barycentre path touches.  Attribute names, argument
+meaning and error behaviour follow the reference so that its call sites run unchanged; the bodies are this package's
+own (forwarding properties are generated, iteration is one shared cursor, fitting is batched).  Plotting,
+anomaly / climatology handling and pickling are out of scope.
 """
 from __future__ import annotations
 
@@ -14,26 +16,50 @@ from . import dists
 from .labelled import DataArray, as_labelled
 
 
+def _forwarded(call: tp.Callable[[tp.Any], tp.Any], doc: str) -> property:
+    """A read-only property that forwards to the wrapped labelled array (or list of models)."""
+    return property(call, doc=doc)
+
+
+class _Cursor:
+    """The reference's containers are their own iterators: ``__iter__`` returns the object and ``__next__`` walks an
+    ``idx`` attribute that is rewound when the walk runs off the end (data.py:337-352, 369-383) -- so a ``break``
+    leaves the cursor where it stopped.  Subclasses provide ``_at(i)`` raising ``IndexError`` past the end."""
+
+    idx: int
+
+    def __iter__(self):
+        return self
+
+    def __next__(self):
+        try:
+            item = self._at(self.idx)
+        except IndexError:
+            self.idx = 0
+            raise StopIteration from None
+        self.idx += 1
+        return item
+
+
 @dataclass
 class Distribution:
-    """ensembles/data.py:18-56,133-143.  ``dist_type(mu, covariance)`` is called POSITIONALLY
-    (data.py:38-39), so the meaning of ``covariance`` depends on ``dist_type`` (quirk Q-SCALE)."""
+    """ensembles/data.py:18-56,133-143.  ``dist_type(mu, covariance)`` is called POSITIONALLY (data.py:38-39), so what
+    ``covariance`` means depends on ``dist_type`` (quirk Q-SCALE: a ``Normal`` takes it as the scale).  A batched fit
+    hands over the distribution it already holds on the GPU through ``_prebuilt``."""
 
     mu: np.ndarray
     covariance: np.ndarray
     dim_array: DataArray
     dist_type: tp.Any
-    _prebuilt: tp.Any = None  # a distribution already resident on the GPU (batched fits)
+    _prebuilt: tp.Any = None
 
     def __post_init__(self):
-        self._dist = self._prebuilt if self._prebuilt is not None else self.dist_type(self.mu, self.covariance)
+        self._dist = self.dist_type(self.mu, self.covariance) if self._prebuilt is None else self._prebuilt
 
     def reshape(self, vals, name=False):
-        reshaped_vals = np.asarray(vals).reshape(self.dim_array.shape)
-        reshaped_array = self.dim_array.copy(data=reshaped_vals)
-        if name:
-            reshaped_array = reshaped_array.rename(name)
-        return reshaped_array
+        """Flat values -> a labelled array with the coordinates of ``dim_array`` (data.py:41-56)."""
+        labelled = self.dim_array.copy(data=np.asarray(vals).reshape(self.dim_array.shape))
+        return labelled.rename(name) if name else labelled
 
     @property
     def mean(self):
@@ -44,13 +70,13 @@ class Distribution:
         return self.reshape(self._dist.variance(), name="Distribution variance")
 
     def sample(self):
-        samples = np.asarray(self._dist.sample(seed=np.random.randint(0, 110000)))
-        return self.reshape(samples, name="Distribution sample")
+        draw = self._dist.sample(seed=np.random.randint(0, 110000))  # the reference's seed range (data.py:141)
+        return self.reshape(np.asarray(draw), name="Distribution sample")
 
 
 @dataclass
-class ProcessModel:
-    """ensembles/data.py:146-352 (data handling only)."""
+class ProcessModel(_Cursor):
+    """ensembles/data.py:146-352, data handling only: one climate model's realisations ``[realisation, time, ...]``."""
 
     model_data: DataArray
     model_name: str
@@ -62,39 +88,19 @@ class ProcessModel:
             self.model_data = as_labelled(self.model_data)
         except TypeError:
             raise AssertionError("Input must be xr.DataArray")
-        self.model_mean = self.model_data.mean()
-        self.model_std = self.model_data.std()
+        data = self.model_data
+        assert data.dims[0] == "realisation"
+        assert np.any(~np.isnan(data.values)), "Input data must not contain NaN"
+        self.model_mean, self.model_std = data.mean(), data.std()
         self.climatology = None
-        assert self.model_data.dims[0] == "realisation"
-        assert np.any(~np.isnan(self.model_data.values)), "Input data must not contain NaN"
 
-    @property
-    def max_val(self):
-        return self.model_data.max()
-
-    @property
-    def min_val(self):
-        return self.model_data.min()
-
-    @property
-    def n_realisations(self) -> int:
-        return self.model_data.realisation.size
-
-    @property
-    def time(self):
-        return self.model_data.time
-
-    @property
-    def mean_across_realisations(self):
-        return self.model_data.mean("realisation")
-
-    @property
-    def std_across_realisations(self):
-        return self.model_data.std("realisation")
-
-    @property
-    def ndim(self):
-        return self.model_data.ndim
+    max_val = _forwarded(lambda self: self.model_data.max(), "largest value over all realisations")
+    min_val = _forwarded(lambda self: self.model_data.min(), "smallest value over all realisations")
+    time = _forwarded(lambda self: self.model_data.time, "the time coordinate")
+    ndim = _forwarded(lambda self: self.model_data.ndim, "number of dimensions, the realisation axis included")
+    n_realisations = _forwarded(lambda self: self.model_data.realisation.size, "number of realisations")
+    mean_across_realisations = _forwarded(lambda self: self.model_data.mean("realisation"), "mean over realisations")
+    std_across_realisations = _forwarded(lambda self: self.model_data.std("realisation"), "std over realisations")
 
     @property
     def distribution(self) -> Distribution:
@@ -107,22 +113,13 @@ class ProcessModel:
     def __len__(self) -> int:
         return self.n_realisations
 
-    def __iter__(self):
-        return self
-
-    def __next__(self):
-        try:
-            out = self.model_data.isel(realisation=self.idx)
-            self.idx += 1
-        except IndexError:
-            self.idx = 0
-            raise StopIteration
-        return out
+    def _at(self, i):
+        return self.model_data.isel(realisation=i)
 
 
 @dataclass
-class ModelCollection:
-    """ensembles/data.py:355-562 (data handling + ``fit``)."""
+class ModelCollection(_Cursor):
+    """ensembles/data.py:355-562: the ensemble's models, with ``fit`` and the time-axis check."""
 
     models: tp.List[ProcessModel]
     idx: int = 0
@@ -130,60 +127,8 @@ class ModelCollection:
     def __post_init__(self):
         self.check_time_axes()
 
-    def __iter__(self):
-        return self
-
-    def __next__(self):
-        try:
-            out = self.models[self.idx]
-            self.idx += 1
-        except IndexError:
-            self.idx = 0
-            raise StopIteration
-        return out
-
-    def fit(self, model, **kwargs):
-        """ensembles/data.py:385-395.  The reference loops members serially; when the
-        statistical model offers ``fit_batch`` (GPDTW1D does) all members of equal shape are
-        fitted in ONE batched device call -- same results, one launch sequence."""
-        for process_model in self.models:
-            if process_model.distribution != None:  # noqa: E711  (as the reference)
-                warnings.warn("Removing the model's previously learnt distribution")
-        if hasattr(model, "fit_batch"):
-            dists_ = model.fit_batch(self.models, **kwargs)
-            for process_model, dist in zip(self.models, dists_):
-                process_model.distribution = dist
-            return
-        for process_model in self.models:
-            dist = model.fit(process_model, **kwargs)
-            process_model.distribution = dist
-
-    def save(self, path: str):
-        """ensembles/data.py:397-404, as a library-independent ``.npz`` instead of a pickle of
-        xarray / distrax objects; reload with ``utils.load_model_collection(path)``."""
-        from .checkpoint import save_model_collection
-
-        save_model_collection(self, path)
-
-    @property
-    def time(self):
-        return self.models[0].time
-
-    @property
-    def max_val(self):
-        return np.max([model.max_val.values for model in self.models])
-
-    @property
-    def min_val(self):
-        return np.min([model.min_val.values for model in self.models])
-
-    @property
-    def number_of_models(self):
-        return len(self.models)
-
-    @property
-    def model_names(self):
-        return [model.model_name for model in self.models]
+    def _at(self, i):
+        return self.models[i]
 
     def __len__(self):
         return len(self.models)
@@ -191,25 +136,48 @@ class ModelCollection:
     def __getitem__(self, item):
         return self.models[item]
 
+    time = _forwarded(lambda self: self.models[0].time, "the first model's time coordinate")
+    number_of_models = _forwarded(lambda self: len(self.models), "number of models")
+    model_names = _forwarded(lambda self: [m.model_name for m in self.models], "the models' names, in order")
+    max_val = _forwarded(lambda self: np.max([m.max_val.values for m in self.models]), "largest value of any model")
+    min_val = _forwarded(lambda self: np.min([m.min_val.values for m in self.models]), "smallest value of any model")
+
     def distributions(self) -> tp.Dict[str, Distribution]:
-        return {model.model_name: model.distribution for model in self.models}
+        return {m.model_name: m.distribution for m in self.models}
+
+    def fit(self, model, **kwargs):
+        """ensembles/data.py:385-395.  The reference fits the members one after the other; a statistical model that
+        offers ``fit_batch`` (GPDTW1D does) gets all members at once and fits those of equal shape in ONE batched
+        device call -- same results, one launch sequence."""
+        for m in self.models:
+            if m.distribution != None:  # noqa: E711  (the reference's comparison)
+                warnings.warn("Removing the model's previously learnt distribution")
+        if hasattr(model, "fit_batch"):
+            fitted = model.fit_batch(self.models, **kwargs)
+        else:
+            fitted = [model.fit(m, **kwargs) for m in self.models]
+        for m, dist in zip(self.models, fitted):
+            m.distribution = dist
+
+    def save(self, path: str):
+        """ensembles/data.py:397-404, as a library-independent ``.npz`` instead of a pickle of xarray / distrax
+        objects; reload with ``utils.load_model_collection(path)``."""
+        from .checkpoint import save_model_collection
+
+        save_model_collection(self, path)
 
     def check_time_axes(self):
-        """ensembles/data.py:542-562."""
-        time_axes_match = True
-        for model1 in self.models:
-            for model2 in self.models:
-                t1, t2 = model1.model_data.time.values, model2.model_data.time.values
-                if t1.shape != t2.shape or np.any(t1 != t2):
-                    time_axes_match = False
-        if time_axes_match == False:  # noqa: E712
-            warnings.warn(
-                "Time axes of models don't match: applying naive fix. Check models are collocated correctly in time!"
-            )
-            new_time = self.time
-            for model in self:
-                model.model_data["time"] = new_time
-        return
+        """ensembles/data.py:542-562: if any two models' time coordinates differ, warn and give every model the first
+        model's axis (the reference's "naive fix")."""
+        axes = [m.model_data.time.values for m in self.models]
+        first = axes[0]
+        if all(t.shape == first.shape and not np.any(t != first) for t in axes[1:]):
+            return
+        warnings.warn(
+            "Time axes of models don't match: applying naive fix. Check models are collocated correctly in time!")
+        shared = self.time
+        for m in self.models:
+            m.model_data["time"] = shared
 
 
 # the distrax names the reference passes as ``dist_type``

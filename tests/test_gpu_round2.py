@@ -280,3 +280,32 @@ def test_crps_kernel_table_step_against_exact_values(backend):
     got = cm[0, 0].cpu().numpy()
     assert got[0] == np.inf and got[1] == np.inf and np.isnan(got[2])
     assert abs(got[3] - (np.sqrt(2.0) - 1.0) / np.sqrt(np.pi)) < 1e-16
+
+
+def test_fit_batch_in_two_halves_equals_one_batch(backend):
+    """GPDTW1D.fit_batch fits a group whose covariances exceed 256 MB in two halves (the first half's device-to-host
+    copy runs under the second half's kernels).  Every member's host mean / covariance must be bit-identical to the
+    one-batch device result, in the order of the collection."""
+    import torch
+
+    import bayesian_ensembling_b200 as es
+    from bayesian_ensembling_b200.labelled import DataArray
+
+    M, R, T = 8, 3, 2100  # 8 x 2100^2 x 8 B = 282 MB: the two-halves path
+    reals, _ = _cell(M, R, T, 2, seed=77)
+    tcoord = np.arange(T)
+    pms = [es.ProcessModel(DataArray(reals[m], ("realisation", "time"), {"realisation": np.arange(R), "time": tcoord}),
+                           f"model{m}") for m in range(M)]
+    mc = es.ModelCollection(pms)
+    mc.fit(es.GPDTW1D(hyperparameters=(0.5, 6.0), y_mean="mean"), progress_bar=False)
+    X, ym, yv = backend.gpdtw1d_inputs(_t(backend, reals))
+    var = torch.full((M,), 0.5, dtype=torch.float64, device=backend.device)
+    ls = torch.full((M,), 6.0, dtype=torch.float64, device=backend.device)
+    ref = backend.gp_posterior(X, ym, yv, var, ls)
+    assert int(ref.info_fit.abs().sum()) == 0
+    mu_ref, cov_ref = ref.mu.cpu().numpy(), ref.cov.cpu().numpy()
+    for m in range(M):
+        d = mc[m].distribution
+        assert np.array_equal(np.asarray(d.mu), mu_ref[m]), m
+        assert np.array_equal(np.asarray(d.covariance), cov_ref[m]), m
+        assert np.array_equal(d.mean.values, mu_ref[m])

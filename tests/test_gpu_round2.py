@@ -309,3 +309,21 @@ def test_fit_batch_in_two_halves_equals_one_batch(backend):
         assert np.array_equal(np.asarray(d.mu), mu_ref[m]), m
         assert np.array_equal(np.asarray(d.covariance), cov_ref[m]), m
         assert np.array_equal(d.mean.values, mu_ref[m])
+
+
+@pytest.mark.parametrize("T", [61, 165, 251])
+def test_l2_loop_small_t_factor_kernel_vs_blocked_path(backend, monkeypatch, T):
+    """At T <= 254 the two factor-and-invert steps of an L2 iteration run in k_small_factor_inverse and the loop's
+    padded dimension is the small-T kernels' (a multiple of 32); BE_NO_SMALL_T sends the same call through the blocked
+    path (padded to a multiple of 16).  Same trained hyper-parameters and posterior to rounding."""
+    reals, _ = _cell(3, 4, T, 2, seed=300 + T)
+    X, ym, yv = backend.gpdtw1d_inputs(_t(backend, reals))
+    post_a, var_a, ls_a = backend.vgp_fit(X, ym, yv, 8)
+    monkeypatch.setenv("BE_NO_SMALL_T", "1")
+    post_b, var_b, ls_b = backend.vgp_fit(X, ym, yv, 8)
+    monkeypatch.delenv("BE_NO_SMALL_T")
+    assert int(post_a.info_fit.abs().sum()) == 0 and int(post_b.info_fit.abs().sum()) == 0
+    assert rel_err(var_a.cpu().numpy(), var_b.cpu().numpy()) < 1e-10
+    assert rel_err(ls_a.cpu().numpy(), ls_b.cpu().numpy()) < 1e-10
+    assert rel_err(post_a.mu.cpu().numpy(), post_b.mu.cpu().numpy()) < 1e-9
+    assert rel_err(post_a.cov.cpu().numpy(), post_b.cov.cpu().numpy()) < 1e-9

@@ -51,8 +51,8 @@ constexpr int SM_DIAG_WARPS = BE_SMALL_DIAG_WARPS;
 constexpr int SM_DIAG_THREADS = 32 * SM_DIAG_WARPS;
 constexpr int SM_PROD_THREADS = SM_THREADS - SM_DIAG_THREADS;
 constexpr int SM_LDT = 20;              // scratch tile of the recursive-doubling inverse (== 4 mod 16)
-constexpr int SM_SMEM_DOUBLES = SB * SM_LDB + 3 * SB * SM_LDD + SB + 16 * SM_LDT + 2;  // + two mbarriers
-constexpr int SM_SMEM_BYTES = SM_SMEM_DOUBLES * 8;  // 100 864 B: two CTAs per SM
+constexpr int SM_SMEM_DOUBLES = SB * SM_LDB + 3 * SB * SM_LDD + SB + 16 * SM_LDT + 2 + SM_MAX_DIM;  // + two mbarriers + yv
+constexpr int SM_SMEM_BYTES = SM_SMEM_DOUBLES * 8;  // 102 912 B: two CTAs per SM
 
 __host__ __device__ inline int small_dim(int T) { return ((T + 2 + SB - 1) / SB) * SB; }
 
@@ -95,10 +95,12 @@ struct SmallSmem {
     double* rd;   // [32]          1 / diag
     double* Tmp;  // [16][SM_LDT]  scratch of the inverse
     unsigned long long* bars;  // [2] mbarriers of the panel loads: whole CTA, product group
+    double* yv;   // [256]         the problem's y_var (kernel B's epilogue reads it per element)
     __device__ explicit SmallSmem(double* base)
         : B(base), D(base + SB * SM_LDB), Inv(base + SB * SM_LDB + SB * SM_LDD), rd(base + SB * SM_LDB + 3 * SB * SM_LDD),
           Tmp(base + SB * SM_LDB + 3 * SB * SM_LDD + SB),
-          bars(reinterpret_cast<unsigned long long*>(base + SB * SM_LDB + 3 * SB * SM_LDD + SB + 16 * SM_LDT)) {}
+          bars(reinterpret_cast<unsigned long long*>(base + SB * SM_LDB + 3 * SB * SM_LDD + SB + 16 * SM_LDT)),
+          yv(base + SB * SM_LDB + 3 * SB * SM_LDD + SB + 16 * SM_LDT + 2) {}
 };
 
 // Phase parities of the two panel mbarriers, kept per thread (every thread that waits on a barrier flips its copy).
@@ -150,6 +152,17 @@ __device__ __forceinline__ void sub_store(const SubAcc& a, double* tile, int ld)
         for (int ni = 0; ni < 4; ++ni)
             *reinterpret_cast<double2*>(tile + (size_t)(8 * mi + g) * ld + 8 * ni + 2 * q) =
                 make_double2(a.v[mi][ni][0], a.v[mi][ni][1]);
+}
+
+// Asks for the 16 rows x 32 doubles at p (one 128-byte line per lane) without holding registers.  The products of
+// these kernels are bound per warp -- a window lasts as long as its slowest warp -- and every 16 x 32 item begins with
+// the L2 round trip of its first A fragments and (updates) ends with that of the tile it updates: prefetched into the
+// L1 before the product, the latter leaves the warp's critical path (+1.3 % of the cfg4 step, r02Z).  Prefetching the
+// NEXT item's leading A rows as well, the late update's tile and the scale phase's next tile measured 1.2 % slower
+// than the update tile alone (r02a2): those stay plain loads.
+__device__ __forceinline__ void prefetch_rows16(const double* p, int ld) {
+    const int lane = threadIdx.x & 31;
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(p + (size_t)(lane >> 1) * ld + ((lane & 1) << 4)));
 }
 
 // acc += sum_{k in [k0, k1)} A[r, k] * B[c, k]   (r < 16, c < 32; k0, k1 multiples of 8)
@@ -525,8 +538,11 @@ __device__ __forceinline__ void update_early(const Grp& g, double* Mat, int ld, 
     for (int r = first_owned(2 * kn, g.w, g.nw); r < 2 * nb; r += g.nw) {
         SubAcc acc, c;
         sub_zero(acc);
-        sub_gemm(acc, Mat + (size_t)16 * r * ld, ld, sm.B, 0, 0, kend);
         double* tile = Mat + (size_t)16 * r * ld + SB * kn;
+        // the tile being updated is needed after the product: asked for now (loading it into registers BEFORE the
+        // product cost 100 bytes of spills and 2 %: r02Y)
+        prefetch_rows16(tile, ld);
+        sub_gemm(acc, Mat + (size_t)16 * r * ld, ld, sm.B, 0, 0, kend);
         sub_load(c, tile, ld);
 #pragma unroll
         for (int mi = 0; mi < 2; ++mi)
@@ -809,7 +825,11 @@ __global__ void __launch_bounds__(SM_THREADS, 2)
     const int b = blockIdx.x, nb = n / SB;
     const double* Vb = Vt + (size_t)b * n * n;
     double* Wb = Work + (size_t)b * n * n;
-    const CovEpilogue ep{y_var + (size_t)b * T, mu + (size_t)b * T, var_diag + (size_t)b * T,
+    // the epilogue of every 16 x 32 item reads y_var of its 2 rows and 8 column pairs: from shared memory, not as
+    // global loads whose latency sits at the end of each item of each warp (a window lasts as long as its slowest
+    // warp): 8.74 -> 8.35 ms per 10 240 problems (r02X)
+    for (int j = threadIdx.x; j < T; j += SM_THREADS) sm.yv[j] = y_var[(size_t)b * T + j];
+    const CovEpilogue ep{sm.yv, mu + (size_t)b * T, var_diag + (size_t)b * T,
                          cov_dense ? cov_dense + (size_t)b * T * T : nullptr, jitter, T};
     PhaseClock clk(1);
     PanelPhase ph;

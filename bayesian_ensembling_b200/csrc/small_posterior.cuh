@@ -175,7 +175,8 @@ __device__ __forceinline__ void sub_gemm(SubAcc& acc, const double* A, int lda, 
     const double* a1p = a0p + (size_t)8 * lda;
     const double* bp = sB + g * SM_LDB + 2 * q - kB0;
     // A fragments run PF k-groups ahead of the DMMAs that consume them (L2 latency is ~800 cycles, a k-group is 16
-    // DMMAs = 256 cycles of this sub-partition's FP64 pipe: two groups ahead left the pipe waiting, ncu r02e)
+    // DMMAs = 256 cycles of this sub-partition's FP64 pipe: two groups ahead left the pipe waiting, ncu r02e; three,
+    // five and six groups ahead measured 0.8 / 1.6 / 2.3 % slower than four on the cfg4 step, r02g2)
     constexpr int PF = 4;
     double2 ra[PF][2];
 #pragma unroll
